@@ -1,0 +1,87 @@
+"""ctypes binding of libsct_b200.so (the C ABI declared in include/sct_b200.h).
+
+PyTorch is only the owner of device memory and streams here: every call passes raw device pointers
+(`tensor.data_ptr()`) and the current CUDA stream handle.  There is no fallback of any kind: if the
+library is missing or the device is not sm_100, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = Path(os.environ.get("SCT_B200_LIB", _PKG / "libsct_b200.so"))
+
+_p = C.c_void_p
+_i64 = C.c_int64
+_i32 = C.c_int32
+_u64 = C.c_uint64
+_f = C.c_float
+
+# name -> argtypes, mirrors include/sct_b200.h one to one
+SIGNATURES = {
+    "sct_embed_ln_pe_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _f, _f, _u64, _u64, _p],
+    "sct_embed_ln_pe_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _f, _f, _u64, _u64, _p],
+    "sct_add_dropout_ln_fwd": [_p, _p, _f, _p, _p, _p, _p, _p, _p, _i64, _i64, _f, _u64, _u64, _p],
+    "sct_add_dropout_ln_bwd": [_p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _i64, _i64, _f, _u64, _u64, _p],
+    "sct_ln_act_fwd": [_p, _p, _p, _p, _p, _i64, _i64, _f, _u64, _u64, _p],
+    "sct_ln_act_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _f, _u64, _u64, _p],
+    "sct_gelu_dropout_fwd": [_p, _p, _i64, _f, _u64, _u64, _p],
+    "sct_gelu_dropout_bwd": [_p, _p, _p, _i64, _f, _u64, _u64, _p],
+    "sct_colsum_bf16": [_p, _i64, _p, _i64, _i64, _f, _p],
+    "sct_cast_scale": [_p, _p, _p, _i64, _i64, _i64, _i64, _f, _p],
+    "sct_seq_mean_fwd": [_p, _p, _p, _i64, _i64, _i64, _p],
+    "sct_seq_mean_bwd": [_p, _p, _p, _i64, _i64, _i64, _p],
+    "sct_gemm_bf16_nt": [_p, _i64, _p, _i64, _p, _i64, _p, _f, _i64, _i64, _i64, _i32, _p],
+    "sct_gemm_bf16_nn": [_p, _i64, _p, _i64, _p, _i64, _p, _f, _i64, _i64, _i64, _i32, _p],
+    "sct_gemm_bf16_tn": [_p, _i64, _p, _i64, _p, _i64, _f, _i64, _i64, _i64, _i32, _p],
+    "sct_attn_fwd": [_p, _i64, _p, _p, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _f, _f,
+                     _u64, _u64, _p],
+    "sct_attn_bwd": [_p, _i64, _p, _p, _i64, _p, _p, _i64, _p, _p, _p, _i64, _p, _p, _i64, _p, _i64, _i64,
+                     _i64, _i64, _i64, _i32, _f, _f, _u64, _u64, _p],
+    "sct_ce_rows": [_p, _p, _p, _p, _i64, _i64, _i64, _f, _i32, _p],
+    "sct_small_linear_fwd": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p],
+    "sct_small_linear_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p],
+    "sct_gan_loss_fwd": [_p, _i64, _p, _p, _p],
+    "sct_gan_loss_bwd": [_p, _i64, _p, _p, _p, _p, _p],
+}
+NOARG = {"sct_version": _i32, "sct_device_check": _i32, "sct_debug_timeouts": _i32, "sct_last_error": C.c_char_p}
+
+_lib = None
+
+
+def exported_symbols() -> list[str]:
+    return sorted(list(SIGNATURES) + list(NOARG))
+
+
+def load() -> C.CDLL:
+    """Loads the library (once).  Raises if it has not been built — there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -m sct_gan_b200.build` "
+            "(or __graft_entry__.build()); sct_gan_b200 has no CPU or PyTorch fallback")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = _i32
+    for name, res in NOARG.items():
+        fn = getattr(lib, name)
+        fn.argtypes = []
+        fn.restype = res
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().sct_last_error().decode("utf-8", "replace")
+
+
+def call(name: str, *args) -> None:
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed (rc={rc}): {last_error()}")

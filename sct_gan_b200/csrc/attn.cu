@@ -1,0 +1,753 @@
+// sct_b200 — K3: fused multi-head attention (forward + backward) on tcgen05 / TMEM, head_dim = 96.
+//
+// Replaces F.scaled_dot_product_attention / the bmm+softmax+dropout+bmm path of nn.MultiheadAttention
+// for every attention site of the reference (SCT-GAN/model.py:56-77 encoder/decoder layers, :209-222
+// ast_attention / cross_attention, :241-246 disc_path_attention; torch nn/functional.py:6244-6691):
+// softmax(q k^T / sqrt(dh) + key_padding(-inf) + causal(-inf)) -> dropout -> @ v, never materialising
+// the [B,H,Lq,Lk] probabilities.  The averaged attention weights the reference returns from its
+// top-level MHAs are discarded by every caller (model.py:433,443,1186), so they are not produced.
+//
+// Data layout: Q/K/V/O and their gradients stay in the projection GEMMs' row-major layouts
+// ([B*L, ld] with head h in columns [96h, 96h+96)); tiles are fetched by 3-D TMA ([B, L, cols] so rows
+// past L zero-fill) as three [rows x 32 col] blocks with the 64-byte swizzle.  The same smem tile is
+// consumed K-major (rows = M/N, e.g. Q and K in S = Q K^T) or MN-major (rows = K, e.g. V in O = P V)
+// purely by choice of UMMA descriptor, so nothing is ever transposed.
+//
+// TMEM accumulator rows map 1:1 to threads (tcgen05.ld 32x32b), so the online softmax needs no
+// cross-thread reduction.  Masks are applied from the [B,Lk] key-padding bytes and the causal
+// predicate; dropout is regenerated from (seed, offset, element index).
+#include <math.h>
+
+#include "../../include/sct_b200.h"
+#include "common.cuh"
+
+namespace sct {
+namespace {
+
+constexpr int DH = 96;            // head dim
+constexpr int TILE = 128;         // q-tile and kv-tile rows
+constexpr int BLK = TILE * 64;    // bytes of one [128 x 32 bf16] swizzle-64 column block
+constexpr int QKV_BYTES = 3 * BLK;          // one [128 x 96] operand tile
+constexpr int P_BYTES = 2 * TILE * 128;     // one [128 x 128] bf16 tile as 2 swizzle-128 blocks
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct AttnParams {
+  int B, H, Lq, Lk;
+  int ldo;               // O / dO row pitch (elements)
+  int ldq_out, ldkv_out; // pitches of dQ and dK/dV outputs
+  int causal;
+  float scale_log2;      // scale * log2(e)
+  float scale;
+  const uint8_t* kpm;    // [B, Lk], 1 = ignore key; nullable
+  float* lse2;           // [B, H, Lq]  log2-domain logsumexp of the scaled scores
+  float* dvec;           // [B, H, Lq]  D = rowsum(dO * O)
+  __nv_bfloat16* o;      // forward output
+  __nv_bfloat16 *dq, *dk, *dv;
+  uint64_t seed, offset;
+  uint32_t thresh16;
+  float inv_keep;
+};
+
+__device__ __forceinline__ float drop_mult(const AttnParams& p, uint64_t idx) {
+  if (p.thresh16 == 0) return 1.f;
+  const uint32_t h = rng_pair(p.seed, p.offset, idx);
+  return ((h & 0xFFFFu) >= p.thresh16) ? p.inv_keep : 0.f;
+}
+
+// K-major descriptor of a swizzle-64 operand tile ([rows x 96], 3 blocks), k16 step `k` (0..5).
+__device__ __forceinline__ uint64_t desc_k64(uint32_t tile, int k) {
+  return umma_smem_desc(tile + (k >> 1) * BLK + (k & 1) * 32, 16, 512, UMMA_SW64);
+}
+// MN-major descriptor of the same tile (rows = contraction index), k16 step `k` (0..7): N = 96 spans the
+// three column blocks (LBO = BLK), 8-row groups are 512 B apart (SBO), 16 rows per step = 1024 B.
+__device__ __forceinline__ uint64_t desc_mn64(uint32_t tile, int k) {
+  return umma_smem_desc(tile + k * 1024, BLK, 512, UMMA_SW64);
+}
+// K-major descriptor of a [128 x 128] bf16 swizzle-128 tile (P / dS), k16 step `k` (0..7).
+__device__ __forceinline__ uint64_t desc_k128(uint32_t tile, int k) {
+  return umma_smem_desc(tile + (k >> 2) * (TILE * 128) + (k & 3) * 32, 16, 1024, UMMA_SW128);
+}
+// MN-major descriptor of the same [128(k) x 128(mn)] tile (used for dQ-style products if ever needed).
+
+// write 32 consecutive bf16 (columns c0..c0+31, c0 % 32 == 0) of row r into a swizzle-128 [128x128] tile
+__device__ __forceinline__ void store_row32_sw128(uint32_t tile, int r, int c0, const float (&v)[32]) {
+  const uint32_t rowbase = tile + (c0 >> 6) * (TILE * 128) + r * 128;
+  const int chunk0 = (c0 & 63) >> 3;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t dst = rowbase + ((((chunk0 + q) ^ (r & 7)) & 7) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
+                 "r"(pack_bf16(v[8 * q], v[8 * q + 1])), "r"(pack_bf16(v[8 * q + 2], v[8 * q + 3])),
+                 "r"(pack_bf16(v[8 * q + 4], v[8 * q + 5])), "r"(pack_bf16(v[8 * q + 6], v[8 * q + 7]))
+                 : "memory");
+  }
+}
+
+__device__ __forceinline__ void load_tile(const CUtensorMap* m, uint32_t bar, uint32_t dst, int col0,
+                                          int row0, int b) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) tma_load_3d(m, bar, dst + c * BLK, col0 + 32 * c, row0, b);
+}
+
+// =================================================================================================
+// forward: one CTA (128 threads) per (q-tile, head, batch); two CTAs co-reside per SM so one CTA's
+// softmax overlaps the other's MMAs.
+// =================================================================================================
+constexpr int FWD_SMEM = 1024 + 3 * QKV_BYTES + P_BYTES + 1024;
+
+__global__ void __launch_bounds__(128, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sQ = base, sK = sQ + QKV_BYTES, sV = sK + QKV_BYTES, sP = sV + QKV_BYTES;
+  const uint32_t aux = sP + P_BYTES;
+  float* bias_s = reinterpret_cast<float*>(gen + (aux - base));  // 128 floats
+  const uint32_t bar_q = aux + 512, bar_k = aux + 520, bar_v = aux + 528, bar_mma = aux + 536;
+  const uint32_t tmem_ptr_addr = aux + 544;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen + (tmem_ptr_addr - base));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nq_tiles = gridDim.x;
+  const int qt = nq_tiles - 1 - blockIdx.x;  // heavy (late) causal tiles first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qt * TILE;
+  int nkv = (p.Lk + TILE - 1) / TILE;
+  if (p.causal) nkv = min(nkv, qt + 1);
+
+  if (tid == 0) {
+    mbar_init(bar_q, 1);
+    mbar_init(bar_k, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr_addr, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_gen;
+  const uint32_t tS = tmem, tO = tmem + 128;
+  const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
+
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+  constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, false, true);
+
+  if (tid == 0) {
+    mbar_expect_tx(bar_q, QKV_BYTES);
+    load_tile(&tmQ, bar_q, sQ, h * DH, q0, b);
+    mbar_expect_tx(bar_k, QKV_BYTES);
+    load_tile(&tmK, bar_k, sK, h * DH, 0, b);
+    mbar_expect_tx(bar_v, QKV_BYTES);
+    load_tile(&tmV, bar_v, sV, h * DH, 0, b);
+    mbar_wait(bar_q, 0);
+    mbar_wait(bar_k, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < 6; ++k) tc_mma_bf16(tS, desc_k64(sQ, k), desc_k64(sK, k), idesc_s, k > 0);
+    tc_commit(bar_mma);
+  }
+
+  const int r = tid;           // local q row
+  const int q = q0 + r;
+  float m_run = -INFINITY, l_run = 0.f;
+  const uint64_t drop_row = ((uint64_t)(b * p.H + h) * p.Lq + (uint64_t)q) * (uint64_t)p.Lk;
+
+  for (int j = 0; j < nkv; ++j) {
+    const int kv0 = j * TILE;
+    {
+      const int kv = kv0 + tid;
+      bool masked = kv >= p.Lk;
+      if (!masked && p.kpm) masked = p.kpm[(long long)b * p.Lk + kv] != 0;
+      bias_s[tid] = masked ? -INFINITY : 0.f;
+    }
+    __syncthreads();
+    mbar_wait(bar_mma, j & 1);  // S_j ready; P V_{j-1} retired
+    tc_fence_after();
+    if (tid == 0) {
+      if (j + 1 < nkv) {
+        mbar_expect_tx(bar_k, QKV_BYTES);
+        load_tile(&tmK, bar_k, sK, h * DH, kv0 + TILE, b);
+      }
+      if (j > 0) {
+        mbar_expect_tx(bar_v, QKV_BYTES);
+        load_tile(&tmV, bar_v, sV, h * DH, kv0, b);
+      }
+    }
+    const bool diag = p.causal && (j == qt);
+    // pass 1: row max
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t rr[32];
+      tmem_ld32(tS + lane_sel + c * 32, rr);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float t = __uint_as_float(rr[i]) * p.scale_log2 + bias_s[c * 32 + i];
+        if (diag && (c * 32 + i > r)) t = -INFINITY;
+        mx = fmaxf(mx, t);
+      }
+    }
+    const float m_new = fmaxf(m_run, mx);
+    const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+    const float alpha = exp2f(m_run - m_use);
+    // pass 2: probabilities -> bf16 P tile in smem (dropout applied to the stored copy only)
+    float rs = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t rr[32];
+      tmem_ld32(tS + lane_sel + c * 32, rr);
+      tmem_ld_wait();
+      float pv[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float t = __uint_as_float(rr[i]) * p.scale_log2 + bias_s[c * 32 + i];
+        if (diag && (c * 32 + i > r)) t = -INFINITY;
+        const float e = exp2f(t - m_use);
+        rs += e;
+        pv[i] = e * drop_mult(p, drop_row + (uint64_t)(kv0 + c * 32 + i));
+      }
+      store_row32_sw128(sP, r, c * 32, pv);
+    }
+    l_run = l_run * alpha + rs;
+    m_run = m_new;
+    // rescale the running output when any row of this warp moved its max
+    if (j > 0 && !__all_sync(0xffffffffu, alpha == 1.0f)) {
+#pragma unroll 1
+      for (int c = 0; c < 3; ++c) {
+        uint32_t rr[32];
+        tmem_ld32(tO + lane_sel + c * 32, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) * alpha);
+        tmem_st32(tO + lane_sel + c * 32, rr);
+      }
+      tmem_st_wait();
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      mbar_wait(bar_v, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        tc_mma_bf16(tO, desc_k128(sP, k), desc_mn64(sV, k), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+      if (j + 1 < nkv) {
+        mbar_wait(bar_k, (j + 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 6; ++k) tc_mma_bf16(tS, desc_k64(sQ, k), desc_k64(sK, k), idesc_s, k > 0);
+      }
+      tc_commit(bar_mma);
+    }
+  }
+  mbar_wait(bar_mma, nkv & 1);
+  tc_fence_after();
+  {
+    const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
+    const bool valid = q < p.Lq;
+    __nv_bfloat16* dst = p.o + ((long long)b * p.Lq + q) * p.ldo + h * DH;
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+      uint32_t rr[32];
+      tmem_ld32(tO + lane_sel + c * 32, rr);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(rr[8 * qd]) * inv_l, __uint_as_float(rr[8 * qd + 1]) * inv_l);
+          u.y = pack_bf16(__uint_as_float(rr[8 * qd + 2]) * inv_l, __uint_as_float(rr[8 * qd + 3]) * inv_l);
+          u.z = pack_bf16(__uint_as_float(rr[8 * qd + 4]) * inv_l, __uint_as_float(rr[8 * qd + 5]) * inv_l);
+          u.w = pack_bf16(__uint_as_float(rr[8 * qd + 6]) * inv_l, __uint_as_float(rr[8 * qd + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + c * 32 + qd * 8) = u;
+        }
+      }
+    }
+    if (valid && p.lse2)
+      p.lse2[((long long)b * p.H + h) * p.Lq + q] = l_run > 0.f ? (m_run + log2f(l_run)) : INFINITY;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// =================================================================================================
+// backward preprocess: D[b,h,q] = sum_c dO[b,q,h,c] * O[b,q,h,c]
+// =================================================================================================
+__global__ void __launch_bounds__(256)
+attn_bwd_dvec_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+                     float* __restrict__ dvec, int rows, int Lq, int H, int ldo) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int b = row / Lq, q = row % Lq;
+  // lane covers 24 consecutive elements of the 768-wide row; 4 lanes = one head (dh = 96)
+  const __nv_bfloat16* po = o + (long long)row * ldo + lane * 24;
+  const __nv_bfloat16* pg = d_o + (long long)row * ldo + lane * 24;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const uint4 a = *reinterpret_cast<const uint4*>(po + i * 8);
+    const uint4 g = *reinterpret_cast<const uint4*>(pg + i * 8);
+    const uint32_t aa[4] = {a.x, a.y, a.z, a.w}, gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 x = unpack_bf16(aa[k]), y = unpack_bf16(gg[k]);
+      s += x.x * y.x + x.y * y.y;
+    }
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  if ((lane & 3) == 0) {
+    const int h = lane >> 2;
+    if (h < H) dvec[((long long)b * H + h) * Lq + q] = s;
+  }
+}
+
+// =================================================================================================
+// backward, dK/dV: one CTA (256 threads) per (kv-tile, head, batch), streaming q-tiles.
+//   S^T = K Q^T, dP^T = V dO^T (TMEM, rows = kv) -> P^T, dS^T (bf16, smem) -> dV += P^T dO, dK += dS^T Q
+// =================================================================================================
+constexpr int BWD_KV_SMEM = 1024 + 2 * QKV_BYTES + 4 * QKV_BYTES + 2 * P_BYTES + 2048 + 256;
+
+__global__ void __launch_bounds__(256, 1)
+attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                     const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sK = base, sV = sK + QKV_BYTES;
+  const uint32_t sQ0 = sV + QKV_BYTES;             // stage s: sQ0 + s*2*QKV_BYTES, dO right after Q
+  const uint32_t sPT = sQ0 + 4 * QKV_BYTES, sDST = sPT + P_BYTES;
+  const uint32_t aux = sDST + P_BYTES;
+  float* lse_s = reinterpret_cast<float*>(gen + (aux - base));   // [2][128]
+  float* dv_s = lse_s + 256;                                      // [2][128]
+  const uint32_t bar_kv = aux + 2048, bar_qdo0 = aux + 2056 /* +8 for stage 1 */, bar_mma = aux + 2072;
+  const uint32_t tmem_ptr_addr = aux + 2080;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen + (tmem_ptr_addr - base));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int jt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int kv0 = jt * TILE;
+  const int nq_tiles = (p.Lq + TILE - 1) / TILE;
+  const int i_begin = p.causal ? jt : 0;
+  const int n_it = nq_tiles - i_begin;
+
+  if (tid == 0) {
+    mbar_init(bar_kv, 1);
+    mbar_init(bar_qdo0, 1);
+    mbar_init(bar_qdo0 + 8, 1);
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr_addr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_gen;
+  const uint32_t tST = tmem, tDPT = tmem + 128, tDV = tmem + 256, tDK = tmem + 352;
+  const int quad = warp & 3, half = warp >> 2;
+  const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+  const int r = quad * 32 + lane;  // local kv row
+  const int kv = kv0 + r;
+  bool row_valid = kv < p.Lk;
+  if (row_valid && p.kpm) row_valid = p.kpm[(long long)b * p.Lk + kv] == 0;
+
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+  constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, false, true);
+
+  if (tid == 0 && n_it > 0) {
+    mbar_expect_tx(bar_kv, 2 * QKV_BYTES);
+    load_tile(&tmK, bar_kv, sK, h * DH, kv0, b);
+    load_tile(&tmV, bar_kv, sV, h * DH, kv0, b);
+    mbar_expect_tx(bar_qdo0, 2 * QKV_BYTES);
+    load_tile(&tmQ, bar_qdo0, sQ0, h * DH, i_begin * TILE, b);
+    load_tile(&tmdO, bar_qdo0, sQ0 + QKV_BYTES, h * DH, i_begin * TILE, b);
+  }
+
+  for (int it = 0; it < n_it; ++it) {
+    const int s = it & 1;
+    const int qi = i_begin + it;
+    const int q0 = qi * TILE;
+    const uint32_t sQ = sQ0 + s * 2 * QKV_BYTES, sdO = sQ + QKV_BYTES;
+    if (tid == 0) {
+      if (it == 0) mbar_wait(bar_kv, 0);
+      mbar_wait(bar_qdo0 + 8 * s, (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 6; ++k) tc_mma_bf16(tST, desc_k64(sK, k), desc_k64(sQ, k), idesc_s, k > 0);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) tc_mma_bf16(tDPT, desc_k64(sV, k), desc_k64(sdO, k), idesc_s, k > 0);
+      tc_commit(bar_mma);
+    }
+    {
+      // per-q statistics of this tile (columns of S^T)
+      const int c = tid & 127;
+      const int qq = q0 + c;
+      const long long o = ((long long)b * p.H + h) * p.Lq + qq;
+      if (tid < 128) lse_s[s * 128 + c] = qq < p.Lq ? p.lse2[o] : INFINITY;
+      else dv_s[s * 128 + c] = qq < p.Lq ? p.dvec[o] : 0.f;
+    }
+    __syncthreads();
+    mbar_wait(bar_mma, it & 1);
+    tc_fence_after();
+    if (tid == 0 && it + 1 < n_it) {
+      const uint32_t nb = bar_qdo0 + 8 * (s ^ 1);
+      const uint32_t nQ = sQ0 + (s ^ 1) * 2 * QKV_BYTES;
+      mbar_expect_tx(nb, 2 * QKV_BYTES);
+      load_tile(&tmQ, nb, nQ, h * DH, q0 + TILE, b);
+      load_tile(&tmdO, nb, nQ + QKV_BYTES, h * DH, q0 + TILE, b);
+    }
+    const bool diag = p.causal && (qi == jt);
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c0 = half * 64 + cc * 32;
+      uint32_t rs[32], rp[32];
+      tmem_ld32(tST + lane_sel + c0, rs);
+      tmem_ld32(tDPT + lane_sel + c0, rp);
+      tmem_ld_wait();
+      float pd[32], ds[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int c = c0 + i;
+        float pr = 0.f;
+        if (row_valid && !(diag && r > c))
+          pr = exp2f(__uint_as_float(rs[i]) * p.scale_log2 - lse_s[s * 128 + c]);
+        const float dm = drop_mult(
+            p, (((uint64_t)(b * p.H + h) * p.Lq + (uint64_t)(q0 + c)) * (uint64_t)p.Lk) + (uint64_t)kv);
+        pd[i] = pr * dm;
+        ds[i] = pr * (__uint_as_float(rp[i]) * dm - dv_s[s * 128 + c]);
+      }
+      store_row32_sw128(sPT, r, c0, pd);
+      store_row32_sw128(sDST, r, c0, ds);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        tc_mma_bf16(tDV, desc_k128(sPT, k), desc_mn64(sdO, k), idesc_g, (it > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        tc_mma_bf16(tDK, desc_k128(sDST, k), desc_mn64(sQ, k), idesc_g, (it > 0 || k > 0) ? 1u : 0u);
+      if (it + 1 == n_it) tc_commit(bar_mma);
+    }
+  }
+  if (n_it > 0) {
+    mbar_wait(bar_mma, n_it & 1);
+    tc_fence_after();
+  }
+  {
+    // half 0 drains dV, half 1 drains dK (scaled)
+    const uint32_t src = half == 0 ? tDV : tDK;
+    const float sc = half == 0 ? 1.0f : p.scale;
+    __nv_bfloat16* dst = (half == 0 ? p.dv : p.dk) + ((long long)b * p.Lk + kv) * p.ldkv_out + h * DH;
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+      uint32_t rr[32];
+      if (n_it > 0) {
+        tmem_ld32(src + lane_sel + c * 32, rr);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rr[i] = 0u;
+      }
+      if (kv < p.Lk) {
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(rr[8 * qd]) * sc, __uint_as_float(rr[8 * qd + 1]) * sc);
+          u.y = pack_bf16(__uint_as_float(rr[8 * qd + 2]) * sc, __uint_as_float(rr[8 * qd + 3]) * sc);
+          u.z = pack_bf16(__uint_as_float(rr[8 * qd + 4]) * sc, __uint_as_float(rr[8 * qd + 5]) * sc);
+          u.w = pack_bf16(__uint_as_float(rr[8 * qd + 6]) * sc, __uint_as_float(rr[8 * qd + 7]) * sc);
+          *reinterpret_cast<uint4*>(dst + c * 32 + qd * 8) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// =================================================================================================
+// backward, dQ: one CTA (256 threads) per (q-tile, head, batch), streaming kv-tiles.
+//   S = Q K^T, dP = dO V^T (TMEM, rows = q) -> dS (bf16, smem) -> dQ += dS K
+// =================================================================================================
+constexpr int BWD_Q_SMEM = 1024 + 2 * QKV_BYTES + 4 * QKV_BYTES + P_BYTES + 1024;
+
+__global__ void __launch_bounds__(256, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                   const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sQ = base, sdO = sQ + QKV_BYTES;
+  const uint32_t sK0 = sdO + QKV_BYTES;  // stage s: K at sK0 + s*2*QKV_BYTES, V right after
+  const uint32_t sDS = sK0 + 4 * QKV_BYTES;
+  const uint32_t aux = sDS + P_BYTES;
+  float* bias_s = reinterpret_cast<float*>(gen + (aux - base));  // 128 floats
+  const uint32_t bar_q = aux + 512, bar_kv0 = aux + 520 /* +8 */, bar_mma = aux + 536;
+  const uint32_t tmem_ptr_addr = aux + 544;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen + (tmem_ptr_addr - base));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nq_tiles = gridDim.x;
+  const int qt = nq_tiles - 1 - blockIdx.x;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qt * TILE;
+  int nkv = (p.Lk + TILE - 1) / TILE;
+  if (p.causal) nkv = min(nkv, qt + 1);
+
+  if (tid == 0) {
+    mbar_init(bar_q, 1);
+    mbar_init(bar_kv0, 1);
+    mbar_init(bar_kv0 + 8, 1);
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr_addr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_gen;
+  const uint32_t tS = tmem, tDP = tmem + 128, tDQ = tmem + 256;
+  const int quad = warp & 3, half = warp >> 2;
+  const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+  const int r = quad * 32 + lane;  // local q row
+  const int q = q0 + r;
+  const long long stat_o = ((long long)b * p.H + h) * p.Lq + q;
+  const float lse2 = q < p.Lq ? p.lse2[stat_o] : INFINITY;
+  const float dvec = q < p.Lq ? p.dvec[stat_o] : 0.f;
+  const uint64_t drop_row = ((uint64_t)(b * p.H + h) * p.Lq + (uint64_t)q) * (uint64_t)p.Lk;
+
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+  constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, false, true);
+
+  if (tid == 0) {
+    mbar_expect_tx(bar_q, 2 * QKV_BYTES);
+    load_tile(&tmQ, bar_q, sQ, h * DH, q0, b);
+    load_tile(&tmdO, bar_q, sdO, h * DH, q0, b);
+    mbar_expect_tx(bar_kv0, 2 * QKV_BYTES);
+    load_tile(&tmK, bar_kv0, sK0, h * DH, 0, b);
+    load_tile(&tmV, bar_kv0, sK0 + QKV_BYTES, h * DH, 0, b);
+  }
+
+  for (int j = 0; j < nkv; ++j) {
+    const int s = j & 1;
+    const int kv0 = j * TILE;
+    const uint32_t sK = sK0 + s * 2 * QKV_BYTES, sV = sK + QKV_BYTES;
+    if (tid == 0) {
+      if (j == 0) mbar_wait(bar_q, 0);
+      mbar_wait(bar_kv0 + 8 * s, (j >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 6; ++k) tc_mma_bf16(tS, desc_k64(sQ, k), desc_k64(sK, k), idesc_s, k > 0);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) tc_mma_bf16(tDP, desc_k64(sdO, k), desc_k64(sV, k), idesc_s, k > 0);
+      tc_commit(bar_mma);
+    }
+    if (tid < 128) {
+      const int kv = kv0 + tid;
+      bool masked = kv >= p.Lk;
+      if (!masked && p.kpm) masked = p.kpm[(long long)b * p.Lk + kv] != 0;
+      bias_s[tid] = masked ? -INFINITY : 0.f;
+    }
+    __syncthreads();
+    mbar_wait(bar_mma, j & 1);
+    tc_fence_after();
+    if (tid == 0 && j + 1 < nkv) {
+      const uint32_t nb = bar_kv0 + 8 * (s ^ 1);
+      const uint32_t nK = sK0 + (s ^ 1) * 2 * QKV_BYTES;
+      mbar_expect_tx(nb, 2 * QKV_BYTES);
+      load_tile(&tmK, nb, nK, h * DH, kv0 + TILE, b);
+      load_tile(&tmV, nb, nK + QKV_BYTES, h * DH, kv0 + TILE, b);
+    }
+    const bool diag = p.causal && (j == qt);
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c0 = half * 64 + cc * 32;
+      uint32_t rs[32], rp[32];
+      tmem_ld32(tS + lane_sel + c0, rs);
+      tmem_ld32(tDP + lane_sel + c0, rp);
+      tmem_ld_wait();
+      float ds[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int c = c0 + i;
+        float t = __uint_as_float(rs[i]) * p.scale_log2 + bias_s[c] - lse2;
+        if (diag && c > r) t = -INFINITY;
+        const float pr = exp2f(t);
+        const float dm = drop_mult(p, drop_row + (uint64_t)(kv0 + c));
+        ds[i] = pr * (__uint_as_float(rp[i]) * dm - dvec);
+      }
+      store_row32_sw128(sDS, r, c0, ds);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        tc_mma_bf16(tDQ, desc_k128(sDS, k), desc_mn64(sK, k), idesc_g, (j > 0 || k > 0) ? 1u : 0u);
+      if (j + 1 == nkv) tc_commit(bar_mma);
+    }
+  }
+  mbar_wait(bar_mma, nkv & 1);
+  tc_fence_after();
+  {
+    __nv_bfloat16* dst = p.dq + ((long long)b * p.Lq + q) * p.ldq_out + h * DH;
+#pragma unroll 1
+    for (int c = half * 2; c < (half == 0 ? 2 : 3); ++c) {
+      uint32_t rr[32];
+      tmem_ld32(tDQ + lane_sel + c * 32, rr);
+      tmem_ld_wait();
+      if (q < p.Lq) {
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(rr[8 * qd]) * p.scale, __uint_as_float(rr[8 * qd + 1]) * p.scale);
+          u.y = pack_bf16(__uint_as_float(rr[8 * qd + 2]) * p.scale, __uint_as_float(rr[8 * qd + 3]) * p.scale);
+          u.z = pack_bf16(__uint_as_float(rr[8 * qd + 4]) * p.scale, __uint_as_float(rr[8 * qd + 5]) * p.scale);
+          u.w = pack_bf16(__uint_as_float(rr[8 * qd + 6]) * p.scale, __uint_as_float(rr[8 * qd + 7]) * p.scale);
+          *reinterpret_cast<uint4*>(dst + c * 32 + qd * 8) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// -----------------------------------------------------------------------------------------------
+int make_qkv_map(CUtensorMap* m, const void* ptr, int64_t ld, int64_t B, int64_t L, int64_t H) {
+  return make_tmap_3d(m, ptr, 2, (uint64_t)(H * DH), (uint64_t)L, (uint64_t)B, (uint64_t)ld * 2,
+                      (uint64_t)L * ld * 2, 32, TILE, SWZ_64);
+}
+
+int fill_params(AttnParams& p, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int32_t causal, float scale,
+                const uint8_t* kpm, float p_drop, uint64_t seed, uint64_t offset) {
+  SCT_CHECK(B > 0 && H > 0 && Lq > 0 && Lk > 0, "empty attention problem");
+  SCT_CHECK(B <= 65535 && H <= 65535, "grid overflow");
+  SCT_CHECK(!causal || Lq == Lk, "causal attention requires Lq == Lk");
+  SCT_CHECK(p_drop >= 0.f && p_drop < 1.f, "p_drop out of range");
+  p.B = (int)B; p.H = (int)H; p.Lq = (int)Lq; p.Lk = (int)Lk;
+  p.causal = causal;
+  p.scale = scale;
+  p.scale_log2 = scale * kLog2e;
+  p.kpm = kpm;
+  p.seed = seed; p.offset = offset;
+  double t = (double)p_drop * 65536.0 + 0.5;
+  p.thresh16 = p_drop > 0.f ? (uint32_t)(t > 65535.0 ? 65535.0 : t) : 0u;
+  p.inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+  p.lse2 = nullptr; p.dvec = nullptr; p.o = nullptr; p.dq = p.dk = p.dv = nullptr;
+  p.ldo = p.ldq_out = p.ldkv_out = 0;
+  return 0;
+}
+
+__global__ void read_flag_kernel(int* out) { *out = g_timeout_flag; }
+
+}  // namespace
+
+int attn_timeout_flag() {
+  int* d = nullptr;
+  int h = 0;
+  if (cudaMalloc(&d, sizeof(int)) != cudaSuccess) return -1;
+  read_flag_kernel<<<1, 1>>>(d);
+  cudaMemcpy(&h, d, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return h;
+}
+
+}  // namespace sct
+
+using namespace sct;
+
+extern "C" {
+
+int32_t sct_attn_fwd(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* o,
+                     int64_t ldo, float* lse2, const uint8_t* kpm, int64_t B, int64_t H, int64_t Lq,
+                     int64_t Lk, int64_t head_dim, int32_t causal, float scale, float p_drop,
+                     uint64_t seed, uint64_t offset, void* stream) {
+  SCT_CHECK(q && k && v && o, "null pointer");
+  SCT_CHECK(head_dim == DH, "head_dim %lld unsupported (kernel is specialised for 96)", (long long)head_dim);
+  SCT_CHECK(ldo % 8 == 0, "ldo must be a multiple of 8");
+  AttnParams p;
+  if (int rc = fill_params(p, B, H, Lq, Lk, causal, scale, kpm, p_drop, seed, offset)) return rc;
+  p.o = (__nv_bfloat16*)o;
+  p.ldo = (int)ldo;
+  p.lse2 = lse2;
+  CUtensorMap tq, tk, tv;
+  if (int rc = make_qkv_map(&tq, q, ldq, B, Lq, H)) return rc;
+  if (int rc = make_qkv_map(&tk, k, ldkv, B, Lk, H)) return rc;
+  if (int rc = make_qkv_map(&tv, v, ldkv, B, Lk, H)) return rc;
+  static bool attr = false;
+  if (!attr) {
+    SCT_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    attr = true;
+  }
+  dim3 grid((unsigned)((Lq + TILE - 1) / TILE), (unsigned)H, (unsigned)B);
+  attn_fwd_kernel<<<grid, 128, FWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  SCT_LAUNCH_CHECK();
+  return 0;
+}
+
+int32_t sct_attn_bwd(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                     const void* o, const void* d_o, int64_t ldo, const float* lse2, float* dvec,
+                     void* dq, int64_t lddq, void* dk, void* dv, int64_t lddkv, const uint8_t* kpm,
+                     int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t head_dim, int32_t causal,
+                     float scale, float p_drop, uint64_t seed, uint64_t offset, void* stream) {
+  SCT_CHECK(q && k && v && o && d_o && lse2 && dvec && dq && dk && dv, "null pointer");
+  SCT_CHECK(head_dim == DH, "head_dim %lld unsupported (kernel is specialised for 96)", (long long)head_dim);
+  SCT_CHECK(H * DH == 768 || H * DH <= ldo, "unexpected head layout");
+  SCT_CHECK(lddq % 8 == 0 && lddkv % 8 == 0 && ldo % 8 == 0, "gradient pitches must be multiples of 8");
+  AttnParams p;
+  if (int rc = fill_params(p, B, H, Lq, Lk, causal, scale, kpm, p_drop, seed, offset)) return rc;
+  p.lse2 = const_cast<float*>(lse2);
+  p.dvec = dvec;
+  p.dq = (__nv_bfloat16*)dq; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv;
+  p.ldq_out = (int)lddq; p.ldkv_out = (int)lddkv; p.ldo = (int)ldo;
+  cudaStream_t st = (cudaStream_t)stream;
+  SCT_CHECK(H * DH == 32 * 24, "D-vector kernel assumes 8 heads x 96 (row width 768)");
+  {
+    const int rows = (int)(B * Lq);
+    attn_bwd_dvec_kernel<<<(rows + 7) / 8, 256, 0, st>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o,
+                                                         dvec, rows, (int)Lq, (int)H, (int)ldo);
+    SCT_LAUNCH_CHECK();
+  }
+  CUtensorMap tq, tk, tv, tdo;
+  if (int rc = make_qkv_map(&tq, q, ldq, B, Lq, H)) return rc;
+  if (int rc = make_qkv_map(&tk, k, ldkv, B, Lk, H)) return rc;
+  if (int rc = make_qkv_map(&tv, v, ldkv, B, Lk, H)) return rc;
+  if (int rc = make_qkv_map(&tdo, d_o, ldo, B, Lq, H)) return rc;
+  static bool attr = false;
+  if (!attr) {
+    SCT_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_KV_SMEM));
+    SCT_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_Q_SMEM));
+    attr = true;
+  }
+  {
+    dim3 grid((unsigned)((Lk + TILE - 1) / TILE), (unsigned)H, (unsigned)B);
+    attn_bwd_dkdv_kernel<<<grid, 256, BWD_KV_SMEM, st>>>(tq, tk, tv, tdo, p);
+    SCT_LAUNCH_CHECK();
+  }
+  {
+    dim3 grid((unsigned)((Lq + TILE - 1) / TILE), (unsigned)H, (unsigned)B);
+    attn_bwd_dq_kernel<<<grid, 256, BWD_Q_SMEM, st>>>(tq, tk, tv, tdo, p);
+    SCT_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,392 @@
+// sct_b200 — K2: persistent, warp-specialised bf16 GEMM on tcgen05 / TMEM, fed by TMA.
+//
+// Replaces every nn.Linear / MHA projection / FFN / vocab-projection matmul of the reference hot path
+// (SCT-GAN/model.py:56-82, 209-271; torch nn/functional.py linear -> cuBLASLt addmm) and their
+// autograd backward (dgrad, wgrad).
+//
+//   D[M,N] = A[M,K] * B[N,K]^T (+ bias[N])
+//
+// Each operand may be K-major (the contraction index is contiguous in global memory) or MN-major (the
+// M / N index is contiguous).  All three training GEMMs are therefore served by one kernel without any
+// transposed copy in HBM:
+//   forward  Y  = X  W^T : A = X  [M,K]   K-major,  B = W  [N,K]   K-major
+//   dgrad    dX = dY W   : A = dY [M,K'] K-major,   B = W  [K',N'] MN-major (same bytes as forward W)
+//   wgrad    dW = dY^T X : A = dY [K',M'] MN-major, B = X  [K',N'] MN-major, fp32 split-K reduce-add
+//
+// Layout in shared memory (per pipeline stage): operand tiles are stored as column blocks of
+// [rows x 128 B] with the TMA/UMMA 128-byte swizzle; a K-major tile is one block [128|BN rows x 64 k],
+// an MN-major tile is BM/64 (BN/64) blocks of [64 k-rows x 64 mn].
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2-5 = epilogue (TMEM -> registers -> swizzled smem -> TMA store / TMA reduce-add).
+// Two TMEM accumulator stages let the epilogue of tile i overlap the mainloop of tile i+1.
+#include "../../include/sct_b200.h"
+#include "common.cuh"
+
+namespace sct {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 192;
+constexpr int kSmemLimit = 232448;  // 227 KB
+
+struct GemmParams {
+  int M, N, K;
+  int m_tiles, n_tiles, k_splits;
+  int kb_total, kb_per_split;
+  int n_fast;         // 1: consecutive tiles walk N first (A tile reused from L2), 0: walk M first
+  const float* bias;  // nullable, fp32 [N]
+  float alpha;        // output scale applied before bias
+};
+
+template <int BN, bool OUT_F32>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int C_BYTES = BM * BN * (OUT_F32 ? 4 : 2);
+  static constexpr int AUX_BYTES = 1024;  // barriers + tmem ptr + bias tile
+  static constexpr int STAGES_RAW = (kSmemLimit - 1024 - C_BYTES - AUX_BYTES - BN * 4) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + C_BYTES + AUX_BYTES + BN * 4;
+  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages (256 or 512, powers of two)
+  static_assert(STAGES >= 2, "pipeline too shallow");
+};
+
+struct TileCoord {
+  int m_blk, n_blk, kb0, kb1;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t) {
+  TileCoord c;
+  const int ks = t % p.k_splits;
+  const int t2 = t / p.k_splits;
+  if (p.n_fast) {
+    c.n_blk = t2 % p.n_tiles;
+    c.m_blk = t2 / p.n_tiles;
+  } else {
+    c.m_blk = t2 % p.m_tiles;
+    c.n_blk = t2 / p.m_tiles;
+  }
+  c.kb0 = ks * p.kb_per_split;
+  c.kb1 = min(c.kb0 + p.kb_per_split, p.kb_total);
+  return c;
+}
+
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
+  using C = Cfg<BN, OUT_F32>;
+  constexpr int STAGES = C::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sC = smem_base + STAGES * C::STAGE_BYTES;
+  const uint32_t sAux = sC + C::C_BYTES;
+  // aux: full[STAGES] | empty[STAGES] | tfull[2] | tempty[2] | tmem_ptr
+  const uint32_t bar_full = sAux;
+  const uint32_t bar_empty = sAux + 8 * STAGES;
+  const uint32_t bar_tfull = sAux + 16 * STAGES;
+  const uint32_t bar_tempty = bar_tfull + 16;
+  const uint32_t tmem_ptr_addr = bar_tempty + 16;
+  volatile uint32_t* tmem_ptr_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_addr - smem_base));
+  float* bias_s = reinterpret_cast<float*>(smem_gen + (sAux + C::AUX_BYTES - smem_base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.k_splits;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_tfull + 8 * s, 1);
+      mbar_init(bar_tempty + 8 * s, 4);  // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_addr, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          const uint32_t full = bar_full + 8 * s;
+          mbar_expect_tx(full, C::STAGE_BYTES);
+          const uint32_t sA = smem_base + s * C::STAGE_BYTES;
+          const uint32_t sB = sA + C::A_BYTES;
+          if (!A_MN) {
+            tma_load_2d(&tmA, full, sA, kb * BK, tc.m_blk * BM);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c)
+              tma_load_2d(&tmA, full, sA + c * (BK * 128), tc.m_blk * BM + c * 64, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(&tmB, full, sB, kb * BK, tc.n_blk * BN);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(&tmB, full, sB + c * (BK * 128), tc.n_blk * BN + c * 64, kb * BK);
+          }
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      // K-major: 8-row groups are 1024 B apart (SBO); LBO unused for swizzled K-major.
+      // MN-major: 8-k-row groups are 1024 B apart (SBO); 64-wide MN blocks are BK*128 B apart (LBO).
+      constexpr uint32_t A_LBO = A_MN ? BK * 128 : 16, B_LBO = B_MN ? BK * 128 : 16;
+      constexpr uint32_t A_KSTEP = A_MN ? 2048 : 32, B_KSTEP = B_MN ? 2048 : 32;
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        mbar_wait(bar_tempty + 8 * as, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sA = smem_base + s * C::STAGE_BYTES;
+          const uint32_t sB = sA + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = umma_smem_desc(sA + k * A_KSTEP, A_LBO, 1024, UMMA_SW128);
+            const uint64_t bd = umma_smem_desc(sB + k * B_KSTEP, B_LBO, 1024, UMMA_SW128);
+            tc_mma_bf16(d_tmem, ad, bd, idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(bar_empty + 8 * s);  // frees the smem stage once these MMAs retire
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+        tc_commit(bar_tfull + 8 * as);  // accumulator ready for the epilogue
+        if (++as == 2) {
+          as = 0;
+          aph ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 = 128 threads) =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;
+    const int etid = threadIdx.x - 64;  // 0..127
+    const bool store_thread = (etid == 0);
+    int as = 0;
+    uint32_t aph = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(p, t);
+      const int n0 = tc.n_blk * BN;
+      mbar_wait(bar_tfull + 8 * as, aph);
+      tc_fence_after();
+      if (store_thread) tma_wait_group_read0();  // previous tile's staging has been read out
+      for (int i = etid; i < BN; i += 128) {
+        const int n = n0 + i;
+        bias_s[i] = (p.bias != nullptr && n < p.N && tc.kb0 == 0) ? p.bias[n] : 0.f;
+      }
+      named_bar_sync(1, 128);
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c32 = 0; c32 < BN / 32; ++c32) {
+        uint32_t r[32];
+        tmem_ld32(t_addr + c32 * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha + bias_s[c32 * 32 + j];
+        if (OUT_F32) {
+          const uint32_t blk = sC + c32 * (BM * 128) + row * 128;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t dst = blk + (((q ^ (row & 7)) & 7) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(v[4 * q]),
+                         "f"(v[4 * q + 1]), "f"(v[4 * q + 2]), "f"(v[4 * q + 3])
+                         : "memory");
+          }
+        } else {
+          const uint32_t blk = sC + (c32 >> 1) * (BM * 128) + row * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int chunk = (c32 & 1) * 4 + q;
+            const uint32_t dst = blk + (((chunk ^ (row & 7)) & 7) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
+                         "r"(pack_bf16(v[8 * q], v[8 * q + 1])),
+                         "r"(pack_bf16(v[8 * q + 2], v[8 * q + 3])),
+                         "r"(pack_bf16(v[8 * q + 4], v[8 * q + 5])),
+                         "r"(pack_bf16(v[8 * q + 6], v[8 * q + 7]))
+                         : "memory");
+          }
+        }
+      }
+      // TMEM stage drained: hand it back to the MMA warp.
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (store_thread) {
+        constexpr int CW = OUT_F32 ? 32 : 64;  // columns per 128-byte staging block
+#pragma unroll 1
+        for (int cb = 0; cb < BN / CW; ++cb) {
+          if (n0 + cb * CW < p.N) {
+            if (OUT_F32)
+              tma_reduce_add_2d(&tmD, sC + cb * (BM * 128), n0 + cb * CW, tc.m_blk * BM);
+            else
+              tma_store_2d(&tmD, sC + cb * (BM * 128), n0 + cb * CW, tc.m_blk * BM);
+          }
+        }
+        tma_commit_group();
+      }
+      if (++as == 2) {
+        as = 0;
+        aph ^= 1;
+      }
+    }
+    if (store_thread) tma_wait_group0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// -----------------------------------------------------------------------------------------------
+// host launcher
+// -----------------------------------------------------------------------------------------------
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
+int launch(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd,
+           const float* bias, float alpha, int64_t M, int64_t N, int64_t K, int k_splits_req,
+           cudaStream_t stream) {
+  using C = Cfg<BN, OUT_F32>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, OUT_F32>;
+  static bool attr_set = false;  // benign race: idempotent call
+  if (!attr_set) {
+    SCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB, tmD;
+  int rc;
+  if (!A_MN)
+    rc = make_tmap_2d(&tmA, A, 2, false, K, M, lda * 2, BK, BM, SWZ_128);
+  else
+    rc = make_tmap_2d(&tmA, A, 2, false, M, K, lda * 2, 64, BK, SWZ_128);
+  if (rc) return rc;
+  if (!B_MN)
+    rc = make_tmap_2d(&tmB, B, 2, false, K, N, ldb * 2, BK, BN, SWZ_128);
+  else
+    rc = make_tmap_2d(&tmB, B, 2, false, N, K, ldb * 2, 64, BK, SWZ_128);
+  if (rc) return rc;
+  if (OUT_F32)
+    rc = make_tmap_2d(&tmD, D, 4, true, N, M, ldd * 4, 32, BM, SWZ_128);
+  else
+    rc = make_tmap_2d(&tmD, D, 2, false, N, M, ldd * 2, 64, BM, SWZ_128);
+  if (rc) return rc;
+
+  GemmParams p;
+  p.M = (int)M;
+  p.N = (int)N;
+  p.K = (int)K;
+  p.m_tiles = (int)((M + BM - 1) / BM);
+  p.n_tiles = (int)((N + BN - 1) / BN);
+  p.kb_total = (int)((K + BK - 1) / BK);
+  const int sms = num_sms();
+  int ks = 1;
+  if (OUT_F32) {
+    // split-K so that a small [N_out x K_in] weight-gradient still fills the machine
+    ks = k_splits_req > 0 ? k_splits_req : (2 * sms) / (p.m_tiles * p.n_tiles);
+    if (ks < 1) ks = 1;
+    if (ks > p.kb_total) ks = p.kb_total;
+  }
+  p.kb_per_split = (p.kb_total + ks - 1) / ks;
+  p.k_splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.n_fast = (p.n_tiles <= p.m_tiles) ? 1 : 0;
+  p.bias = bias;
+  p.alpha = alpha;
+  const int total = p.m_tiles * p.n_tiles * p.k_splits;
+  const int grid = total < sms ? total : sms;
+  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, tmD, p);
+  SCT_LAUNCH_CHECK();
+  return 0;
+}
+
+int check_common(const void* A, const void* B, const void* D, int64_t M, int64_t N, int64_t K) {
+  SCT_CHECK(A && B && D, "null operand pointer");
+  SCT_CHECK(M > 0 && N > 0 && K > 0, "empty GEMM (M=%lld N=%lld K=%lld)", (long long)M, (long long)N,
+            (long long)K);
+  SCT_CHECK(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "dimension overflow");
+  return 0;
+}
+
+__global__ void read_flag_kernel(int* out) { *out = g_timeout_flag; }
+
+}  // namespace
+
+int gemm_timeout_flag() {
+  int* d = nullptr;
+  int h = 0;
+  if (cudaMalloc(&d, sizeof(int)) != cudaSuccess) return -1;
+  read_flag_kernel<<<1, 1>>>(d);
+  cudaMemcpy(&h, d, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return h;
+}
+
+}  // namespace sct
+
+extern "C" {
+
+int32_t sct_gemm_bf16_nt(const void* A, int64_t lda, const void* W, int64_t ldw, void* D, int64_t ldd,
+                         const float* bias, float alpha, int64_t M, int64_t N, int64_t K, int32_t bn,
+                         void* stream) {
+  if (int rc = sct::check_common(A, W, D, M, N, K)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (bn == 256) return sct::launch<256, false, false, false>(A, lda, W, ldw, D, ldd, bias, alpha, M, N, K, 1, st);
+  return sct::launch<128, false, false, false>(A, lda, W, ldw, D, ldd, bias, alpha, M, N, K, 1, st);
+}
+
+int32_t sct_gemm_bf16_nn(const void* A, int64_t lda, const void* W, int64_t ldw, void* D, int64_t ldd,
+                         const float* bias, float alpha, int64_t M, int64_t N, int64_t K, int32_t bn,
+                         void* stream) {
+  if (int rc = sct::check_common(A, W, D, M, N, K)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (bn == 256) return sct::launch<256, false, true, false>(A, lda, W, ldw, D, ldd, bias, alpha, M, N, K, 1, st);
+  return sct::launch<128, false, true, false>(A, lda, W, ldw, D, ldd, bias, alpha, M, N, K, 1, st);
+}
+
+int32_t sct_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int64_t ldb, float* D, int64_t ldd,
+                         float alpha, int64_t M, int64_t N, int64_t K, int32_t k_splits, void* stream) {
+  if (int rc = sct::check_common(A, B, D, M, N, K)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return sct::launch<128, true, true, true>(A, lda, B, ldb, D, ldd, nullptr, alpha, M, N, K, k_splits, st);
+}
+
+}  // extern "C"
