@@ -30,7 +30,7 @@ SIGNATURES = {
     "sct_gelu_dropout_fwd": [_p, _p, _i64, _f, _u64, _u64, _p],
     "sct_gelu_dropout_bwd": [_p, _p, _p, _i64, _f, _u64, _u64, _p],
     "sct_colsum_bf16": [_p, _i64, _p, _i64, _i64, _f, _p],
-    "sct_cast_scale": [_p, _p, _p, _i64, _i64, _i64, _i64, _f, _p],
+    "sct_cast_scale": [_p, _p, _i64, _p, _i64, _i64, _i64, _i64, _f, _p],
     "sct_seq_mean_fwd": [_p, _p, _p, _i64, _i64, _i64, _p],
     "sct_seq_mean_bwd": [_p, _p, _p, _i64, _i64, _i64, _p],
     "sct_gemm_bf16_nt": [_p, _i64, _p, _i64, _p, _i64, _p, _f, _i64, _i64, _i64, _i32, _p],

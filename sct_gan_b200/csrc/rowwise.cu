@@ -511,15 +511,15 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* __r
 // without torch.cat (model.py:450) and the bf16 GEMM views of fp32 tensors.
 __global__ void __launch_bounds__(256)
 cast_scale_kernel(const float* __restrict__ src_f32, const __nv_bfloat16* __restrict__ src_bf16,
-                  __nv_bfloat16* __restrict__ dst, long long rows, int cols, long long ld_dst,
-                  int col_off, float scale) {
+                  long long ld_src, __nv_bfloat16* __restrict__ dst, long long rows, int cols,
+                  long long ld_dst, int col_off, float scale) {
   const int c4n = cols / 4;
   const long long total = rows * c4n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / c4n;
     const int c = (int)(i % c4n) * 4;
-    float4 v = src_f32 ? ld4(src_f32 + r * cols + c) : ldbf4(src_bf16 + r * cols + c);
+    float4 v = src_f32 ? ld4(src_f32 + r * ld_src + c) : ldbf4(src_bf16 + r * ld_src + c);
     v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
     stbf4(dst + r * ld_dst + col_off + c, v);
   }
@@ -722,17 +722,20 @@ int32_t sct_colsum_bf16(const void* x, int64_t ld, float* out, int64_t M, int64_
   return 0;
 }
 
-int32_t sct_cast_scale(const float* src_f32, const void* src_bf16, void* dst, int64_t rows,
-                       int64_t cols, int64_t ld_dst, int64_t col_off, float scale, void* stream) {
+int32_t sct_cast_scale(const float* src_f32, const void* src_bf16, int64_t ld_src, void* dst,
+                       int64_t rows, int64_t cols, int64_t ld_dst, int64_t col_off, float scale,
+                       void* stream) {
   SCT_CHECK((src_f32 != nullptr) != (src_bf16 != nullptr), "exactly one source");
-  SCT_CHECK(cols % 4 == 0 && ld_dst % 4 == 0 && col_off % 4 == 0, "cast_scale needs multiples of 4");
+  SCT_CHECK(cols % 4 == 0 && ld_dst % 4 == 0 && col_off % 4 == 0 && ld_src % 4 == 0 && ld_src >= cols,
+            "cast_scale needs multiples of 4");
   const long long total = rows * (cols / 4);
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   cast_scale_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
-      src_f32, (const __nv_bfloat16*)src_bf16, (__nv_bfloat16*)dst, rows, (int)cols, ld_dst, (int)col_off, scale);
+      src_f32, (const __nv_bfloat16*)src_bf16, ld_src, (__nv_bfloat16*)dst, rows, (int)cols, ld_dst,
+      (int)col_off, scale);
   SCT_LAUNCH_CHECK();
   return 0;
 }

@@ -1,0 +1,451 @@
+"""Autograd layer over the C-ABI kernels (kernels.py): one torch.autograd.Function per fused op.
+
+Conventions
+  * the residual stream is fp32 [rows, d]; everything fed to a GEMM is bf16 [rows, *]
+  * master parameters stay fp32 nn.Parameters (state_dict-compatible with the reference); GEMMs read a
+    private bf16 shadow (ShadowCache) that is refreshed when the parameter's version counter moves
+  * dropout masks are never stored: every site draws a (seed, offset) pair from DropoutRng in forward
+    and replays it in backward
+  * weight gradients are produced in fp32 and returned to autograd for the fp32 parameter, so the
+    reference's parameter hooks (feature_fusion clamp, model.py:285-286) and optimizer groups work
+    unchanged
+"""
+from __future__ import annotations
+
+import torch
+
+from . import kernels as kn
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+# ------------------------------------------------------------------------------------------------
+class DropoutRng:
+    """(seed, offset) source for the counter-based dropout of the kernels."""
+    seed = 0x5C7B200
+    counter = 0
+
+    @classmethod
+    def reseed(cls, seed: int):
+        cls.seed = int(seed) & 0x7FFFFFFFFFFFFFFF
+        cls.counter = 0
+
+    @classmethod
+    def draw(cls):
+        cls.counter += 1
+        return cls.seed, cls.counter
+
+
+class ShadowCache:
+    """bf16 copies of fp32 parameters for the tensor-core GEMMs (private, non-persistent)."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, p: torch.Tensor) -> torch.Tensor:
+        key = id(p)
+        ent = self._store.get(key)
+        if ent is not None and ent[0] == p._version and ent[1].device == p.device and ent[2] == p.data_ptr():
+            return ent[1]
+        src = p.detach()
+        src2 = src if src.dim() == 2 else src.view(1, -1)
+        assert src2.is_contiguous()
+        buf = ent[1] if (ent is not None and ent[1].device == p.device and ent[1].shape == src.shape) else \
+            torch.empty(src.shape, dtype=BF16, device=p.device)
+        kn.cast_scale(src2, buf.view(src2.shape), 0, 1.0)
+        self._store[key] = (p._version, buf, p.data_ptr())
+        return buf
+
+    def clear(self):
+        self._store.clear()
+
+
+# ------------------------------------------------------------------------------------------------
+class EmbedLnPe(torch.autograd.Function):
+    """K1: LayerNorm(dropout(table[ids] * sqrt(d))) + pe[s]  (model.py:412-421, 944-947)."""
+
+    @staticmethod
+    def forward(ctx, ids, table, gamma, beta, pe, seq_len, scale, p_drop, want_f32, want_bf16):
+        seed, off = DropoutRng.draw() if p_drop > 0 else (0, 0)
+        ids_flat = ids.reshape(-1).contiguous()
+        out_f32, out_bf16, stats = kn.embed_ln_pe_fwd(ids_flat, table.detach(), gamma.detach(), beta.detach(),
+                                                      pe, seq_len, scale, p_drop, seed, off, want_f32, want_bf16)
+        ctx.save_for_backward(ids_flat, table, gamma, stats)
+        ctx.cfg = (scale, p_drop, seed, off)
+        ctx.set_materialize_grads(False)
+        return out_f32, out_bf16
+
+    @staticmethod
+    def backward(ctx, g_f32, g_bf16):
+        ids_flat, table, gamma, stats = ctx.saved_tensors
+        scale, p_drop, seed, off = ctx.cfg
+        if g_f32 is not None and g_bf16 is not None:
+            g = g_f32 + g_bf16.float()
+        else:
+            g = g_f32 if g_f32 is not None else g_bf16
+        dtable = torch.zeros_like(table)
+        dgamma = torch.zeros_like(gamma)
+        dbeta = torch.zeros_like(gamma)
+        if g is not None:
+            kn.embed_ln_pe_bwd(g.contiguous(), ids_flat, table.detach(), gamma.detach(), stats, dtable, dgamma,
+                               dbeta, scale, p_drop, seed, off)
+        return None, dtable, dgamma, dbeta, None, None, None, None, None, None
+
+
+def embed_ln_pe(ids, table, gamma, beta, pe, seq_len, scale, p_drop=0.0, want_f32=True, want_bf16=False):
+    return EmbedLnPe.apply(ids, table, gamma, beta, pe, seq_len, scale, p_drop, want_f32, want_bf16)
+
+
+# ------------------------------------------------------------------------------------------------
+class ResidualLn(torch.autograd.Function):
+    """K4a: x' = x + alpha * dropout(branch); second output = LayerNorm(x') or bf16(x').
+
+    mode: 'ln' (needs gamma/beta), 'cast', or 'none'.  Returns (x' fp32 or None, second bf16 or None)."""
+
+    @staticmethod
+    def forward(ctx, x, branch, gamma, beta, alpha, p_drop, mode, want_x):
+        use_drop = p_drop > 0 and branch is not None
+        seed, off = DropoutRng.draw() if use_drop else (0, 0)
+        p = p_drop if use_drop else 0.0
+        g_ = gamma.detach() if gamma is not None else None
+        b_ = beta.detach() if beta is not None else None
+        need_xprime = want_x or mode == "ln"
+        x_out, y_ln, y_cast, stats = kn.add_dropout_ln_fwd(
+            x, branch, alpha, g_, b_, want_x=need_xprime, want_ln=(mode == "ln"), want_cast=(mode == "cast"),
+            p_drop=p, seed=seed, offset=off)
+        ctx.mode, ctx.alpha, ctx.drop = mode, alpha, (p, seed, off)
+        ctx.has_x, ctx.has_branch = x is not None, branch is not None
+        if mode == "ln":
+            ctx.save_for_backward(x_out, stats, gamma)
+        ctx.set_materialize_grads(False)
+        return (x_out if want_x else None), (y_ln if mode == "ln" else y_cast)
+
+    @staticmethod
+    def backward(ctx, g_xout, g_second):
+        p, seed, off = ctx.drop
+        dgamma = dbeta = None
+        g_yln = g_ycast = None
+        xprime = stats = gamma = None
+        if ctx.mode == "ln":
+            xprime, stats, gamma = ctx.saved_tensors
+            if g_second is not None:
+                g_yln = g_second.contiguous()
+            dgamma = torch.zeros_like(gamma)
+            dbeta = torch.zeros_like(gamma)
+        elif ctx.mode == "cast" and g_second is not None:
+            g_ycast = g_second.contiguous()
+        if g_xout is None and g_yln is None and g_ycast is None:
+            return None, None, dgamma, dbeta, None, None, None, None
+        if g_xout is not None:
+            g_xout = g_xout.contiguous()
+        g_x, g_branch = kn.add_dropout_ln_bwd(
+            g_xout, g_yln, g_ycast, xprime if g_yln is not None else None, stats if g_yln is not None else None,
+            gamma.detach() if g_yln is not None else None, ctx.alpha, dgamma if g_yln is not None else None,
+            dbeta if g_yln is not None else None, want_gx=ctx.has_x, want_gbranch=ctx.has_branch,
+            p_drop=p, seed=seed, offset=off)
+        return g_x, g_branch, dgamma, dbeta, None, None, None, None
+
+
+def residual_ln(x, branch, gamma=None, beta=None, alpha=1.0, p_drop=0.0, mode="ln", want_x=True):
+    return ResidualLn.apply(x, branch, gamma, beta, alpha, p_drop, mode, want_x)
+
+
+class LnAct(torch.autograd.Function):
+    """dropout(gelu(LayerNorm(z))) on bf16 rows (model.py:225-235, 253-271)."""
+
+    @staticmethod
+    def forward(ctx, z, gamma, beta, p_drop):
+        seed, off = DropoutRng.draw() if p_drop > 0 else (0, 0)
+        h, stats = kn.ln_act_fwd(z, gamma.detach(), beta.detach(), p_drop, seed, off)
+        ctx.save_for_backward(z, stats, gamma, beta)
+        ctx.drop = (p_drop, seed, off)
+        return h
+
+    @staticmethod
+    def backward(ctx, g_h):
+        z, stats, gamma, beta = ctx.saved_tensors
+        p, seed, off = ctx.drop
+        dgamma, dbeta = torch.zeros_like(gamma), torch.zeros_like(beta)
+        g_z = kn.ln_act_bwd(g_h.contiguous(), z, stats, gamma.detach(), beta.detach(), dgamma, dbeta, p, seed, off)
+        return g_z, dgamma, dbeta, None
+
+
+def ln_act(z, gamma, beta, p_drop=0.0):
+    return LnAct.apply(z, gamma, beta, p_drop)
+
+
+class GeluDropout(torch.autograd.Function):
+    """dropout(gelu_erf(z)) — the FFN activation (torch transformer.py _ff_block)."""
+
+    @staticmethod
+    def forward(ctx, z, p_drop):
+        seed, off = DropoutRng.draw() if p_drop > 0 else (0, 0)
+        h = kn.gelu_dropout_fwd(z, p_drop, seed, off)
+        ctx.save_for_backward(z)
+        ctx.drop = (p_drop, seed, off)
+        return h
+
+    @staticmethod
+    def backward(ctx, g_h):
+        (z,) = ctx.saved_tensors
+        p, seed, off = ctx.drop
+        return kn.gelu_dropout_bwd(g_h.contiguous(), z, p, seed, off), None
+
+
+def gelu_dropout(z, p_drop=0.0):
+    return GeluDropout.apply(z, p_drop)
+
+
+class ConcatScaled(torch.autograd.Function):
+    """[a, scale_b * b] along features without torch.cat (model.py:450)."""
+
+    @staticmethod
+    def forward(ctx, a, b, scale_b):
+        rows, da = a.shape
+        db = b.shape[1]
+        out = torch.empty((rows, da + db), dtype=BF16, device=a.device)
+        kn.cast_scale(a, out, 0, 1.0)
+        kn.cast_scale(b, out, da, scale_b)
+        ctx.dims = (da, db, scale_b)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        da, db, scale_b = ctx.dims
+        g = g.contiguous()
+        ga = torch.empty((g.shape[0], da), dtype=BF16, device=g.device)
+        gb = torch.empty((g.shape[0], db), dtype=BF16, device=g.device)
+        kn.cast_scale(g[:, :da], ga, 0, 1.0)
+        kn.cast_scale(g[:, da:], gb, 0, scale_b)
+        return ga, gb, None
+
+
+def concat_scaled(a, b, scale_b):
+    return ConcatScaled.apply(a, b, scale_b)
+
+
+# ------------------------------------------------------------------------------------------------
+class Linear(torch.autograd.Function):
+    """K2: y = x W^T + b on tcgen05 (forward nt, dgrad nn, wgrad tn split-K fp32, bias grad colsum)."""
+
+    @staticmethod
+    def forward(ctx, x, w_f32, bias, w_bf16):
+        y = kn.gemm_nt(x, w_bf16, bias.detach() if bias is not None else None)
+        ctx.save_for_backward(x, w_bf16)
+        ctx.has_bias = bias is not None
+        ctx.w_shape = w_f32.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w_bf16 = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = kn.gemm_nn(dy, w_bf16)
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros(ctx.w_shape, dtype=F32, device=dy.device)
+            kn.gemm_tn(dy, x, dw)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.zeros(ctx.w_shape[0], dtype=F32, device=dy.device)
+            kn.colsum_bf16(dy, db)
+        return dx, dw, db, None
+
+
+def linear(x, w_f32, bias, w_bf16):
+    return Linear.apply(x, w_f32, bias, w_bf16)
+
+
+# ------------------------------------------------------------------------------------------------
+class SelfAttention(torch.autograd.Function):
+    """K3 on a packed [B*L, 3d] q|k|v projection."""
+
+    @staticmethod
+    def forward(ctx, qkv, B, H, L, kpm, causal, p_drop):
+        d = qkv.shape[1] // 3
+        seed, off = DropoutRng.draw() if p_drop > 0 else (0, 0)
+        o, lse2 = kn.attn_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], B, H, L, L, kpm=kpm, causal=causal,
+                              p_drop=p_drop, seed=seed, offset=off, head_dim=d // H)
+        ctx.save_for_backward(qkv, o, lse2, kpm if kpm is not None else torch.empty(0))
+        ctx.cfg = (B, H, L, causal, p_drop, seed, off, kpm is not None)
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        qkv, o, lse2, kpm = ctx.saved_tensors
+        B, H, L, causal, p_drop, seed, off, has_kpm = ctx.cfg
+        d = qkv.shape[1] // 3
+        dqkv = torch.empty_like(qkv)
+        kn.attn_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], o, d_o.contiguous(), lse2, B, H, L, L,
+                    dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:], kpm=kpm if has_kpm else None, causal=causal,
+                    p_drop=p_drop, seed=seed, offset=off, head_dim=d // H)
+        return dqkv, None, None, None, None, None, None
+
+
+class CrossAttention(torch.autograd.Function):
+    """K3 with q [B*Lq, d] and a packed [B*Lk, 2d] k|v projection of the memory / path stream."""
+
+    @staticmethod
+    def forward(ctx, q, kv, B, H, Lq, Lk, kpm, p_drop):
+        d = q.shape[1]
+        seed, off = DropoutRng.draw() if p_drop > 0 else (0, 0)
+        o, lse2 = kn.attn_fwd(q, kv[:, :d], kv[:, d:], B, H, Lq, Lk, kpm=kpm, causal=False, p_drop=p_drop,
+                              seed=seed, offset=off, head_dim=d // H)
+        ctx.save_for_backward(q, kv, o, lse2, kpm if kpm is not None else torch.empty(0))
+        ctx.cfg = (B, H, Lq, Lk, p_drop, seed, off, kpm is not None)
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        q, kv, o, lse2, kpm = ctx.saved_tensors
+        B, H, Lq, Lk, p_drop, seed, off, has_kpm = ctx.cfg
+        d = q.shape[1]
+        dq = torch.empty_like(q)
+        dkv = torch.empty_like(kv)
+        kn.attn_bwd(q, kv[:, :d], kv[:, d:], o, d_o.contiguous(), lse2, B, H, Lq, Lk, dq, dkv[:, :d], dkv[:, d:],
+                    kpm=kpm if has_kpm else None, causal=False, p_drop=p_drop, seed=seed, offset=off,
+                    head_dim=d // H)
+        return dq, dkv, None, None, None, None, None, None
+
+
+def self_attention(qkv, B, H, L, kpm=None, causal=False, p_drop=0.0):
+    return SelfAttention.apply(qkv, B, H, L, kpm, causal, p_drop)
+
+
+def cross_attention(q, kv, B, H, Lq, Lk, kpm=None, p_drop=0.0):
+    return CrossAttention.apply(q, kv, B, H, Lq, Lk, kpm, p_drop)
+
+
+# ------------------------------------------------------------------------------------------------
+class VocabCE(torch.autograd.Function):
+    """K4b: mean token cross-entropy of (h W^T + b) against targets without materialising [rows, V].
+
+    Rows are processed in chunks: vocab GEMM into a bf16 scratch chunk -> sct_ce_rows (loss + in-place
+    d logits) -> dgrad / wgrad GEMMs.  Gradients w.r.t. h, W, b are therefore produced in forward (scaled
+    by 1/n_valid) and only multiplied by the upstream scalar in backward.  targets < 0 exclude a row
+    (the t = T-1 position of each sequence, model.py:962-964)."""
+
+    @staticmethod
+    def forward(ctx, h, w_f32, bias, w_bf16, targets, n_valid, chunk_rows):
+        rows, d = h.shape
+        V = w_bf16.shape[0]
+        ld = (V + 7) // 8 * 8
+        need_grad = torch.is_grad_enabled() and (h.requires_grad or w_f32.requires_grad)
+        dev = h.device
+        chunk_rows = min(chunk_rows, rows)
+        scratch = torch.empty((chunk_rows, ld), dtype=BF16, device=dev)
+        if ld != V:
+            scratch[:, V:].zero_()
+        row_loss = torch.empty(rows, dtype=F32, device=dev)
+        row_lse = torch.empty(rows, dtype=F32, device=dev)
+        dh = torch.empty_like(h) if need_grad else None
+        dw = torch.zeros((V, d), dtype=F32, device=dev) if need_grad else None
+        db = torch.zeros((V,), dtype=F32, device=dev) if (need_grad and bias is not None) else None
+        inv = 1.0 / float(n_valid)
+        b_ = bias.detach() if bias is not None else None
+        for r0 in range(0, rows, chunk_rows):
+            r1 = min(r0 + chunk_rows, rows)
+            n = r1 - r0
+            logits = scratch[:n, :V]
+            kn.gemm_nt(h[r0:r1], w_bf16, b_, out=logits)
+            rl, rs = kn.ce_rows(logits, targets[r0:r1], V, grad_scale=inv, write_grad=need_grad)
+            row_loss[r0:r1] = rl
+            row_lse[r0:r1] = rs
+            if need_grad:
+                kn.gemm_nn(logits, w_bf16, out=dh[r0:r1])
+                kn.gemm_tn(logits, h[r0:r1], dw)
+                if db is not None:
+                    # colsum needs an 8-aligned width: the pad columns of the scratch are zero
+                    full = scratch[:n]
+                    if ld != V:
+                        dbp = torch.zeros(ld, dtype=F32, device=dev)
+                        kn.colsum_bf16(full, dbp)
+                        db += dbp[:V]
+                    else:
+                        kn.colsum_bf16(full, db)
+        loss = row_loss.sum() * inv
+        if need_grad:
+            ctx.save_for_backward(dh, dw, db if db is not None else torch.empty(0))
+        ctx.has_bias = db is not None
+        ctx.mark_non_differentiable(row_lse)
+        return loss, row_lse
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_lse):
+        dh, dw, db = ctx.saved_tensors
+        g = g_loss.to(F32)
+        return (dh.float() * g).to(BF16), dw * g, (db * g) if ctx.has_bias else None, None, None, None, None
+
+
+def vocab_ce(h, w_f32, bias, w_bf16, targets, n_valid, chunk_rows=4096):
+    return VocabCE.apply(h, w_f32, bias, w_bf16, targets, n_valid, chunk_rows)
+
+
+# ------------------------------------------------------------------------------------------------
+class SeqMean(torch.autograd.Function):
+    """mean over the sequence of (x_f32 + y_bf16) (model.py:1187-1193 pooled before the linear projection)."""
+
+    @staticmethod
+    def forward(ctx, x, y, B, S):
+        d = (x if x is not None else y).shape[1]
+        ctx.cfg = (B, S, d, x is not None, y is not None)
+        return kn.seq_mean_fwd(x, y, B, S, d)
+
+    @staticmethod
+    def backward(ctx, g):
+        B, S, d, has_x, has_y = ctx.cfg
+        gx, gy = kn.seq_mean_bwd(g.contiguous(), B, S, d, want_f32=has_x, want_bf16=has_y)
+        return gx, gy, None, None
+
+
+def seq_mean(x, y, B, S):
+    return SeqMean.apply(x, y, B, S)
+
+
+class SmallLinear(torch.autograd.Function):
+    """K5: fp32 nn.Linear on [batch, K] rows (discriminator head MLPs, model.py:250-271)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, out_bf16):
+        y = kn.small_linear_fwd(x.contiguous(), w.detach(), bias.detach() if bias is not None else None, out_bf16)
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx, dw, db = kn.small_linear_bwd(dy.contiguous(), x.contiguous(), w.detach(), need_dx=True,
+                                         dx_bf16=(x.dtype == BF16))
+        return dx, dw, (db if ctx.has_bias else None), None
+
+
+def small_linear(x, w, bias, out_bf16=False):
+    return SmallLinear.apply(x, w, bias, out_bf16)
+
+
+class GanLoss(torch.autograd.Function):
+    """K5: (d_loss, adv_loss, confidence) of train.py:1201-1234 with device-side 0.3 / 0.8 predicates."""
+
+    @staticmethod
+    def forward(ctx, z, c_in):
+        zf = z.reshape(-1).contiguous()
+        out4 = kn.gan_loss_fwd(zf, c_in)
+        ctx.save_for_backward(zf, out4)
+        ctx.shape = z.shape
+        conf = out4[2].clone()
+        ctx.mark_non_differentiable(conf)
+        return out4[0].clone(), out4[1].clone(), conf
+
+    @staticmethod
+    def backward(ctx, g_d, g_adv, _g_c):
+        zf, out4 = ctx.saved_tensors
+        z0 = torch.zeros(1, dtype=F32, device=zf.device)
+        gd = g_d.reshape(1).to(F32).contiguous() if g_d is not None else z0
+        ga = g_adv.reshape(1).to(F32).contiguous() if g_adv is not None else z0
+        dz = kn.gan_loss_bwd(zf, out4[2:3], gd, ga)
+        return dz.view(ctx.shape), None
+
+
+def gan_loss(z, c_in=None):
+    return GanLoss.apply(z, c_in)

@@ -1,0 +1,396 @@
+"""Kernel-level parity: every C-ABI entry point against a plain PyTorch fp32 reference of the same op.
+
+Tolerances (stated per test): operands/outputs are bf16 with fp32 accumulation, so elementwise
+agreement is a few bf16 ulps of the output scale; integer work (gather rows, masks) is bit-exact.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def rel_l2(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-20)).item()
+
+
+def _no_timeouts():
+    from sct_gan_b200 import _lib
+
+    torch.cuda.synchronize()
+    assert _lib.load().sct_debug_timeouts() == 0, "a bounded mbarrier wait timed out"
+
+
+# ------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 128, 64, 128), (256, 256, 128, 128), (4096, 768, 768, 128), (4096, 2304, 768, 256),
+    (4096, 2048, 768, 256), (4096, 768, 2048, 128), (1000, 520, 776, 128), (2048, 50265, 768, 256),
+    (333, 384, 768, 128), (4096, 768, 384, 128),
+])
+def test_gemm_nt(cuda_dev, M, N, K, bn):
+    from sct_gan_b200 import kernels as kn
+
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).to(BF16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(BF16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    ldd = (N + 7) // 8 * 8
+    buf = torch.zeros(M, ldd, device="cuda", dtype=BF16)
+    out = kn.gemm_nt(a, w, bias, out=buf[:, :N], bn=bn)
+    _no_timeouts()
+    ref = a.float() @ w.float().t() + bias
+    # bf16 output rounding (2^-9 relative) dominates; fp32 accumulation order differs from torch
+    assert rel_l2(out, ref) < 4e-3
+    assert (out.float() - ref).abs().max().item() < 0.05 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 128, 64, 128), (4096, 768, 2304, 128), (4096, 768, 768, 128), (4096, 2048, 768, 256),
+    (1000, 776, 520, 128), (2048, 768, 50272, 128),
+])
+def test_gemm_nn(cuda_dev, M, N, K, bn):
+    from sct_gan_b200 import kernels as kn
+
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + 1)
+    a = (torch.randn(M, K, device="cuda", generator=g) * (1.0 / math.sqrt(K))).to(BF16)
+    w = torch.randn(K, N, device="cuda", generator=g).to(BF16)
+    out = kn.gemm_nn(a, w, bn=bn)
+    _no_timeouts()
+    ref = a.float() @ w.float()
+    assert rel_l2(out, ref) < 4e-3
+
+
+@pytest.mark.parametrize("M,N,K,ks", [
+    (128, 128, 64, 1), (768, 768, 4096, 0), (2304, 768, 4096, 0), (768, 2048, 4096, 4),
+    (520, 776, 1000, 0), (50265, 768, 2048, 1),
+])
+def test_gemm_tn(cuda_dev, M, N, K, ks):
+    from sct_gan_b200 import kernels as kn
+
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + 2)
+    lda = (M + 7) // 8 * 8  # ragged M (the vocab) lives in a pitch-padded scratch, as in VocabCE
+    a = (torch.randn(K, lda, device="cuda", generator=g) * (1.0 / math.sqrt(K))).to(BF16)[:, :M]
+    b = torch.randn(K, N, device="cuda", generator=g).to(BF16)
+    base = torch.randn(M, N, device="cuda", generator=g)
+    out = base.clone()
+    kn.gemm_tn(a, b, out, alpha=0.5, k_splits=ks)
+    _no_timeouts()
+    ref = base + 0.5 * (a.float().t() @ b.float())
+    # fp32 output: only accumulation-order differences
+    assert rel_l2(out, ref) < 1e-4
+
+
+# -------------------------------------------------------------------------------------- attention
+def _attn_ref(q, k, v, kpm, causal, scale):
+    # q [B,H,Lq,dh] fp32 ...
+    s = torch.einsum("bhqd,bhkd->bhqk", q, k) * scale
+    if kpm is not None:
+        s = s.masked_fill(kpm[:, None, None, :].bool(), float("-inf"))
+    if causal:
+        Lq, Lk = s.shape[-2:]
+        s = s.masked_fill(torch.ones(Lq, Lk, device=s.device, dtype=torch.bool).triu(1), float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    return torch.einsum("bhqk,bhkd->bhqd", p, v)
+
+
+@pytest.mark.parametrize("B,Lq,Lk,causal,masked", [
+    (2, 128, 128, False, False), (2, 256, 256, True, False), (2, 512, 512, False, True),
+    (3, 512, 128, False, True), (2, 200, 77, False, True), (1, 1024, 1024, True, False),
+    (2, 384, 384, True, False), (2, 130, 130, True, False),
+])
+def test_attention_fwd_bwd(cuda_dev, B, Lq, Lk, causal, masked):
+    from sct_gan_b200 import kernels as kn
+
+    H, dh = 8, 96
+    d = H * dh
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + Lq + Lk)
+    # packed projections as the model produces them: q from a [B*Lq, 3d] buffer when self-attention
+    qkv = torch.randn(B * Lq, 3 * d, device="cuda", generator=g).to(BF16)
+    q2 = qkv[:, :d]
+    if Lq == Lk:
+        k2, v2 = qkv[:, d:2 * d], qkv[:, 2 * d:]
+    else:
+        kv = torch.randn(B * Lk, 2 * d, device="cuda", generator=g).to(BF16)
+        k2, v2 = kv[:, :d], kv[:, d:]
+    kpm = None
+    if masked:
+        lens = torch.randint(max(1, Lk // 2), Lk + 1, (B,), device="cuda", generator=g)
+        kpm = (torch.arange(Lk, device="cuda")[None, :] >= lens[:, None]).contiguous()
+    o, lse2 = kn.attn_fwd(q2, k2, v2, B, H, Lq, Lk, kpm=kpm, causal=causal)
+    _no_timeouts()
+
+    def heads(t, L):
+        return t.float().reshape(B, L, H, dh).permute(0, 2, 1, 3).contiguous().requires_grad_(True)
+
+    qf, kf, vf = heads(q2, Lq), heads(k2, Lk), heads(v2, Lk)
+    ref = _attn_ref(qf, kf, vf, kpm, causal, dh ** -0.5)
+    o_h = o.float().reshape(B, Lq, H, dh).permute(0, 2, 1, 3)
+    # P is rounded to bf16 before P@V and O is stored in bf16
+    assert rel_l2(o_h, ref) < 1e-2
+
+    d_o = torch.randn(B * Lq, d, device="cuda", generator=g).to(BF16)
+    dqkv = torch.zeros(B * Lq, 3 * d, device="cuda", dtype=BF16)
+    dq = dqkv[:, :d]
+    if Lq == Lk:
+        dk, dv = dqkv[:, d:2 * d], dqkv[:, 2 * d:]
+    else:
+        dkv = torch.zeros(B * Lk, 2 * d, device="cuda", dtype=BF16)
+        dk, dv = dkv[:, :d], dkv[:, d:]
+    kn.attn_bwd(q2, k2, v2, o, d_o, lse2, B, H, Lq, Lk, dq, dk, dv, kpm=kpm, causal=causal)
+    _no_timeouts()
+    ref.backward(d_o.float().reshape(B, Lq, H, dh).permute(0, 2, 1, 3))
+
+    def unheads(t, L):
+        return t.permute(0, 2, 1, 3).reshape(B * L, d)
+
+    assert rel_l2(dv, unheads(vf.grad, Lk)) < 1.5e-2
+    assert rel_l2(dk, unheads(kf.grad, Lk)) < 1.5e-2
+    assert rel_l2(dq, unheads(qf.grad, Lq)) < 1.5e-2
+
+
+def test_attention_dropout_consistency(cuda_dev):
+    """Dropout cannot match ATen's Philox stream; check the keep-rate/scale statistically and that the
+    backward regenerates the same mask (finite-difference-free check: dV = P_drop^T dO is linear in dO)."""
+    from sct_gan_b200 import kernels as kn
+
+    B, H, dh, L = 2, 8, 96, 256
+    d = H * dh
+    g = torch.Generator(device="cuda").manual_seed(7)
+    qkv = (torch.randn(B * L, 3 * d, device="cuda", generator=g) * 0.1).to(BF16)
+    q2, k2, v2 = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
+    v_ones = torch.ones_like(v2)
+    qkv1 = torch.cat([q2, k2, v_ones], dim=1).contiguous()
+    o, _ = kn.attn_fwd(qkv1[:, :d], qkv1[:, d:2 * d], qkv1[:, 2 * d:], B, H, L, L, p_drop=0.3, seed=11, offset=5)
+    # with V = 1 every output element equals sum_k keep_k * p_k / 0.7: mean 1, never exactly 1
+    assert abs(o.float().mean().item() - 1.0) < 0.02
+    assert o.float().std().item() > 1e-3
+    o2, _ = kn.attn_fwd(qkv1[:, :d], qkv1[:, d:2 * d], qkv1[:, 2 * d:], B, H, L, L, p_drop=0.3, seed=11, offset=5)
+    assert torch.equal(o, o2)
+    o3, _ = kn.attn_fwd(qkv1[:, :d], qkv1[:, d:2 * d], qkv1[:, 2 * d:], B, H, L, L, p_drop=0.3, seed=11, offset=6)
+    assert not torch.equal(o, o3)
+
+
+# ------------------------------------------------------------------------------------ row kernels
+@pytest.mark.parametrize("B,S", [(2, 64), (3, 200), (8, 512)])
+def test_embed_ln_pe(cuda_dev, B, S):
+    from sct_gan_b200 import kernels as kn
+
+    V, d = 50265, 768
+    g = torch.Generator(device="cuda").manual_seed(S)
+    ids = torch.randint(0, V, (B, S), device="cuda", generator=g)
+    ids[0, :4] = torch.tensor([0, 1, 2, V - 1], device="cuda")
+    ids[-1, -8:] = ids[0, 0:8]  # repeated ids: scatter-add collisions
+    table = (torch.randn(V, d, device="cuda", generator=g) * 0.02).requires_grad_(True)
+    gamma = (1 + 0.1 * torch.randn(d, device="cuda", generator=g)).requires_grad_(True)
+    beta = (0.1 * torch.randn(d, device="cuda", generator=g)).requires_grad_(True)
+    pos = torch.arange(1024, device="cuda", dtype=F32)[:, None]
+    div = torch.exp(torch.arange(0, d, 2, device="cuda", dtype=F32) * (-math.log(10000.0) / d))
+    pe = torch.zeros(1024, d, device="cuda")
+    pe[:, 0::2], pe[:, 1::2] = torch.sin(pos * div), torch.cos(pos * div)
+    scale = math.sqrt(d)
+    out_f32, out_bf16, stats = kn.embed_ln_pe_fwd(ids.view(-1), table.detach(), gamma.detach(), beta.detach(), pe, S, scale)
+    x = torch.nn.functional.embedding(ids, table) * scale
+    ref = torch.nn.functional.layer_norm(x, (d,), gamma, beta, 1e-5) + pe[:S][None]
+    # fp32 path: same arithmetic up to reduction order
+    assert (out_f32.view(B, S, d) - ref).abs().max().item() < 2e-4
+    assert torch.equal(out_bf16, out_f32.to(BF16))
+    # gather index is integer work: with gamma=1, beta=0 un-normalising must give the exact table row
+    gy = torch.randn(B * S, d, device="cuda", generator=g)
+    dtable = torch.zeros_like(table)
+    dgamma, dbeta = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+    kn.embed_ln_pe_bwd(gy, ids.view(-1), table.detach(), gamma.detach(), stats, dtable, dgamma, dbeta, scale)
+    ref.backward(gy.view(B, S, d))
+    assert rel_l2(dtable, table.grad) < 1e-4
+    assert rel_l2(dgamma, gamma.grad) < 1e-4
+    assert rel_l2(dbeta, beta.grad) < 1e-4
+    # rows never referenced stay exactly zero (bit-exact scatter targets)
+    touched = torch.zeros(V, dtype=torch.bool, device="cuda")
+    touched[ids.view(-1)] = True
+    assert torch.equal((dtable.abs().sum(1) != 0) | ~touched, torch.ones_like(touched) & ((table.grad.abs().sum(1) != 0) | ~touched))
+    assert dtable[~touched].abs().max().item() == 0.0
+
+
+def test_embed_gather_bit_exact(cuda_dev):
+    """With gamma=1, beta=0, pe=0 the output is LN(row*scale); un-normalising with the returned
+    (mean, rstd) must reproduce the gathered table row for exactly the requested id."""
+    from sct_gan_b200 import kernels as kn
+
+    V, d = 1000, 768
+    g = torch.Generator(device="cuda").manual_seed(3)
+    table = torch.randn(V, d, device="cuda", generator=g)
+    table[:, 0] = torch.arange(V, device="cuda", dtype=F32)  # id written into the row
+    ids = torch.randint(0, V, (4 * 96,), device="cuda", generator=g)
+    out, _, stats = kn.embed_ln_pe_fwd(ids, table, torch.ones(d, device="cuda"), torch.zeros(d, device="cuda"),
+                                       torch.zeros(96, d, device="cuda"), 96, 1.0)
+    rec = out / stats[:, 1:2] + stats[:, 0:1]
+    assert torch.equal(rec[:, 0].round().long(), ids)
+
+
+@pytest.mark.parametrize("d", [768, 384, 1536])
+def test_add_dropout_ln(cuda_dev, d):
+    from sct_gan_b200 import kernels as kn
+
+    n = 1000
+    g = torch.Generator(device="cuda").manual_seed(d)
+    x = torch.randn(n, d, device="cuda", generator=g).requires_grad_(True)
+    br = torch.randn(n, d, device="cuda", generator=g).to(BF16)
+    brf = br.float().requires_grad_(True)
+    gamma = (1 + 0.1 * torch.randn(d, device="cuda", generator=g)).requires_grad_(True)
+    beta = (0.1 * torch.randn(d, device="cuda", generator=g)).requires_grad_(True)
+    x_out, y_ln, y_cast, stats = kn.add_dropout_ln_fwd(x.detach(), br, 0.1, gamma.detach(), beta.detach(), want_cast=True)
+    xr = x + 0.1 * brf
+    yr = torch.nn.functional.layer_norm(xr, (d,), gamma, beta, 1e-5)
+    assert (x_out - xr).abs().max().item() < 1e-5
+    assert rel_l2(y_ln, yr) < 4e-3  # bf16 output
+    assert torch.equal(y_cast, x_out.to(BF16))
+    g_x = torch.randn(n, d, device="cuda", generator=g)
+    g_y = torch.randn(n, d, device="cuda", generator=g).to(BF16)
+    dgamma, dbeta = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+    gx, gb = kn.add_dropout_ln_bwd(g_x, g_y, None, x_out, stats, gamma.detach(), 0.1, dgamma, dbeta)
+    (xr * g_x).sum().backward(retain_graph=True)
+    (yr * g_y.float()).sum().backward()
+    assert rel_l2(gx, x.grad) < 1e-4
+    assert rel_l2(gb, brf.grad) < 4e-3
+    assert rel_l2(dgamma, gamma.grad) < 1e-3
+    assert rel_l2(dbeta, beta.grad) < 1e-3
+
+
+def test_dropout_mask_replay(cuda_dev):
+    from sct_gan_b200 import kernels as kn
+
+    n, d = 2048, 768
+    x = torch.zeros(n, d, device="cuda")
+    br = torch.ones(n, d, device="cuda", dtype=BF16)
+    x_out, _, _, _ = kn.add_dropout_ln_fwd(x, br, 1.0, None, None, want_ln=False, p_drop=0.3, seed=5, offset=9)
+    keep = x_out != 0
+    assert abs(keep.float().mean().item() - 0.7) < 5e-3
+    assert torch.allclose(x_out[keep], torch.full_like(x_out[keep], 1 / 0.7), rtol=1e-6)
+    gx, gb = kn.add_dropout_ln_bwd(torch.ones(n, d, device="cuda"), None, None, None, None, None, 1.0, None, None,
+                                   p_drop=0.3, seed=5, offset=9)
+    assert torch.equal(gb.float() != 0, keep)  # backward regenerates the forward's mask
+
+
+@pytest.mark.parametrize("d", [768, 384, 1536])
+def test_ln_act(cuda_dev, d):
+    from sct_gan_b200 import kernels as kn
+
+    n = 777
+    g = torch.Generator(device="cuda").manual_seed(d + 1)
+    z = torch.randn(n, d, device="cuda", generator=g).to(BF16)
+    zf = z.float().requires_grad_(True)
+    gamma = (1 + 0.1 * torch.randn(d, device="cuda", generator=g)).requires_grad_(True)
+    beta = (0.1 * torch.randn(d, device="cuda", generator=g)).requires_grad_(True)
+    h, stats = kn.ln_act_fwd(z, gamma.detach(), beta.detach())
+    ref = torch.nn.functional.gelu(torch.nn.functional.layer_norm(zf, (d,), gamma, beta, 1e-5))
+    assert rel_l2(h, ref) < 4e-3
+    gh = torch.randn(n, d, device="cuda", generator=g).to(BF16)
+    dgamma, dbeta = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+    gz = kn.ln_act_bwd(gh, z, stats, gamma.detach(), beta.detach(), dgamma, dbeta)
+    ref.backward(gh.float())
+    assert rel_l2(gz, zf.grad) < 5e-3
+    assert rel_l2(dgamma, gamma.grad) < 2e-3
+    assert rel_l2(dbeta, beta.grad) < 2e-3
+
+
+def test_gelu_dropout(cuda_dev):
+    from sct_gan_b200 import kernels as kn
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    z = (2 * torch.randn(512, 2048, device="cuda", generator=g)).to(BF16)
+    zf = z.float().requires_grad_(True)
+    h = kn.gelu_dropout_fwd(z)
+    ref = torch.nn.functional.gelu(zf)
+    assert rel_l2(h, ref) < 4e-3
+    gh = torch.randn(512, 2048, device="cuda", generator=g).to(BF16)
+    gz = kn.gelu_dropout_bwd(gh, z)
+    ref.backward(gh.float())
+    assert rel_l2(gz, zf.grad) < 5e-3
+
+
+def test_colsum_cast_seqmean(cuda_dev):
+    from sct_gan_b200 import kernels as kn
+
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn(3000, 776, device="cuda", generator=g).to(BF16)
+    out = torch.ones(776, device="cuda")
+    kn.colsum_bf16(x, out, 0.5)
+    assert rel_l2(out, 1 + 0.5 * x.float().sum(0)) < 1e-4
+    src = torch.randn(100, 768, device="cuda", generator=g)
+    dst = torch.zeros(100, 1536, device="cuda", dtype=BF16)
+    kn.cast_scale(src, dst, col_off=768, scale=0.1)
+    assert torch.equal(dst[:, 768:], (src * 0.1).to(BF16)) and dst[:, :768].abs().max().item() == 0
+    B, S, d = 4, 300, 768
+    xf = torch.randn(B * S, d, device="cuda", generator=g)
+    yb = torch.randn(B * S, d, device="cuda", generator=g).to(BF16)
+    m = kn.seq_mean_fwd(xf, yb, B, S, d)
+    assert rel_l2(m, (xf + yb.float()).view(B, S, d).mean(1)) < 1e-5
+    gx, gy = kn.seq_mean_bwd(m, B, S, d, want_f32=True, want_bf16=True)
+    assert rel_l2(gx.view(B, S, d), (m / S)[:, None, :].expand(B, S, d)) < 1e-6
+    assert torch.equal(gy, gx.to(BF16))
+
+
+# ------------------------------------------------------------------------------------ loss kernels
+@pytest.mark.parametrize("rows,V", [(64, 50265), (257, 1000), (16, 8)])
+def test_ce_rows(cuda_dev, rows, V):
+    from sct_gan_b200 import kernels as kn
+
+    g = torch.Generator(device="cuda").manual_seed(V)
+    ld = (V + 7) // 8 * 8
+    logits = (3 * torch.randn(rows, ld, device="cuda", generator=g)).to(BF16)
+    tgt = torch.randint(0, V, (rows,), device="cuda", generator=g)
+    tgt[1] = -1  # excluded row
+    lf = logits[:, :V].float().requires_grad_(True)
+    work = logits.clone()
+    row_loss, row_lse = kn.ce_rows(work[:, :V], tgt, V, grad_scale=1.0 / rows, write_grad=True)
+    valid = tgt >= 0
+    ref_rows = torch.nn.functional.cross_entropy(lf[valid], tgt[valid], reduction="none")
+    assert (row_loss[valid] - ref_rows).abs().max().item() < 2e-5 * max(1.0, ref_rows.abs().max().item()) + 1e-5
+    assert row_loss[1].item() == 0.0
+    (ref_rows.sum() / rows).backward()
+    gref = lf.grad
+    assert rel_l2(work[:, :V][valid], gref[valid]) < 5e-3  # bf16 gradient storage
+    assert work[1, :V].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("K,N", [(768, 1536), (1536, 768), (768, 384), (384, 1)])
+def test_small_linear(cuda_dev, K, N):
+    from sct_gan_b200 import kernels as kn
+
+    M = 32
+    g = torch.Generator(device="cuda").manual_seed(K + N)
+    x = torch.randn(M, K, device="cuda", generator=g).requires_grad_(True)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).requires_grad_(True)
+    b = torch.randn(N, device="cuda", generator=g).requires_grad_(True)
+    y = kn.small_linear_fwd(x.detach(), w.detach(), b.detach())
+    ref = torch.nn.functional.linear(x, w, b)
+    assert rel_l2(y, ref) < 1e-5
+    dy = torch.randn(M, N, device="cuda", generator=g)
+    dx, dw, db = kn.small_linear_bwd(dy, x.detach(), w.detach())
+    ref.backward(dy)
+    assert rel_l2(dx, x.grad) < 1e-5 and rel_l2(dw, w.grad) < 1e-5 and rel_l2(db, b.grad) < 1e-5
+
+
+@pytest.mark.parametrize("shift", [-3.0, 0.0, 3.0])
+def test_gan_loss(cuda_dev, shift):
+    """train.py:1201-1234 — thresholds 0.3 / 0.8 exercised by shifting the logits."""
+    from sct_gan_b200 import kernels as kn
+
+    g = torch.Generator(device="cuda").manual_seed(11)
+    z = (torch.randn(32, device="cuda", generator=g) + shift).requires_grad_(True)
+    out4 = kn.gan_loss_fwd(z.detach())
+    bce = torch.nn.BCEWithLogitsLoss()
+    zz = z.view(-1, 1)
+    d = bce(zz, torch.ones_like(zz))
+    c = torch.sigmoid(zz).mean().item()
+    adv = bce(zz, torch.zeros_like(zz)) if c < 0.3 else torch.zeros((), device="cuda")
+    if c > 0.8:
+        d = d + 1.0 * torch.mean(torch.sigmoid(zz) ** 2) + 2.0 * torch.mean(torch.sigmoid(zz) ** 4)
+    assert abs(out4[0].item() - d.item()) < 1e-5 and abs(out4[1].item() - adv.item()) < 1e-5
+    assert abs(out4[2].item() - c) < 1e-6
+    (0.05 * d + 0.02 * adv).backward()
+    dz = kn.gan_loss_bwd(z.detach(), out4[2:3], torch.tensor([0.05], device="cuda"), torch.tensor([0.02], device="cuda"))
+    assert rel_l2(dz, z.grad) < 1e-4
