@@ -1,0 +1,507 @@
+"""CPU oracle for the SCT-GAN adversarial train-step hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is the checker, never the product: only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import it.  The shipped path (sct_gan_b200/) never does.
+
+It restates, as plain functional PyTorch on CPU tensors (fp32 or fp64, straight loops where the reference
+loops), the arithmetic of the reference's path from a `state_dict`:
+
+  forward_train      SmartContractTransformer.forward, training branch      SCT-GAN/model.py:395-476, 938-973
+  line_heads         line-level heads incl. the per-line Python loops        SCT-GAN/model.py:480-759
+  discriminator      discriminator_forward                                   SCT-GAN/model.py:1174-1201
+  step_losses        train_epoch's loss arithmetic                           SCT-GAN/train.py:937-997, 1185-1270
+  generate_greedy    the sampling loop with argmax in place of multinomial   SCT-GAN/model.py:862-930
+  adamw_step         zero_grad/backward/3 clips/skip rules/AdamW groups      SCT-GAN/train.py:512-540, 1273-1311
+
+The arithmetic of nn.TransformerEncoder/Decoder(norm_first), nn.MultiheadAttention, nn.LayerNorm,
+F.gelu (erf) and F.cross_entropy lives in third-party PyTorch (un-vendored, unpinned by the reference; this
+container has torch 2.11.0+cu128: torch/nn/modules/transformer.py:944-983, 1131-1205 and
+torch/nn/functional.py:6244-6691); it is restated here from its published definition.
+
+PARITY PINNING: the reference ships no tests, golden vectors or fixtures for this path (SURVEY.md §4,
+§8c).  The oracle is therefore pinned against outputs of the reference itself: oracle/make_golden.py
+imports the unmodified /root/reference/SCT-GAN/model.py and train.py loss classes in the build container,
+checks this restatement against them (fp64: <= 1e-9, fp32: <= 2e-4) and writes tests/golden/*.pt, which
+tests/test_oracle.py replays on every run.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+DEFAULT_CFG = dict(d_model=768, nhead=8, num_encoder_layers=6, num_decoder_layers=6, dim_feedforward=2048,
+                   dropout=0.3, max_length=1024, vocab_size=50265, num_vulnerability_types=8, use_gan=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# deterministic synthetic weights / batches (shared by the oracle, the goldens and the CUDA parity tests)
+# ------------------------------------------------------------------------------------------------
+def randomize_1d_params(sd: dict, seed: int = 0) -> dict:
+    """The reference zero-initialises every 1-D parameter (model.py:290-294: all LayerNorm gammas and all
+    biases), which makes logits == 0 and parity trivial.  Re-draw them: gamma ~ N(1, 0.1), beta/bias ~
+    N(0, 0.02).  Deterministic given `seed` and the key order."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k, v in sd.items():
+        if k == "pos_encoder.pe" or v.dim() != 1:
+            out[k] = v.clone()
+            continue
+        is_gamma = k.endswith("weight")  # 1-D "weight" = a LayerNorm gamma
+        noise = torch.randn(v.shape, generator=g, dtype=torch.float32)
+        out[k] = (1.0 + 0.1 * noise) if is_gamma else 0.02 * noise
+        if k == "empty_line_embedding":
+            out[k] = 0.02 * noise
+    if "ast_embedding.weight" in out:
+        out["path_embedding.weight"] = out["ast_embedding.weight"]
+    return out
+
+
+def make_batch(B, S, P, vocab, seed=1234, ragged=True, lines_per=12, device="cpu"):
+    """Synthetic token batch of SURVEY.md §8d: ids ~ U{3..V-1}, prefix masks with len ~ U{L/2..L}."""
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(3, vocab, (B, S), generator=g)
+    ast = torch.randint(3, vocab, (B, P), generator=g)
+    tgt = torch.randint(3, vocab, (B, S), generator=g)
+    if ragged:
+        ls = torch.randint(S // 2, S + 1, (B,), generator=g)
+        lp = torch.randint(max(1, P // 2), P + 1, (B,), generator=g)
+    else:
+        ls, lp = torch.full((B,), S), torch.full((B,), P)
+    am = (torch.arange(S)[None, :] < ls[:, None]).long()
+    pm = (torch.arange(P)[None, :] < lp[:, None]).long()
+    t2l = (torch.arange(S) // lines_per)[None, :].expand(B, S).contiguous()
+    cv = (torch.rand(B, 8, generator=g) < 0.2).float()
+    vl = (torch.rand(B, 1024, 8, generator=g) < 0.01).float()
+    batch = dict(input_ids=ids, attention_mask=am, ast_input_ids=ast, ast_attention_mask=pm, target_ids=tgt,
+                 token_to_line=t2l, contract_vulnerabilities=cv, vulnerable_lines=vl)
+    return {k: v.to(device) for k, v in batch.items()}
+
+
+# ------------------------------------------------------------------------------------------------
+# building blocks
+# ------------------------------------------------------------------------------------------------
+def layer_norm(x, w, b, eps=1e-5):
+    mu = x.mean(-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(-1, keepdim=True)  # biased
+    return (x - mu) / torch.sqrt(var + eps) * w + b
+
+
+def gelu(x):
+    return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+def linear(x, w, b=None):
+    y = x @ w.t()
+    return y if b is None else y + b
+
+
+def positional_table(n, d, dtype):
+    """model.py:12-17"""
+    pos = torch.arange(n, dtype=torch.float32).unsqueeze(1)
+    div = torch.exp(torch.arange(0, d, 2).float() * (-math.log(10000.0) / d))
+    pe = torch.zeros(n, d)
+    pe[:, 0::2] = torch.sin(pos * div)
+    pe[:, 1::2] = torch.cos(pos * div)
+    return pe.to(dtype)
+
+
+def embed(sd, prefix_emb, prefix_norm, ids, d, dtype):
+    """model.py:412-415: table[ids]*sqrt(d) -> (dropout) -> LayerNorm -> + pe[s]"""
+    x = sd[prefix_emb + ".weight"].to(dtype)[ids] * math.sqrt(d)
+    x = layer_norm(x, sd[prefix_norm + ".weight"].to(dtype), sd[prefix_norm + ".bias"].to(dtype))
+    return x + sd["pos_encoder.pe"].to(dtype)[: ids.shape[1], 0][None]
+
+
+def mha(sd, prefix, q_in, k_in, v_in, nhead, dtype, key_padding_mask=None, causal=False):
+    """nn.MultiheadAttention (packed in-proj, rows [0,d)=Q, [d,2d)=K, [2d,3d)=V; scale 1/sqrt(dh);
+    bool key_padding_mask True = ignore -> -inf; torch functional.py:6244-6691)."""
+    d = q_in.shape[-1]
+    W, bW = sd[prefix + ".in_proj_weight"].to(dtype), sd[prefix + ".in_proj_bias"].to(dtype)
+    q = linear(q_in, W[:d], bW[:d])
+    k = linear(k_in, W[d:2 * d], bW[d:2 * d])
+    v = linear(v_in, W[2 * d:], bW[2 * d:])
+    B, Lq, _ = q.shape
+    Lk = k.shape[1]
+    dh = d // nhead
+    q = q.view(B, Lq, nhead, dh).transpose(1, 2)
+    k = k.view(B, Lk, nhead, dh).transpose(1, 2)
+    v = v.view(B, Lk, nhead, dh).transpose(1, 2)
+    s = (q @ k.transpose(-1, -2)) / math.sqrt(dh)
+    if key_padding_mask is not None:
+        s = s.masked_fill(key_padding_mask[:, None, None, :], float("-inf"))
+    if causal:
+        s = s.masked_fill(torch.ones(Lq, Lk, dtype=torch.bool).triu(1), float("-inf"))
+    o = (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(B, Lq, d)
+    return linear(o, sd[prefix + ".out_proj.weight"].to(dtype), sd[prefix + ".out_proj.bias"].to(dtype))
+
+
+def _ln(sd, prefix, x, dtype):
+    return layer_norm(x, sd[prefix + ".weight"].to(dtype), sd[prefix + ".bias"].to(dtype))
+
+
+def _lin(sd, prefix, x, dtype):
+    return linear(x, sd[prefix + ".weight"].to(dtype), sd[prefix + ".bias"].to(dtype))
+
+
+def encoder(sd, x, kpm, cfg, dtype):
+    """6 x TransformerEncoderLayer(norm_first): x += SA(LN1 x); x += W2 gelu(W1 LN2 x)"""
+    for i in range(cfg["num_encoder_layers"]):
+        p = f"encoder.layers.{i}"
+        y = _ln(sd, p + ".norm1", x, dtype)
+        x = x + mha(sd, p + ".self_attn", y, y, y, cfg["nhead"], dtype, key_padding_mask=kpm)
+        y = _ln(sd, p + ".norm2", x, dtype)
+        x = x + _lin(sd, p + ".linear2", gelu(_lin(sd, p + ".linear1", y, dtype)), dtype)
+    return x
+
+
+def decoder(sd, x, memory, mem_kpm, cfg, dtype):
+    """6 x TransformerDecoderLayer(norm_first): causal SA; cross-attn on memory; FFN.  No tgt padding mask."""
+    for i in range(cfg["num_decoder_layers"]):
+        p = f"decoder.layers.{i}"
+        y = _ln(sd, p + ".norm1", x, dtype)
+        x = x + mha(sd, p + ".self_attn", y, y, y, cfg["nhead"], dtype, causal=True)
+        y = _ln(sd, p + ".norm2", x, dtype)
+        x = x + mha(sd, p + ".multihead_attn", y, memory, memory, cfg["nhead"], dtype, key_padding_mask=mem_kpm)
+        y = _ln(sd, p + ".norm3", x, dtype)
+        x = x + _lin(sd, p + ".linear2", gelu(_lin(sd, p + ".linear1", y, dtype)), dtype)
+    return x
+
+
+def sequential(sd, prefix, x, dtype, layout):
+    """nn.Sequential of Linear / LayerNorm / GELU / Dropout(eval) given as a string layout, e.g. 'LNG_LNG_L'."""
+    for idx, kind in enumerate(layout):
+        if kind == "L":
+            x = _lin(sd, f"{prefix}.{idx}", x, dtype)
+        elif kind == "N":
+            x = _ln(sd, f"{prefix}.{idx}", x, dtype)
+        elif kind == "G":
+            x = gelu(x)
+    return x
+
+
+def encode_memory(sd, cfg, batch, dtype):
+    """model.py:412-451: embeddings, encoder, the two 0.1-scaled AST attentions and the fusion MLP."""
+    d, H = cfg["d_model"], cfg["nhead"]
+    x = embed(sd, "embedding", "embedding_norm", batch["input_ids"], d, dtype)
+    a = embed(sd, "ast_embedding", "ast_embedding_norm", batch["ast_input_ids"], d, dtype)
+    src_kpm = ~batch["attention_mask"].bool()
+    ast_kpm = ~batch["ast_attention_mask"].bool()
+    memory = encoder(sd, x, src_kpm, cfg, dtype)
+    memory = memory + 0.1 * mha(sd, "ast_attention", memory, a, a, H, dtype, key_padding_mask=ast_kpm)
+    cross = mha(sd, "cross_attention", memory, a, a, H, dtype, key_padding_mask=ast_kpm)
+    fused = sequential(sd, "feature_fusion", torch.cat([memory, 0.1 * cross], dim=-1), dtype, "LNG_LNG_L")
+    return memory + 0.1 * fused, src_kpm
+
+
+def contract_heads(sd, cfg, memory, dtype):
+    """model.py:455-476"""
+    q = memory.mean(dim=1, keepdim=True)
+    att = mha(sd, "contract_vuln_attention", q, memory, memory, cfg["nhead"], dtype)
+    rep = torch.cat([memory.mean(dim=1), att.squeeze(1)], dim=-1)
+    feats = sequential(sd, "contract_feature_aggregation", rep, dtype, "LNG_LNG_")
+    return sequential(sd, "contract_vulnerability_head", feats, dtype, "LNG_LNG_L")
+
+
+def line_position_encoding(line_idx, d, dtype):
+    """model.py:1207-1217"""
+    div = torch.exp(torch.arange(0, d, 2, dtype=torch.float) * -(math.log(10000.0) / d))
+    pe = torch.zeros(d)
+    pe[0::2] = torch.sin(torch.tensor(float(line_idx)) * div)
+    pe[1::2] = torch.cos(torch.tensor(float(line_idx)) * div)
+    return pe.to(dtype)
+
+
+def line_heads(sd, cfg, memory, token_to_line, dtype):
+    """model.py:480-759, loops kept as loops (use on small cases)."""
+    B, S, d = memory.shape
+    H = cfg["nhead"]
+    if token_to_line is not None:
+        max_lines = int(token_to_line.max().item()) + 1
+        feats = []
+        for b in range(B):
+            t2l = token_to_line if token_to_line.dim() == 1 else token_to_line[b]
+            rows = []
+            for li in range(max_lines):
+                m = t2l == li
+                base = memory[b][m].mean(dim=0) if m.any() else sd["empty_line_embedding"].to(dtype)
+                rows.append(base + line_position_encoding(li, d, dtype))
+            feats.append(torch.stack(rows))
+        line_features = torch.stack(feats)
+    else:
+        line_features = memory
+    original = line_features
+    p = "line_feature_extractor"
+    y = gelu(_ln(sd, p + ".norm1", _lin(sd, p + ".linear1", line_features, dtype), dtype))
+    y = _ln(sd, p + ".norm2", _lin(sd, p + ".linear2", y, dtype), dtype)
+    lf = y + 0.1 * line_features
+    if lf.std().item() < 1e-6:
+        lf = original * 0.1
+    att1 = mha(sd, "line_vuln_attention", lf, lf, lf, H, dtype)
+    lf = lf + 0.05 * att1
+    att2 = mha(sd, "vuln_type_attention", lf, lf, lf, H, dtype)
+    lf = lf + 0.05 * att2
+    combined = torch.cat([lf, att1], dim=-1)
+    outs = []
+    for li in range(combined.shape[1]):
+        main = sequential(sd, "line_vulnerability_head_1", combined[:, li], dtype, "LG_LG_L")
+        spec = sequential(sd, "line_specific_processor", original[:, li], dtype, "LG_LG_")
+        typed = torch.cat([sequential(sd, f"vuln_type_processor.{t}", spec, dtype, "LG_L")
+                           for t in range(cfg["num_vulnerability_types"])], dim=1)
+        outs.append(main + 0.1 * typed)
+    logits = torch.stack(outs, dim=1)
+    n = logits.shape[1]
+    if n < 1024:
+        logits = torch.cat([logits, torch.zeros(B, 1024 - n, logits.shape[2], dtype=dtype)], dim=1)
+    elif n > 1024:
+        logits = logits[:, :1024]
+    return logits
+
+
+def discriminator(sd, cfg, features, dtype):
+    """model.py:1174-1201: x = f + MHA(f,f,f) (no mask); projection; mean over ALL positions; two MLPs."""
+    x = features + mha(sd, "disc_path_attention", features, features, features, cfg["nhead"], dtype)
+    x = _lin(sd, "disc_grammar_projection", x, dtype).mean(dim=1)
+    x = sequential(sd, "disc_feature_extractor", x, dtype, "LNG_LNG_")
+    return sequential(sd, "disc_synthetic_head", x, dtype, "LNG_L")
+
+
+def forward_train(sd, cfg, batch, dtype=torch.float32, with_line_heads=True):
+    """Returns the reference's training-branch dict (model.py:966-973) plus 'memory'."""
+    memory, src_kpm = encode_memory(sd, cfg, batch, dtype)
+    tgt = batch["target_ids"]
+    x = embed(sd, "embedding", "embedding_norm", tgt, cfg["d_model"], dtype)
+    out = decoder(sd, x, memory, src_kpm, cfg, dtype)
+    logits = _lin(sd, "output_layer", _ln(sd, "output_norm", out, dtype), dtype)
+    V = logits.shape[-1]
+    res = {
+        "logits": logits[:, :-1, :].reshape(-1, V),
+        "target_ids": tgt[:, 1:].reshape(-1),
+        "contract_vulnerability_logits": contract_heads(sd, cfg, memory, dtype),
+        "line_vulnerability_logits": line_heads(sd, cfg, memory, batch.get("token_to_line"), dtype)
+        if with_line_heads else None,
+        "encoder_output": memory.mean(dim=1),
+        "discriminator_logits": discriminator(sd, cfg, memory, dtype) if cfg.get("use_gan") else None,
+        "memory": memory,
+    }
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
+# losses (train.py)
+# ------------------------------------------------------------------------------------------------
+def bce_with_logits(z, t):
+    return torch.clamp(z, min=0) - z * t + torch.log1p(torch.exp(-z.abs()))
+
+
+def contract_focal_loss(pred, target, alpha=0.05, gamma=4.0):
+    """ContractLevelFocalLoss, train.py:433-478 (trainer constructs it with alpha=0.05, gamma=4: :561-565)."""
+    probs = torch.sigmoid(pred)
+    bce = bce_with_logits(pred, target)
+    focal = alpha * (1 - torch.exp(-bce)) ** gamma * bce
+    fn = torch.where((target == 1) & (probs < 0.5), 2.0, 1.0).to(pred.dtype)
+    return (focal * fn).mean()
+
+
+def spatial_penalty(pred, target, token_to_line):
+    """SpatialAwareFocalLoss._compute_spatial_penalty, train.py:174-245, loops kept."""
+    total = pred.shape[0]
+    if token_to_line is None:
+        return torch.zeros_like(pred)
+    if token_to_line.shape[0] == total:
+        bs, sl = 1, total
+    elif total % 1024 == 0:
+        bs, sl = total // 1024, 1024
+    else:
+        bs, sl = 1, total
+    if bs * sl != total or token_to_line.numel() != bs * sl:
+        return torch.zeros_like(pred)
+    C = pred.shape[1]
+    pr, tg, tl = pred.view(bs, sl, C), target.view(bs, sl, C), token_to_line.view(bs, sl)
+    rows = []
+    for b in range(bs):
+        for i in range(sl):
+            near = (tl[b] - tl[b, i]).abs() <= 2
+            near[i] = False
+            if near.any() and tg[b, near].sum() > 0:
+                rows.append(torch.sigmoid(pr[b, near]).mean(dim=0) * 0.1)
+            else:
+                rows.append(torch.zeros(C, dtype=pred.dtype))
+    return torch.stack(rows).view(-1, C)
+
+
+def spatial_focal_loss(pred, target, token_to_line, alpha, gamma, spatial_weight):
+    """SpatialAwareFocalLoss.forward, train.py:128-172"""
+    probs = torch.sigmoid(pred)
+    bce = bce_with_logits(pred, target)
+    focal = alpha * (1 - torch.exp(-bce)) ** gamma * bce
+    focal = focal + torch.where(target == 1.0, torch.relu(0.3 - probs) * 0.5, torch.zeros_like(probs))
+    focal = focal + torch.where(target == 0.0, torch.relu(probs - 0.5) * 0.2, torch.zeros_like(probs))
+    if token_to_line is not None and spatial_weight > 0:
+        focal = focal + spatial_weight * spatial_penalty(pred, target, token_to_line)
+    return focal.mean()
+
+
+DEFAULT_HP = dict(use_gan=True, use_augmentation=True, contract_vuln_weight=3.0, line_vuln_weight=2.0,
+                  warmup_factor=0.2, stability_factor=1.0, line_loss_scale=1.0, syntax_penalty=0.0)
+
+
+def step_losses(out, batch, hp=None, c_override=None):
+    """train_epoch's loss arithmetic (train.py:937-947 CE mean without ignore_index + constant penalty;
+    :974-997 contract / line losses with the trainer's alpha/gamma switching of :1174-1184 applied as the
+    FIRST step sees it, i.e. the constructor values 0.25/2.0/0.2; :1185-1194 floors and down-scaling;
+    :1201-1234 GAN terms with the 0.3/0.8 thresholds; :1245-1270 weights)."""
+    hp = {**DEFAULT_HP, **(hp or {})}
+    logits, tgt = out["logits"], out["target_ids"]
+    lse = torch.logsumexp(logits, dim=-1)
+    ce = (lse - logits.gather(1, tgt[:, None]).squeeze(1)).mean()
+    gen = ce + 0.5 * hp["syntax_penalty"]
+    res = {"gen_ce_loss": ce, "gen_loss": gen}
+    cv = contract_focal_loss(out["contract_vulnerability_logits"], batch["contract_vulnerabilities"].to(logits.dtype))
+    lv_logits = out["line_vulnerability_logits"]
+    t2l = batch.get("token_to_line")
+    lv = spatial_focal_loss(lv_logits.reshape(-1, lv_logits.shape[-1]),
+                            batch["vulnerable_lines"].reshape(-1, lv_logits.shape[-1]).to(logits.dtype),
+                            t2l.reshape(-1) if t2l is not None else None, 0.25, 2.0, 0.2)
+    cv = torch.maximum(cv, torch.tensor(0.0001, dtype=cv.dtype))
+    lv = torch.maximum(lv, torch.tensor(0.000001, dtype=lv.dtype))
+    if lv.item() > 5.0:
+        lv = lv * 0.1
+    elif lv.item() > 1.0:
+        lv = lv * 0.5
+    w_line = hp["line_vuln_weight"] * hp["warmup_factor"] * hp["stability_factor"] * hp["line_loss_scale"]
+    d_loss = adv = torch.zeros((), dtype=logits.dtype)
+    conf = 0.5
+    if hp["use_gan"] and out.get("discriminator_logits") is not None:
+        z = out["discriminator_logits"]
+        d_loss = bce_with_logits(z, torch.ones_like(z)).mean()
+        conf = torch.sigmoid(z).mean().item() if c_override is None else c_override
+        if conf < 0.3:
+            adv = bce_with_logits(z, torch.zeros_like(z)).mean()
+        if conf > 0.8:
+            d_loss = d_loss + 1.0 * (torch.sigmoid(z) ** 2).mean() + 2.0 * (torch.sigmoid(z) ** 4).mean()
+    if hp["use_augmentation"] and hp["use_gan"]:
+        total = 0.5 * gen + 0.25 * cv * hp["contract_vuln_weight"] + 0.2 * lv * w_line + 0.05 * d_loss
+    elif hp["use_augmentation"]:
+        total = 0.6 * gen + 0.25 * cv * hp["contract_vuln_weight"] + 0.15 * lv * w_line
+    else:
+        total = 0.5 * gen + 0.3 * cv * hp["contract_vuln_weight"] + 0.2 * lv * w_line
+    if hp["use_gan"] and adv.item() > 0:
+        total = total + 0.02 * adv
+    res.update(contract_vuln_loss=cv, line_vuln_loss=lv, discriminator_loss=d_loss, adversarial_loss=adv,
+               discriminator_confidence=conf, total_loss=total)
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
+# generation (greedy restatement of model.py:862-930) and the optimiser step
+# ------------------------------------------------------------------------------------------------
+def generate_greedy(sd, cfg, batch, n_new, dtype=torch.float32, apply_syntax_constraints=True):
+    memory, src_kpm = encode_memory(sd, cfg, batch, dtype)
+    B = memory.shape[0]
+    tgt = torch.ones((B, 1), dtype=torch.long)
+    gaps = []
+    for _ in range(n_new):
+        x = embed(sd, "embedding", "embedding_norm", tgt, cfg["d_model"], dtype)
+        out = _ln(sd, "output_norm", decoder(sd, x, memory, src_kpm, cfg, dtype), dtype)
+        logits = _lin(sd, "output_layer", out[:, -1, :], dtype) / 0.7
+        if apply_syntax_constraints:
+            hit = (tgt[:, -1] >= 2000) & (tgt[:, -1] <= 2002)
+            if logits.shape[1] > 59:
+                logits[:, 59] = torch.where(hit, logits[:, 59] * 2.0, logits[:, 59])
+        top2 = logits.topk(2, dim=-1).values
+        gaps.append(top2[:, 0] - top2[:, 1])
+        tgt = torch.cat([tgt, logits.argmax(dim=-1, keepdim=True)], dim=1)
+    return tgt, torch.stack(gaps, dim=1)
+
+
+def param_groups(names):
+    """train.py:512-540: name-substring rules -> (group index, lr multiplier)."""
+    mult = {0: 1.0, 1: 2.0, 2: 3.0, 3: 0.5}
+    out = {}
+    for n in names:
+        if "disc_" in n:
+            g = 3
+        elif "contract_vulnerability_head" in n or "contract_feature_aggregation" in n or "contract_vuln_attention" in n:
+            g = 1
+        elif ("line_vulnerability_head" in n or "line_feature_extractor" in n or "line_vuln_attention" in n
+              or "vuln_type_attention" in n):
+            g = 2
+        else:
+            g = 0
+        out[n] = (g, mult[g])
+    return out
+
+
+def clip_and_adamw(params: dict, grads: dict, state: dict, lr=1e-6, wd=0.1, max_grad_norm=1.0,
+                   betas=(0.9, 0.98), eps=1e-9, use_gan=True):
+    """train.py:1277-1311 on name->tensor dicts (in place on copies the caller owns): global clip 1.0, then
+    'disc_' clip 0.3, then vulnerability-head clip 2.0 (clip_grad_norm_ semantics: coef = min(1, max/(norm+1e-6))),
+    skip when the post-clip norm > 1000 or non-finite, AdamW with the 4 lr groups.  Returns (stepped, norm)."""
+    def clip(keys, max_norm):
+        ks = [k for k in keys if grads.get(k) is not None]
+        if not ks:
+            return
+        norm = torch.sqrt(sum((grads[k].double() ** 2).sum() for k in ks)).float()
+        coef = torch.clamp(max_norm / (norm + 1e-6), max=1.0)
+        for k in ks:
+            grads[k] = grads[k] * coef
+    names = list(params)
+    clip(names, max_grad_norm)
+    if use_gan:
+        clip([n for n in names if "disc_" in n], max_grad_norm * 0.3)
+    clip([n for n in names if "vulnerability_head" in n or "line_feature_extractor" in n
+          or "line_vuln_attention" in n or "vuln_type_attention" in n], max_grad_norm * 2.0)
+    total = math.sqrt(sum(float(g.norm(2)) ** 2 for g in grads.values() if g is not None))
+    if not math.isfinite(total) or total > 1000:
+        return False, total
+    groups = param_groups(names)
+    state["step"] = state.get("step", 0) + 1
+    t = state["step"]
+    for n in names:
+        g = grads.get(n)
+        if g is None:
+            continue
+        lr_n = lr * groups[n][1]
+        m = state.setdefault("m", {}).setdefault(n, torch.zeros_like(params[n]))
+        v = state.setdefault("v", {}).setdefault(n, torch.zeros_like(params[n]))
+        params[n].mul_(1 - lr_n * wd)
+        m.mul_(betas[0]).add_(g, alpha=1 - betas[0])
+        v.mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])
+        denom = (v.sqrt() / math.sqrt(1 - betas[1] ** t)).add_(eps)
+        params[n].addcdiv_(m, denom, value=-lr_n / (1 - betas[0] ** t))
+    return True, total
+
+
+# ------------------------------------------------------------------------------------------------
+# deterministic synthetic state_dict from a key -> shape table
+# ------------------------------------------------------------------------------------------------
+def synth_state_dict(shapes: dict, seed: int = 0) -> dict:
+    """Weights that depend only on (key, shape, seed): matrices N(0, 2/(fan_in+fan_out)) (embeddings and the
+    vocab projection N(0, 0.02) like model.py:297-303), LayerNorm gamma N(1, 0.1), biases N(0, 0.02), the
+    sinusoidal `pos_encoder.pe`, and the `path_embedding` alias.  1-D parameters are deliberately non-zero
+    (see randomize_1d_params)."""
+    import zlib
+
+    sd = {}
+    for k in sorted(shapes):
+        shp = tuple(shapes[k])
+        if k == "pos_encoder.pe":
+            sd[k] = positional_table(shp[0], shp[2], torch.float32).unsqueeze(1)
+            continue
+        if k == "path_embedding.weight":
+            continue
+        g = torch.Generator().manual_seed((zlib.crc32(k.encode()) + 7919 * seed) & 0x7FFFFFFF)
+        noise = torch.randn(shp, generator=g, dtype=torch.float32)
+        if len(shp) == 2:
+            small = k in ("embedding.weight", "ast_embedding.weight", "output_layer.weight", "disc_grammar_embedding.weight")
+            std = 0.02 if small else math.sqrt(2.0 / (shp[0] + shp[1]))
+            sd[k] = noise * std
+        elif k.endswith("weight"):
+            sd[k] = 1.0 + 0.1 * noise
+        else:
+            sd[k] = 0.02 * noise
+    if "path_embedding.weight" in shapes:
+        sd["path_embedding.weight"] = sd["ast_embedding.weight"]
+    return sd

@@ -81,7 +81,40 @@ def last_error() -> str:
     return load().sct_last_error().decode("utf-8", "replace")
 
 
+# kernels launched per C-ABI call (sct_attn_bwd = D-vector + dK/dV + dQ, sct_seq_mean_fwd = memset + reduce, ...)
+KERNELS_PER_CALL = {"sct_attn_bwd": 3, "sct_small_linear_bwd": 2, "sct_seq_mean_fwd": 2}
+
+
+class Stats:
+    """Launch accounting + optional per-call CUDA-event timing (bench.py's roofline leg).
+
+    `launches` counts device kernels launched through the C ABI.  With `events` set to a list, every call
+    whose name is in `timed` is bracketed by CUDA events recorded on the launching (current torch) stream
+    and appended as (name, work, start_event, end_event), `work` being the call's algorithmic flops/bytes
+    supplied by the wrapper through `annotate`."""
+    launches = 0
+    events = None
+    timed = ()
+    _work = 0.0
+
+    @classmethod
+    def annotate(cls, work: float):
+        cls._work = work
+
+
 def call(name: str, *args) -> None:
-    rc = getattr(load(), name)(*args)
+    fn = getattr(load(), name)
+    ev = Stats.events
+    if ev is not None and name in Stats.timed:
+        import torch
+
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        ev.append((name, Stats._work, e0, e1))
+    else:
+        rc = fn(*args)
+    Stats.launches += KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         raise RuntimeError(f"{name} failed (rc={rc}): {last_error()}")

@@ -89,6 +89,8 @@ def add_dropout_ln_fwd(x, branch, alpha, gamma, beta, want_x=True, want_ln=True,
     y_ln = torch.empty((n_rows, d), dtype=BF16, device=dev) if want_ln else None
     y_cast = torch.empty((n_rows, d), dtype=BF16, device=dev) if want_cast else None
     stats = torch.empty((n_rows, 2), dtype=F32, device=dev) if want_ln else None
+    _lib.Stats.annotate(float(n_rows * d * ((4 if x is not None else 0) + (2 if branch is not None else 0)
+                                            + (4 if want_x else 0) + (2 if want_ln else 0) + (2 if want_cast else 0))))
     _lib.call("sct_add_dropout_ln_fwd", _ptr(x), _ptr(branch), float(alpha), _ptr(gamma), _ptr(beta),
               _ptr(x_out), _ptr(y_ln), _ptr(y_cast), _ptr(stats), n_rows, d, float(p_drop), seed,
               offset, _stream())
@@ -188,11 +190,12 @@ def gemm_nt(a, w, bias=None, alpha=1.0, out=None, bn=None):
     M, K = a.shape
     N, K2 = w.shape
     assert K == K2
-    if out is None:
-        out = torch.empty((M, N), dtype=BF16, device=a.device)
+    if out is None:  # row pitch padded to a multiple of 8 elements (TMA needs 16-byte pitches)
+        out = torch.empty((M, (N + 7) // 8 * 8), dtype=BF16, device=a.device)[:, :N]
     out, ldd = _rows2d(out, BF16, "out")
     if bias is not None:
         _chk(bias, F32, "bias")
+    _lib.Stats.annotate(2.0 * M * N * K)
     _lib.call("sct_gemm_bf16_nt", _ptr(a), lda, _ptr(w), ldw, _ptr(out), ldd, _ptr(bias), float(alpha),
               M, N, K, bn or _pick_bn(N), _stream())
     return out
@@ -206,8 +209,9 @@ def gemm_nn(a, w, alpha=1.0, out=None, bn=None):
     K2, N = w.shape
     assert K == K2
     if out is None:
-        out = torch.empty((M, N), dtype=BF16, device=a.device)
+        out = torch.empty((M, (N + 7) // 8 * 8), dtype=BF16, device=a.device)[:, :N]
     out, ldd = _rows2d(out, BF16, "out")
+    _lib.Stats.annotate(2.0 * M * N * K)
     _lib.call("sct_gemm_bf16_nn", _ptr(a), lda, _ptr(w), ldw, _ptr(out), ldd, None, float(alpha), M, N, K,
               bn or _pick_bn(N), _stream())
     return out
@@ -222,6 +226,7 @@ def gemm_tn(a, b, out, alpha=1.0, k_splits=0):
     assert K == K2
     out, ldd = _rows2d(out, F32, "out")
     assert out.shape == (M, N)
+    _lib.Stats.annotate(2.0 * M * N * K)
     _lib.call("sct_gemm_bf16_tn", _ptr(a), lda, _ptr(b), ldb, _ptr(out), ldd, float(alpha), M, N, K,
               k_splits, _stream())
     return out
@@ -241,6 +246,7 @@ def attn_fwd(q, k, v, B, H, Lq, Lk, kpm=None, causal=False, scale=None, p_drop=0
     lse2 = torch.empty((B, H, Lq), dtype=F32, device=q.device)
     if kpm is not None:
         assert kpm.dtype in (torch.uint8, torch.bool) and kpm.is_contiguous() and kpm.shape == (B, Lk)
+    _lib.Stats.annotate(4.0 * B * H * Lq * Lk * head_dim * (0.5 if causal else 1.0))
     _lib.call("sct_attn_fwd", _ptr(q), ldq, _ptr(k), _ptr(v), ldk, _ptr(o), o.stride(0), _ptr(lse2),
               kpm.data_ptr() if kpm is not None else None, B, H, Lq, Lk, head_dim, int(causal),
               float(scale), float(p_drop), seed, offset, _stream())
@@ -262,6 +268,7 @@ def attn_bwd(q, k, v, o, d_o, lse2, B, H, Lq, Lk, dq, dk, dv, kpm=None, causal=F
     if scale is None:
         scale = head_dim ** -0.5
     dvec = torch.empty((B, H, Lq), dtype=F32, device=q.device)
+    _lib.Stats.annotate(10.0 * B * H * Lq * Lk * head_dim * (0.5 if causal else 1.0))
     _lib.call("sct_attn_bwd", _ptr(q), ldq, _ptr(k), _ptr(v), ldk, _ptr(o), _ptr(d_o), o.stride(0),
               _ptr(lse2), _ptr(dvec), _ptr(dq), lddq, _ptr(dk), _ptr(dv), lddk,
               kpm.data_ptr() if kpm is not None else None, B, H, Lq, Lk, head_dim, int(causal),

@@ -1,0 +1,427 @@
+"""B200-native drop-in for the reference's `SmartContractTransformer` (SCT-GAN/model.py:23-1217).
+
+Same constructor, same `forward` kwargs, same returned dict keys, same sub-module attribute names and the
+same 312 `state_dict` keys (fp32 nn.Parameters, `pos_encoder.pe` buffer, `path_embedding` alias), so the
+reference's train.py / inference.py call sites and checkpoints work unchanged.  The arithmetic of the hot
+path — dual embedding + positional encoding (K1), encoder / AST attention / feature fusion / decoder
+(K2 GEMMs, K3 fused attention, K4a fused residual+dropout+LayerNorm), vocab projection + token
+cross-entropy (K4b) and the integrated discriminator (K5) — runs in the sm_100a kernels behind
+libsct_b200.so.  There is no CPU path: tensors must live on a B200.
+
+Additive, keyword-only extensions (reference-preserving defaults): `fused_loss`, `return_logits`,
+`compute_vuln_heads`, `greedy`, `max_new_tokens`.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .ops import BF16, F32
+
+
+class PositionalEncoding(nn.Module):
+    """Sinusoidal table as a persistent buffer `pe` [max_len, 1, d] (model.py:8-21)."""
+
+    def __init__(self, d_model, max_len=5000):
+        super().__init__()
+        pos = torch.arange(max_len, dtype=torch.float).unsqueeze(1)
+        div = torch.exp(torch.arange(0, d_model, 2).float() * (-math.log(10000.0) / d_model))
+        pe = torch.zeros(max_len, 1, d_model)
+        pe[:, 0, 0::2] = torch.sin(pos * div)
+        pe[:, 0, 1::2] = torch.cos(pos * div)
+        self.register_buffer("pe", pe)
+
+    def forward(self, x):  # seq-first, as the reference calls it
+        return x + self.pe[: x.size(0), :]
+
+
+class ResidualLineFeatureExtractor(nn.Module):
+    """model.py:128-155 (kept in PyTorch: [B, lines, d] rows only)."""
+
+    def __init__(self, d_model):
+        super().__init__()
+        self.linear1 = nn.Linear(d_model, d_model)
+        self.norm1 = nn.LayerNorm(d_model, eps=1e-5)
+        self.linear2 = nn.Linear(d_model, d_model)
+        self.norm2 = nn.LayerNorm(d_model, eps=1e-5)
+        self.dropout = nn.Dropout(0.1)
+
+    def forward(self, x):
+        y = self.dropout(F.gelu(self.norm1(self.linear1(x))))
+        y = self.dropout(self.norm2(self.linear2(y)))
+        return y + 0.1 * x
+
+
+def _mlp(dims_acts):
+    return nn.Sequential(*dims_acts)
+
+
+class SmartContractTransformer(nn.Module):
+    def __init__(self, d_model=768, nhead=8, num_encoder_layers=6, num_decoder_layers=6, dim_feedforward=2048,
+                 dropout=0.3, max_length=1024, vocab_size=50265, num_vulnerability_types=8, use_gan=False):
+        super().__init__()
+        d = d_model
+        # --- module tree: names and registration order follow model.py:40-279 (state_dict compatibility)
+        self.embedding = nn.Embedding(vocab_size, d)
+        self.embedding_dropout = nn.Dropout(dropout)
+        self.embedding_norm = nn.LayerNorm(d)
+        self.pos_encoder = PositionalEncoding(d, max_length)
+        self.ast_embedding = nn.Embedding(vocab_size, d)
+        self.ast_embedding_dropout = nn.Dropout(dropout)
+        self.ast_embedding_norm = nn.LayerNorm(d)
+        self.path_embedding = self.ast_embedding
+        enc_layer = nn.TransformerEncoderLayer(d_model=d, nhead=nhead, dim_feedforward=dim_feedforward,
+                                               dropout=dropout, batch_first=True, activation="gelu", norm_first=True)
+        self.encoder = nn.TransformerEncoder(enc_layer, num_layers=num_encoder_layers, enable_nested_tensor=False)
+        dec_layer = nn.TransformerDecoderLayer(d_model=d, nhead=nhead, dim_feedforward=dim_feedforward,
+                                               dropout=dropout, batch_first=True, activation="gelu", norm_first=True)
+        self.decoder = nn.TransformerDecoder(dec_layer, num_layers=num_decoder_layers)
+        self.output_norm = nn.LayerNorm(d)
+        self.output_dropout = nn.Dropout(dropout)
+        self.output_layer = nn.Linear(d, vocab_size)
+        self.contract_feature_aggregation = nn.Sequential(
+            nn.Linear(2 * d, 2 * d), nn.LayerNorm(2 * d), nn.GELU(), nn.Dropout(dropout),
+            nn.Linear(2 * d, d), nn.LayerNorm(d), nn.GELU(), nn.Dropout(dropout))
+        self.contract_vuln_attention = nn.MultiheadAttention(d, nhead, dropout=dropout, batch_first=True)
+        self.contract_vulnerability_head = nn.Sequential(
+            nn.Linear(d, d), nn.LayerNorm(d), nn.GELU(), nn.Dropout(dropout),
+            nn.Linear(d, d // 2), nn.LayerNorm(d // 2), nn.GELU(), nn.Dropout(dropout),
+            nn.Linear(d // 2, num_vulnerability_types))
+        self.line_feature_extractor = ResidualLineFeatureExtractor(d)
+        self.line_vuln_attention = nn.MultiheadAttention(d, nhead, dropout=dropout * 0.2, batch_first=True)
+        self.vuln_type_attention = nn.MultiheadAttention(d, nhead, dropout=dropout * 0.2, batch_first=True)
+        self.line_vulnerability_head_1 = nn.Sequential(
+            nn.Linear(2 * d, d), nn.GELU(), nn.Dropout(0.1), nn.Linear(d, d // 2), nn.GELU(), nn.Dropout(0.1),
+            nn.Linear(d // 2, num_vulnerability_types))
+        self.line_specific_processor = nn.Sequential(
+            nn.Linear(d, d), nn.GELU(), nn.Dropout(0.1), nn.Linear(d, d // 2), nn.GELU(), nn.Dropout(0.1))
+        self.vuln_type_processor = nn.ModuleList([
+            nn.Sequential(nn.Linear(d // 2, d // 4), nn.GELU(), nn.Dropout(0.1), nn.Linear(d // 4, 1))
+            for _ in range(num_vulnerability_types)])
+        self._debug_mode = False
+        self.ast_attention = nn.MultiheadAttention(d, nhead, dropout=dropout, batch_first=True)
+        self.cross_attention = nn.MultiheadAttention(d, nhead, dropout=dropout, batch_first=True)
+        self.feature_fusion = nn.Sequential(
+            nn.Linear(2 * d, d), nn.LayerNorm(d), nn.GELU(), nn.Dropout(dropout),
+            nn.Linear(d, d // 2), nn.LayerNorm(d // 2), nn.GELU(), nn.Dropout(dropout),
+            nn.Linear(d // 2, d))
+        self.use_gan = use_gan
+        if use_gan:
+            self.disc_path_attention = nn.MultiheadAttention(d, nhead, dropout=dropout, batch_first=True)
+            self.disc_grammar_embedding = nn.Embedding(vocab_size, d)  # never used in forward (model.py:249)
+            self.disc_grammar_projection = nn.Linear(d, d)
+            self.disc_feature_extractor = nn.Sequential(
+                nn.Linear(d, 2 * d), nn.LayerNorm(2 * d), nn.GELU(), nn.Dropout(dropout),
+                nn.Linear(2 * d, d), nn.LayerNorm(d), nn.GELU(), nn.Dropout(dropout))
+            self.disc_synthetic_head = nn.Sequential(
+                nn.Linear(d, d // 2), nn.LayerNorm(d // 2), nn.GELU(), nn.Dropout(dropout), nn.Linear(d // 2, 1))
+        self.d_model = d
+        self.nhead = nhead
+        self.dropout_p = dropout
+        self.max_length = max_length
+        self.vocab_size = vocab_size
+        self.num_vulnerability_types = num_vulnerability_types
+        self.empty_line_embedding = nn.Parameter(torch.zeros(d))
+        self._init_weights()
+        for p in self.feature_fusion.parameters():  # model.py:285-286: clamp parameter grads to +-1
+            p.register_hook(self.hook_fn)
+        self._shadow = ops.ShadowCache()
+        self._step_counter = 0
+
+    # ------------------------------------------------------------------------------------ init
+    def _init_weights(self):
+        """Same distributions as model.py:288-383 (every 1-D parameter zero, matrices Xavier, embeddings /
+        vocab projection / contract head N(0, 0.02), line feature extractor N(0, 0.1), ...)."""
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+            else:
+                nn.init.zeros_(p)
+        for w in (self.embedding.weight, self.ast_embedding.weight, self.output_layer.weight):
+            nn.init.normal_(w, 0.0, 0.02)
+        for m in self.contract_vulnerability_head:
+            if isinstance(m, nn.Linear):
+                nn.init.normal_(m.weight, 0.0, 0.02)
+        for lin in (self.line_feature_extractor.linear1, self.line_feature_extractor.linear2):
+            nn.init.normal_(lin.weight, 0.0, 0.1)
+        for att in (self.line_vuln_attention, self.vuln_type_attention):
+            for p in att.parameters():
+                if p.dim() > 1:
+                    nn.init.xavier_uniform_(p, gain=0.8)
+        last = self.line_vulnerability_head_1[-1]
+        nn.init.normal_(last.weight, 0.0, 0.1)
+        nn.init.constant_(last.bias, -0.2)
+
+    def hook_fn(self, grad):
+        return torch.clamp(grad, -1.0, 1.0)
+
+    def generate_square_subsequent_mask(self, sz):
+        """Float mask, 0 on/below the diagonal and -inf above (model.py:389-393)."""
+        return torch.full((sz, sz), float("-inf")).triu(1)
+
+    def set_current_epoch(self, epoch):
+        self.current_epoch = epoch
+
+    # ------------------------------------------------------------------------------ fused blocks
+    def _p(self):
+        return self.dropout_p if self.training else 0.0
+
+    def _w(self, p):
+        return self._shadow.get(p)
+
+    def _lin(self, x, lin: nn.Linear):
+        return ops.linear(x, lin.weight, lin.bias, self._w(lin.weight))
+
+    def _lin_rows(self, x, weight, bias, r0, r1):
+        """Linear with rows [r0, r1) of a packed in-projection (torch _in_projection_packed)."""
+        return ops.linear(x, weight[r0:r1], bias[r0:r1], self._w(weight)[r0:r1])
+
+    def _embed(self, ids, emb: nn.Embedding, norm: nn.LayerNorm, want_f32, want_bf16):
+        B, S = ids.shape
+        if S > self.pos_encoder.pe.shape[0]:
+            raise RuntimeError(f"sequence length {S} exceeds max_length {self.pos_encoder.pe.shape[0]}")
+        pe = self.pos_encoder.pe.view(-1, self.d_model)
+        return ops.embed_ln_pe(ids, emb.weight, norm.weight, norm.bias, pe, S, math.sqrt(self.d_model), self._p(),
+                               want_f32, want_bf16)
+
+    def _mha_self(self, y, att: nn.MultiheadAttention, B, L, kpm, causal):
+        qkv = ops.linear(y, att.in_proj_weight, att.in_proj_bias, self._w(att.in_proj_weight))
+        o = ops.self_attention(qkv, B, self.nhead, L, kpm, causal, att.dropout if self.training else 0.0)
+        return self._lin(o, att.out_proj)
+
+    def _mha_cross(self, yq, ykv, att: nn.MultiheadAttention, B, Lq, Lk, kpm):
+        d = self.d_model
+        q = self._lin_rows(yq, att.in_proj_weight, att.in_proj_bias, 0, d)
+        kv = self._lin_rows(ykv, att.in_proj_weight, att.in_proj_bias, d, 3 * d)
+        o = ops.cross_attention(q, kv, B, self.nhead, Lq, Lk, kpm, att.dropout if self.training else 0.0)
+        return self._lin(o, att.out_proj)
+
+    def _ffn(self, y, layer):
+        h = ops.gelu_dropout(self._lin(y, layer.linear1), self._p())
+        return self._lin(h, layer.linear2)
+
+    def _encode(self, x, B, S, kpm):
+        """nn.TransformerEncoder, norm_first (torch transformer.py:944-983): x fp32 [B*S, d] -> memory."""
+        p = self._p()
+        layers = self.encoder.layers
+        _, y = ops.residual_ln(x, None, layers[0].norm1.weight, layers[0].norm1.bias, mode="ln", want_x=False)
+        for i, layer in enumerate(layers):
+            a = self._mha_self(y, layer.self_attn, B, S, kpm, False)
+            x, y = ops.residual_ln(x, a, layer.norm2.weight, layer.norm2.bias, 1.0, p, "ln")
+            f = self._ffn(y, layer)
+            if i + 1 < len(layers):
+                nxt = layers[i + 1].norm1
+                x, y = ops.residual_ln(x, f, nxt.weight, nxt.bias, 1.0, p, "ln")
+            else:
+                x, y = ops.residual_ln(x, f, None, None, 1.0, p, "cast")
+        return x, y  # memory fp32 and its bf16 cast
+
+    def _ast_fuse(self, mem, mem_b, ast_b, B, S, P, ast_kpm):
+        """model.py:431-451: two 0.1-scaled AST attentions and the feature-fusion MLP."""
+        p = self._p()
+        a = self._mha_cross(mem_b, ast_b, self.ast_attention, B, S, P, ast_kpm)
+        mem, mem_b = ops.residual_ln(mem, a, None, None, 0.1, 0.0, "cast")
+        c = self._mha_cross(mem_b, ast_b, self.cross_attention, B, S, P, ast_kpm)
+        ff = self.feature_fusion
+        z = self._lin(ops.concat_scaled(mem_b, c, 0.1), ff[0])
+        z = self._lin(ops.ln_act(z, ff[1].weight, ff[1].bias, p), ff[4])
+        z = self._lin(ops.ln_act(z, ff[5].weight, ff[5].bias, p), ff[8])
+        return ops.residual_ln(mem, z, None, None, 0.1, 0.0, "cast")
+
+    def _decode(self, x, mem_b, B, T, S, src_kpm):
+        """nn.TransformerDecoder, norm_first (torch transformer.py:1131-1205) + output_norm/output_dropout.
+        Returns the bf16 rows fed to the vocab projection."""
+        p = self._p()
+        layers = self.decoder.layers
+        _, y = ops.residual_ln(x, None, layers[0].norm1.weight, layers[0].norm1.bias, mode="ln", want_x=False)
+        for i, layer in enumerate(layers):
+            a = self._mha_self(y, layer.self_attn, B, T, None, True)
+            x, y = ops.residual_ln(x, a, layer.norm2.weight, layer.norm2.bias, 1.0, p, "ln")
+            c = self._mha_cross(y, mem_b, layer.multihead_attn, B, T, S, src_kpm)
+            x, y = ops.residual_ln(x, c, layer.norm3.weight, layer.norm3.bias, 1.0, p, "ln")
+            f = self._ffn(y, layer)
+            nxt = layers[i + 1].norm1 if i + 1 < len(layers) else self.output_norm
+            x, y = ops.residual_ln(x, f, nxt.weight, nxt.bias, 1.0, p, "ln", want_x=(i + 1 < len(layers)))
+        if p > 0:
+            _, y = ops.residual_ln(None, y, None, None, 1.0, p, "cast", want_x=False)
+        return y
+
+    def discriminator_forward(self, features, _features_bf16=None):
+        """model.py:1174-1201.  `features` [B, S, d] fp32.  The grammar projection is applied after the
+        sequence mean (mean and Linear commute), so it runs on [B, d] rows."""
+        if not self.use_gan:
+            return None
+        B, S, d = features.shape
+        f2 = features.reshape(B * S, d)
+        fb = _features_bf16
+        if fb is None:
+            _, fb = ops.residual_ln(f2, None, None, None, mode="cast", want_x=False)
+        a = self._mha_self(fb, self.disc_path_attention, B, S, None, False)
+        pooled = ops.seq_mean(f2, a, B, S)
+        p = self._p()
+        x = ops.small_linear(pooled, self.disc_grammar_projection.weight, self.disc_grammar_projection.bias)
+        fe, sh = self.disc_feature_extractor, self.disc_synthetic_head
+        x = ops.ln_act(ops.small_linear(x, fe[0].weight, fe[0].bias, True), fe[1].weight, fe[1].bias, p)
+        x = ops.ln_act(ops.small_linear(x, fe[4].weight, fe[4].bias, True), fe[5].weight, fe[5].bias, p)
+        x = ops.ln_act(ops.small_linear(x, sh[0].weight, sh[0].bias, True), sh[1].weight, sh[1].bias, p)
+        return ops.small_linear(x, sh[4].weight, sh[4].bias)
+
+    # ----------------------------------------------------------------- PyTorch (out-of-scope) heads
+    def _contract_heads(self, memory):
+        """model.py:455-476 (contract-level logits; [B, .] rows, PyTorch)."""
+        q = memory.mean(dim=1, keepdim=True)
+        att, _ = self.contract_vuln_attention(query=q, key=memory, value=memory, need_weights=False)
+        rep = torch.cat([memory.mean(dim=1), att.squeeze(1)], dim=-1)
+        return self.contract_vulnerability_head(self.contract_feature_aggregation(rep))
+
+    def _line_position_encoding(self, n_lines, device):
+        pos = torch.arange(n_lines, dtype=torch.float, device=device).unsqueeze(1)
+        div = torch.exp(torch.arange(0, self.d_model, 2, dtype=torch.float, device=device)
+                        * -(math.log(10000.0) / self.d_model))
+        pe = torch.zeros(n_lines, self.d_model, device=device)
+        pe[:, 0::2] = torch.sin(pos * div)
+        pe[:, 1::2] = torch.cos(pos * div)
+        return pe
+
+    def _line_heads(self, memory, token_to_line):
+        """model.py:480-759 with the two Python loops (batch x lines, lines x types) batched: every line
+        goes through the same weights, so [B, L, .] tensors give the same result."""
+        B, S, d = memory.shape
+        if token_to_line is not None:
+            t2l = token_to_line if token_to_line.dim() == 2 else token_to_line.unsqueeze(0).expand(B, -1)
+            n_lines = int(t2l.max().item()) + 1
+            idx = torch.where((t2l >= 0) & (t2l < n_lines), t2l, torch.full_like(t2l, n_lines)).long()
+            sums = torch.zeros(B, n_lines + 1, d, device=memory.device, dtype=memory.dtype)
+            sums.scatter_add_(1, idx.unsqueeze(-1).expand(-1, -1, d), memory)
+            cnt = torch.zeros(B, n_lines + 1, device=memory.device, dtype=memory.dtype)
+            cnt.scatter_add_(1, idx, torch.ones_like(idx, dtype=memory.dtype))
+            sums, cnt = sums[:, :n_lines], cnt[:, :n_lines].unsqueeze(-1)
+            mean = sums / cnt.clamp(min=1.0)
+            line_features = torch.where(cnt > 0, mean, self.empty_line_embedding.expand(B, n_lines, d))
+            line_features = line_features + self._line_position_encoding(n_lines, memory.device)
+        else:
+            line_features = memory
+        original = line_features
+        lf = self.line_feature_extractor(line_features)
+        lf = torch.where(lf.std() < 1e-6, original * 0.1, lf)
+        att1, _ = self.line_vuln_attention(lf, lf, lf, need_weights=False)
+        lf = lf + 0.05 * att1
+        att2, _ = self.vuln_type_attention(lf, lf, lf, need_weights=False)
+        lf = lf + 0.05 * att2
+        main = self.line_vulnerability_head_1(torch.cat([lf, att1], dim=-1))
+        spec = self.line_specific_processor(original)
+        typed = torch.cat([proc(spec) for proc in self.vuln_type_processor], dim=-1)
+        logits = main + 0.1 * typed
+        n = logits.shape[1]
+        if n < 1024:
+            logits = torch.cat([logits, logits.new_zeros(B, 1024 - n, logits.shape[2])], dim=1)
+        elif n > 1024:
+            logits = logits[:, :1024]
+        return logits
+
+    # --------------------------------------------------------------------------------- forward
+    def forward(self, input_ids, attention_mask=None, ast_input_ids=None, ast_attention_mask=None,
+                target_ids=None, token_to_line=None, apply_syntax_constraints=True, *, fused_loss=False,
+                return_logits=True, compute_vuln_heads=True, greedy=False, max_new_tokens=None):
+        if not input_ids.is_cuda:
+            raise RuntimeError("sct_gan_b200 runs on a B200 only (no CPU fallback): move the batch to cuda")
+        B, S = input_ids.shape
+        d = self.d_model
+        if self.training:
+            self._step_counter += 1
+            ops.DropoutRng.reseed(torch.initial_seed() * 1000003 + self._step_counter)
+        x, _ = self._embed(input_ids, self.embedding, self.embedding_norm, True, False)
+        src_mask = attention_mask.bool() if attention_mask is not None else \
+            torch.ones((B, S), dtype=torch.bool, device=input_ids.device)
+        src_kpm = (~src_mask).contiguous()
+        mem, mem_b = self._encode(x, B, S, src_kpm)
+        if ast_attention_mask is not None:
+            P = ast_input_ids.shape[1]
+            _, ast_b = self._embed(ast_input_ids, self.ast_embedding, self.ast_embedding_norm, False, True)
+            ast_kpm = (~ast_attention_mask.bool()).contiguous()
+            mem, mem_b = self._ast_fuse(mem, mem_b, ast_b, B, S, P, ast_kpm)
+        memory = mem.view(B, S, d)
+
+        if compute_vuln_heads:
+            contract_logits = self._contract_heads(memory)
+            line_logits = self._line_heads(memory, token_to_line)
+        else:
+            contract_logits = line_logits = None
+
+        if target_ids is None:
+            seq = self._generate(mem_b, B, S, src_kpm, apply_syntax_constraints, greedy, max_new_tokens)
+            return {"generated_sequence": seq, "contract_vulnerability_logits": contract_logits,
+                    "line_vulnerability_logits": line_logits}
+
+        T = target_ids.shape[1]
+        tx, _ = self._embed(target_ids, self.embedding, self.embedding_norm, True, False)
+        h = self._decode(tx, mem_b, B, T, S, src_kpm)
+        shifted = target_ids[:, 1:].contiguous().view(-1)
+        out = {"target_ids": shifted}
+        ol = self.output_layer
+        if fused_loss:
+            tgt = torch.full((B, T), -1, dtype=torch.long, device=target_ids.device)
+            tgt[:, :-1] = target_ids[:, 1:]
+            loss, lse = ops.vocab_ce(h, ol.weight, ol.bias, self._w(ol.weight), tgt.view(-1), B * (T - 1))
+            out["gen_ce_loss"] = loss
+            out["lse"] = lse.view(B, T)[:, :-1].reshape(-1)
+        if return_logits and not fused_loss:
+            logits = ops.linear(h, ol.weight, ol.bias, self._w(ol.weight))
+            out["logits"] = logits.view(B, T, -1)[:, :-1, :].float().reshape(B * (T - 1), -1)
+        elif return_logits:
+            with torch.no_grad():
+                logits = ops.linear(h.detach(), ol.weight, ol.bias, self._w(ol.weight))
+            out["logits"] = logits.view(B, T, -1)[:, :-1, :].float().reshape(B * (T - 1), -1)
+        out["contract_vulnerability_logits"] = contract_logits
+        out["line_vulnerability_logits"] = line_logits
+        out["encoder_output"] = memory.mean(dim=1)
+        out["discriminator_logits"] = self.discriminator_forward(memory, mem_b) if self.use_gan else None
+        return out
+
+    # ------------------------------------------------------------------------------ generation
+    def _apply_syntax_constraints(self, logits, prev_tokens):
+        """Only live effect of model.py:975-1060: double the ';' logit (id 59) after ids 2000-2002."""
+        last = prev_tokens[:, -1]
+        hit = (last >= 2000) & (last <= 2002)
+        if logits.size(1) > 59:
+            logits = logits.clone()
+            logits[:, 59] = torch.where(hit, logits[:, 59] * 2.0, logits[:, 59])
+        return logits
+
+    @torch.no_grad()
+    def _generate(self, mem_b, B, S, src_kpm, apply_syntax_constraints, greedy, max_new_tokens):
+        """model.py:862-930: BOS = 1, temperature 0.7, top-k 50, top-p 0.95, multinomial; same stop rules."""
+        dev = mem_b.device
+        tgt = torch.ones((B, 1), dtype=torch.long, device=dev)
+        max_len = min(self.max_length, 1024)
+        steps = max_len - 1 if max_new_tokens is None else min(max_len - 1, max_new_tokens)
+        ol = self.output_layer
+        for i in range(steps):
+            T = tgt.shape[1]
+            tx, _ = self._embed(tgt, self.embedding, self.embedding_norm, True, False)
+            h = self._decode(tx, mem_b, B, T, S, src_kpm)
+            last = h.view(B, T, -1)[:, -1, :].contiguous()
+            logits = ops.linear(last, ol.weight, ol.bias, self._w(ol.weight)).float() / 0.7
+            if apply_syntax_constraints:
+                logits = self._apply_syntax_constraints(logits, tgt)
+            if greedy:
+                nxt = logits.argmax(dim=-1, keepdim=True)
+            else:
+                topv, topi = torch.topk(logits, 50, dim=-1)
+                probs = torch.softmax(topv, dim=-1)
+                cum = torch.cumsum(probs, dim=-1)
+                remove = cum > 0.95
+                remove[:, 1:] = remove[:, :-1].clone()
+                remove[:, 0] = False
+                probs = torch.softmax(topv.masked_fill(remove, float("-inf")), dim=-1)
+                nxt = topi.gather(1, torch.multinomial(probs, 1))
+            tgt = torch.cat([tgt, nxt], dim=1)
+            if max_new_tokens is None:
+                stop = ((nxt == 2).any() | (nxt == 0).any()).item()
+                if (stop and i > 50) or (i > 20 and bool((nxt == 2).all().item())):
+                    break
+        return tgt

@@ -239,7 +239,14 @@ class Linear(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, w_bf16 = ctx.saved_tensors
-        dy = dy.contiguous()
+        N = ctx.w_shape[0]
+        ld = (N + 7) // 8 * 8
+        if ld != N:  # ragged vocab: TMA wants 16-byte row pitches -> zero-padded copy
+            full = torch.zeros((dy.shape[0], ld), dtype=BF16, device=dy.device)
+            full[:, :N] = dy
+            dy = full[:, :N]
+        else:
+            full = dy = dy.contiguous()
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = kn.gemm_nn(dy, w_bf16)
@@ -247,8 +254,9 @@ class Linear(torch.autograd.Function):
             dw = torch.zeros(ctx.w_shape, dtype=F32, device=dy.device)
             kn.gemm_tn(dy, x, dw)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = torch.zeros(ctx.w_shape[0], dtype=F32, device=dy.device)
-            kn.colsum_bf16(dy, db)
+            db = torch.zeros(ld, dtype=F32, device=dy.device)
+            kn.colsum_bf16(full, db)
+            db = db[:N]
         return dx, dw, db, None
 
 
@@ -330,7 +338,7 @@ class VocabCE(torch.autograd.Function):
         rows, d = h.shape
         V = w_bf16.shape[0]
         ld = (V + 7) // 8 * 8
-        need_grad = torch.is_grad_enabled() and (h.requires_grad or w_f32.requires_grad)
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         dev = h.device
         chunk_rows = min(chunk_rows, rows)
         scratch = torch.empty((chunk_rows, ld), dtype=BF16, device=dev)

@@ -1,0 +1,247 @@
+"""The adversarial train step of `SmartContractTrainer.train_epoch` (SCT-GAN/train.py:886-1311) around the
+B200-native model: forward, the reference's loss arithmetic, backward, data-parallel gradient all-reduce
+(NCCL over NVLink), the three gradient clips, the skip rules and AdamW with the reference's four
+learning-rate groups.  Host-side Python; the arithmetic of the hot path runs in libsct_b200.so.
+
+Differences from the reference that do not change results:
+  * the generator cross-entropy comes from the fused chunked vocab kernel (K4b) instead of materialised
+    [B*(T-1), V] logits; the syntax penalty is a non-differentiable constant (train.py:327-330) and is
+    passed in as a number (default 0)
+  * the 0.3 / 0.8 discriminator-confidence branches are device-side predicates (K5); under data
+    parallelism the confidence is all-reduced first so every rank takes the single-GPU branch
+  * per-parameter `.item()` gradient-norm loop (train.py:1294-1299) -> one fused norm
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import ops
+
+
+def _bce(z, t):
+    return F.binary_cross_entropy_with_logits(z, t, reduction="none")
+
+
+def contract_level_focal_loss(pred, target, alpha=0.05, gamma=4.0):
+    """ContractLevelFocalLoss (train.py:433-478; trainer constructs it with alpha=0.05, gamma=4, :561-565)."""
+    probs = torch.sigmoid(pred)
+    bce = _bce(pred, target)
+    focal = alpha * (1 - torch.exp(-bce)) ** gamma * bce
+    penalty = torch.where((target == 1) & (probs < 0.5), 2.0, 1.0)
+    return (focal * penalty).mean()
+
+
+def spatial_penalty(pred, target, token_to_line):
+    """SpatialAwareFocalLoss._compute_spatial_penalty (train.py:174-245) without the B*1024-iteration
+    Python loop.  The reference treats the flattened batch as ONE sequence when token_to_line has as many
+    entries as pred has rows (i.e. S == 1024) and returns zeros otherwise; row i then gets
+    0.1 * mean_j sigmoid(pred_j) over all j != i with |line_j - line_i| <= 2, if those j hold any positive
+    target.  Lines are small integers, so per-line sums + a 5-wide window give the same numbers in O(N)."""
+    total, C = pred.shape
+    if token_to_line is None or token_to_line.numel() != total:
+        return torch.zeros_like(pred)
+    tl = token_to_line.reshape(-1).long()
+    lo = int(tl.min().item())
+    tl = tl - lo
+    L = int(tl.max().item()) + 1
+    sig = torch.sigmoid(pred)
+    cnt = torch.zeros(L + 4, device=pred.device, dtype=pred.dtype).index_add_(0, tl + 2, torch.ones_like(tl, dtype=pred.dtype))
+    s_sig = torch.zeros(L + 4, C, device=pred.device, dtype=pred.dtype).index_add_(0, tl + 2, sig)
+    s_tgt = torch.zeros(L + 4, device=pred.device, dtype=pred.dtype).index_add_(0, tl + 2, target.sum(dim=1))
+
+    def window(x):
+        return x[0:L] + x[1:L + 1] + x[2:L + 2] + x[3:L + 3] + x[4:L + 4]
+
+    n_near = window(cnt)[tl] - 1.0
+    sig_near = window(s_sig)[tl] - sig
+    tgt_near = window(s_tgt)[tl] - target.sum(dim=1)
+    live = (n_near > 0) & (tgt_near > 0)
+    mean = sig_near / n_near.clamp(min=1.0).unsqueeze(1)
+    return torch.where(live.unsqueeze(1), mean * 0.1, torch.zeros_like(mean))
+
+
+def spatial_aware_focal_loss(pred, target, token_to_line, alpha, gamma, spatial_weight):
+    """SpatialAwareFocalLoss.forward (train.py:128-172)."""
+    probs = torch.sigmoid(pred)
+    bce = _bce(pred, target)
+    focal = alpha * (1 - torch.exp(-bce)) ** gamma * bce
+    focal = focal + torch.where(target == 1.0, torch.relu(0.3 - probs) * 0.5, torch.zeros_like(probs))
+    focal = focal + torch.where(target == 0.0, torch.relu(probs - 0.5) * 0.2, torch.zeros_like(probs))
+    if token_to_line is not None and spatial_weight > 0:
+        focal = focal + spatial_weight * spatial_penalty(pred, target, token_to_line)
+    return focal.mean()
+
+
+def param_group_of(name: str, use_gan: bool) -> int:
+    """train.py:518-527 name rules: 0 base, 1 contract heads, 2 line heads, 3 discriminator."""
+    if "disc_" in name and use_gan:
+        return 3
+    if "contract_vulnerability_head" in name or "contract_feature_aggregation" in name or "contract_vuln_attention" in name:
+        return 1
+    if ("line_vulnerability_head" in name or "line_feature_extractor" in name or "line_vuln_attention" in name
+            or "vuln_type_attention" in name):
+        return 2
+    return 0
+
+
+def allreduce_mean_grads(params, world, group=None, bucket_bytes=32 << 20):
+    """Data-parallel gradient exchange: mean-reduce `.grad` across ranks in flat fp32 buckets, launched
+    asynchronously in reverse registration order (the order backward produced them: vocab projection first,
+    embeddings last) and joined before the clips.  Parameters without a gradient (the dead
+    disc_grammar_embedding, empty_line_embedding when every line has tokens) are skipped; they are the same
+    set on every rank because they depend on the module graph, not on the data.  Equal shard sizes + mean
+    losses => the result equals the single-process gradient of the concatenated batch."""
+    live = [p for p in params if p.grad is not None]
+    works, bucket, size = [], [], 0
+
+    def flush():
+        nonlocal bucket, size
+        if bucket:
+            flat = torch.cat([p.grad.reshape(-1) for p in bucket])
+            works.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True), flat, bucket))
+            bucket, size = [], 0
+
+    for p in reversed(live):
+        bucket.append(p)
+        size += p.grad.numel() * p.grad.element_size()
+        if size >= bucket_bytes:
+            flush()
+    flush()
+    inv = 1.0 / world
+    for work, flat, ps in works:
+        work.wait()
+        off = 0
+        for p in ps:
+            n = p.grad.numel()
+            p.grad.copy_(flat[off:off + n].view_as(p.grad)).mul_(inv)
+            off += n
+
+
+class SmartContractTrainer:
+    """Step-level mirror of the reference trainer (constructor keywords of train.py:481-494 that matter for
+    the step).  `train_step(batch)` is the body of the reference's batch loop."""
+
+    LR_MULT = (1.0, 2.0, 3.0, 0.5)
+
+    def __init__(self, model, learning_rate=1e-6, weight_decay=0.1, max_grad_norm=1.0, use_augmentation=False,
+                 use_gan=False, line_vuln_weight=2.0, contract_vuln_weight=3.0, warmup_epochs=5,
+                 compute_vuln_heads=True, process_group=None, bucket_mb=32):
+        self.model = model
+        self.use_augmentation = use_augmentation
+        self.use_gan = use_gan
+        self.max_grad_norm = max_grad_norm
+        self.line_vuln_weight = line_vuln_weight
+        self.contract_vuln_weight = contract_vuln_weight
+        self.warmup_epochs = warmup_epochs
+        self.current_epoch = 0
+        self.stability_factor = 1.0
+        self.line_loss_scale = 1.0
+        self.focal_cfg = (0.25, 2.0, 0.2)  # SpatialAwareFocalLoss constructor values (train.py:568-573)
+        self.compute_vuln_heads = compute_vuln_heads
+        groups = [[], [], [], []]
+        self._names = {}
+        for n, p in model.named_parameters():
+            groups[param_group_of(n, use_gan)].append(p)
+            self._names[p] = n
+        lr = min(learning_rate, 1e-4)  # train.py:598-601
+        pg = [{"params": g, "lr": lr * m} for g, m in zip(groups, self.LR_MULT) if g]
+        self.optimizer = torch.optim.AdamW(pg, weight_decay=weight_decay, betas=(0.9, 0.98), eps=1e-9, fused=True)
+        self.disc_params = [p for n, p in model.named_parameters() if "disc_" in n]
+        self.vuln_params = [p for n, p in model.named_parameters()
+                            if "vulnerability_head" in n or "line_feature_extractor" in n
+                            or "line_vuln_attention" in n or "vuln_type_attention" in n]
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.bucket_bytes = bucket_mb << 20
+        self.last = {}
+
+    # ------------------------------------------------------------------------------------------
+    def compute_losses(self, out, batch, syntax_penalty=0.0):
+        dev = out["gen_ce_loss"].device
+        gen = out["gen_ce_loss"] + 0.5 * syntax_penalty
+        res = {"gen_loss": gen}
+        if self.compute_vuln_heads:
+            cv = contract_level_focal_loss(out["contract_vulnerability_logits"], batch["contract_vulnerabilities"].float())
+            lvl = out["line_vulnerability_logits"]
+            vl = batch["vulnerable_lines"]
+            if lvl.shape != vl.shape and lvl.shape[1] == vl.shape[2] and lvl.shape[2] == vl.shape[1]:
+                vl = vl.transpose(1, 2).contiguous()
+            t2l = batch.get("token_to_line")
+            a, g, sw = self.focal_cfg
+            lv = spatial_aware_focal_loss(lvl.reshape(-1, lvl.shape[-1]), vl.reshape(-1, lvl.shape[-1]).float(),
+                                          t2l.reshape(-1) if t2l is not None else None, a, g, sw)
+            # train.py:1174-1184: the focal settings switch AFTER this batch's loss, on the batch's label count
+            has_line = vl.sum() > 0
+            self._pending_focal = has_line
+            cv = torch.clamp(cv, min=0.0001)
+            lv = torch.clamp(lv, min=0.000001)
+            lv = torch.where(lv > 5.0, lv * 0.1, torch.where(lv > 1.0, lv * 0.5, lv))  # train.py:1189-1194
+        else:
+            cv = lv = torch.zeros((), device=dev)
+        warm = min(1.0, (self.current_epoch + 1) / self.warmup_epochs)
+        w_line = self.line_vuln_weight * warm * self.stability_factor * self.line_loss_scale
+        d_loss = adv = conf = None
+        if self.use_gan and out.get("discriminator_logits") is not None:
+            z = out["discriminator_logits"]
+            c_in = None
+            if self.world > 1:  # global mean confidence so every rank takes the single-GPU branch
+                c_in = torch.sigmoid(z.detach().float()).mean().reshape(1)
+                dist.all_reduce(c_in, op=dist.ReduceOp.SUM, group=self.pg)
+                c_in /= self.world
+            d_loss, adv, conf = ops.gan_loss(z, c_in)
+        if self.use_augmentation and self.use_gan:
+            total = 0.5 * gen + 0.25 * cv * self.contract_vuln_weight + 0.2 * lv * w_line + 0.05 * d_loss
+        elif self.use_augmentation:
+            total = 0.6 * gen + 0.25 * cv * self.contract_vuln_weight + 0.15 * lv * w_line
+        else:
+            total = 0.5 * gen + 0.3 * cv * self.contract_vuln_weight + 0.2 * lv * w_line
+        if self.use_gan and adv is not None:
+            total = total + 0.02 * adv  # adv is exactly 0 unless confidence < 0.3 (train.py:1267-1270)
+        res.update(contract_vuln_loss=cv, line_vuln_loss=lv, discriminator_loss=d_loss, adversarial_loss=adv,
+                   discriminator_confidence=conf, total_loss=total)
+        return res
+
+    def _allreduce_grads(self):
+        if self.world > 1:
+            allreduce_mean_grads(list(self.model.parameters()), self.world, self.pg, self.bucket_bytes)
+
+    def train_step(self, batch, syntax_penalty=0.0):
+        """One optimisation step; returns a dict of device scalars (no host sync except the skip rule)."""
+        model = self.model
+        model.train()
+        target_ids = batch["target_ids"] if self.use_augmentation else batch["input_ids"]
+        out = model(input_ids=batch["input_ids"], attention_mask=batch["attention_mask"],
+                    ast_input_ids=batch["ast_input_ids"], ast_attention_mask=batch["ast_attention_mask"],
+                    target_ids=target_ids, token_to_line=batch.get("token_to_line"), fused_loss=True,
+                    return_logits=False, compute_vuln_heads=self.compute_vuln_heads)
+        losses = self.compute_losses(out, batch, syntax_penalty)
+        self.optimizer.zero_grad(set_to_none=True)
+        losses["total_loss"].backward()
+        self._allreduce_grads()
+        params = [p for p in model.parameters() if p.grad is not None]
+        torch.nn.utils.clip_grad_norm_(params, self.max_grad_norm, foreach=True)
+        if self.use_gan:
+            dp = [p for p in self.disc_params if p.grad is not None]
+            if dp:
+                torch.nn.utils.clip_grad_norm_(dp, self.max_grad_norm * 0.3, foreach=True)
+        vp = [p for p in self.vuln_params if p.grad is not None]
+        if vp:
+            torch.nn.utils.clip_grad_norm_(vp, self.max_grad_norm * 2.0, foreach=True)
+        norms = torch._foreach_norm([p.grad for p in params])
+        total_norm = torch.linalg.vector_norm(torch.stack(norms))
+        ok = torch.isfinite(losses["total_loss"]) & torch.isfinite(total_norm) & (total_norm <= 1000)
+        stepped = bool(ok.item())  # the reference's skip rule is a host decision (train.py:1301-1309)
+        if stepped:
+            self.optimizer.step()
+        else:
+            self.optimizer.zero_grad(set_to_none=True)
+        if self.compute_vuln_heads:  # train.py:1174-1184
+            self.focal_cfg = (0.1, 1.5, 0.1) if bool(self._pending_focal.item()) else (0.05, 1.0, 0.05)
+        losses["grad_norm"] = total_norm
+        losses["stepped"] = stepped
+        self.last = losses
+        return losses

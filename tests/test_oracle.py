@@ -1,0 +1,181 @@
+"""CPU suite: the oracle against the committed golden fixtures (reference outputs, oracle/make_golden.py),
+the drop-in boundary (state_dict keys/shapes, constructor, C-ABI symbols) and host logic."""
+import ctypes
+import glob
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.pt")))
+
+
+def load_golden(path):
+    return torch.load(path, map_location="cpu", weights_only=False)
+
+
+def test_golden_present():
+    assert len(GOLDEN) >= 2
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_oracle_reproduces_reference_outputs(path):
+    """fp32 oracle vs fp32 reference outputs: same arithmetic, different summation order -> 2e-4 relative."""
+    from oracle import sct_oracle as O
+
+    g = load_golden(path)
+    sd = O.synth_state_dict(g["shapes"], g["seed"])
+    batch = O.make_batch(**g["batch_args"])
+    out = O.forward_train(sd, g["cfg"], batch, torch.float32)
+    assert torch.equal(out["target_ids"], g["outputs"]["target_ids"])  # integer work: bit-exact
+    for k in ("logits", "contract_vulnerability_logits", "encoder_output", "discriminator_logits"):
+        ref = g["outputs"][k]
+        assert (out[k] - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item()), k
+    n_lines = g["outputs"]["line_vulnerability_logits"].shape[1]
+    lv = out["line_vulnerability_logits"]
+    assert (lv[:, :n_lines] - g["outputs"]["line_vulnerability_logits"]).abs().max().item() <= 2e-4
+    assert lv[:, n_lines:].abs().max().item() == 0.0  # padded to 1024 with zeros (model.py:751-757)
+    losses = O.step_losses(out, batch, g["hp"])
+    for k in ("gen_ce_loss", "contract_vuln_loss", "line_vuln_loss", "discriminator_loss", "total_loss"):
+        assert abs(float(losses[k]) - g["losses"][k]) <= 2e-4 * max(1.0, abs(g["losses"][k])), k
+
+
+@pytest.mark.parametrize("path", GOLDEN[:1], ids=[os.path.basename(p) for p in GOLDEN[:1]])
+def test_oracle_gradients_match_reference(path):
+    from oracle import sct_oracle as O
+
+    g = load_golden(path)
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and k not in ("pos_encoder.pe",))
+          for k, v in O.synth_state_dict(g["shapes"], g["seed"]).items()}
+    sd["path_embedding.weight"] = sd["ast_embedding.weight"]
+    batch = O.make_batch(**g["batch_args"])
+    out = O.forward_train(sd, g["cfg"], batch, torch.float32)
+    O.step_losses(out, batch, g["hp"])["total_loss"].backward()
+    for n, ref in g["grads"].items():
+        assert (sd[n].grad - ref).norm().item() <= 1e-3 * ref.norm().item() + 1e-9, n
+    for n, ref in g["grad_rows"].items():
+        assert (sd[n].grad[:4] - ref).norm().item() <= 1e-3 * ref.norm().item() + 1e-9, n
+    # parameters the reference leaves without gradient
+    assert g["grad_norms"]["disc_grammar_embedding.weight"] is None
+    assert sd["disc_grammar_embedding.weight"].grad is None
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_oracle_greedy_generation(path):
+    from oracle import sct_oracle as O
+
+    g = load_golden(path)
+    sd = O.synth_state_dict(g["shapes"], g["seed"])
+    batch = O.make_batch(**g["batch_args"])
+    toks, _ = O.generate_greedy(sd, g["cfg"], batch, g["greedy_tokens"].shape[1] - 1)
+    assert torch.equal(toks, g["greedy_tokens"])  # token ids: bit-exact
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_state_dict_is_drop_in(path):
+    """Same keys and shapes as the reference's state_dict (recorded in the fixture), strict load works."""
+    from oracle import sct_oracle as O
+    from sct_gan_b200 import SmartContractTransformer
+
+    g = load_golden(path)
+    m = SmartContractTransformer(**g["cfg"])
+    mine = {k: list(v.shape) for k, v in m.state_dict().items()}
+    assert mine == g["shapes"]
+    m.load_state_dict(O.synth_state_dict(g["shapes"], g["seed"]), strict=True)
+    assert m.path_embedding is m.ast_embedding
+    assert [n for n, _ in m.named_buffers()] == ["pos_encoder.pe"]
+
+
+def test_default_constructor_matches_reference_inventory():
+    """312 state_dict keys / 262,601,074 parameters with use_gan=True; every 1-D parameter is
+    zero-initialised except the line head's output bias (model.py:290-294, 369)."""
+    from sct_gan_b200 import SmartContractTransformer
+
+    m = SmartContractTransformer(use_gan=True)
+    assert len(m.state_dict()) == 312
+    assert sum(p.numel() for p in m.parameters()) == 262_601_074
+    for n, p in m.named_parameters():
+        if p.dim() == 1 and n != "line_vulnerability_head_1.6.bias":
+            assert float(p.abs().max()) == 0.0, n
+    assert torch.allclose(m.line_vulnerability_head_1[6].bias, torch.full((8,), -0.2))
+    for p in m.feature_fusion.parameters():  # the +-1 clamp hook of model.py:285-286
+        assert p._backward_hooks is not None and len(p._backward_hooks) == 1
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 8, dtype=torch.long))  # no CPU fallback
+
+
+def test_param_groups_match_reference_rules():
+    """train.py:518-527 -> 245 / 22 / 22 / 21 tensors."""
+    from oracle import sct_oracle as O
+    from sct_gan_b200 import SmartContractTransformer
+    from sct_gan_b200.trainer import param_group_of
+
+    m = SmartContractTransformer(num_encoder_layers=1, num_decoder_layers=1, dim_feedforward=64, vocab_size=64,
+                                 max_length=16, use_gan=True)
+    names = [n for n, _ in m.named_parameters()]
+    mine = [param_group_of(n, True) for n in names]
+    theirs = [O.param_groups(names)[n][0] for n in names]
+    assert mine == theirs
+    full = SmartContractTransformer(use_gan=True)
+    cnt = [0, 0, 0, 0]
+    for n, _ in full.named_parameters():
+        cnt[param_group_of(n, True)] += 1
+    assert cnt == [245, 22, 22, 21]
+
+
+def test_vectorised_spatial_penalty_matches_loop():
+    """trainer.spatial_penalty (O(N)) against the oracle's restated B*1024-iteration loop (train.py:174-245)."""
+    from oracle import sct_oracle as O
+    from sct_gan_b200.trainer import spatial_aware_focal_loss, spatial_penalty
+
+    g = torch.Generator().manual_seed(5)
+    n, C = 2 * 1024, 8
+    pred = torch.randn(n, C, generator=g, dtype=torch.float64)
+    target = (torch.rand(n, C, generator=g) < 0.02).double()
+    t2l = (torch.arange(1024) // 7).repeat(2)
+    a = spatial_penalty(pred, target, t2l)
+    b = O.spatial_penalty(pred, target, t2l)
+    assert (a - b).abs().max().item() < 1e-12
+    assert abs(float(spatial_aware_focal_loss(pred, target, t2l, 0.25, 2.0, 0.2))
+               - float(O.spatial_focal_loss(pred, target, t2l, 0.25, 2.0, 0.2))) < 1e-12
+    # S != 1024: the reference silently returns zeros (train.py:187-216)
+    assert spatial_penalty(pred, target, t2l[:100]).abs().max().item() == 0.0
+    assert O.spatial_penalty(pred, target, t2l[:100]).abs().max().item() == 0.0
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    """The shared library loads without a GPU and exports exactly what include/sct_b200.h declares."""
+    from sct_gan_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "sct_b200.h")).read()
+    declared = set(re.findall(r"\b(sct_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.exported_symbols())
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().sct_version() == 100
+
+
+def test_line_heads_vectorised_match_oracle_loops():
+    """model._line_heads (batched PyTorch, runs on CPU) vs the oracle's restated loops (model.py:480-759)."""
+    from oracle import sct_oracle as O
+    from sct_gan_b200 import SmartContractTransformer
+
+    g = load_golden(GOLDEN[0])
+    cfg = g["cfg"]
+    m = SmartContractTransformer(**cfg).eval()
+    sd = O.synth_state_dict(g["shapes"], g["seed"])
+    m.load_state_dict(sd)
+    gen = torch.Generator().manual_seed(3)
+    memory = torch.randn(2, 40, cfg["d_model"], generator=gen)
+    t2l = torch.tensor([[0] * 5 + [1] * 10 + [3] * 20 + [4] * 5, [0] * 20 + [2] * 10 + [6] * 10])  # empty lines 2/5, 1/3-5
+    with torch.no_grad():
+        mine = m._line_heads(memory, t2l)
+        ref = O.line_heads(sd, cfg, memory, t2l, torch.float32)
+        assert (mine - ref).abs().max().item() < 1e-4
+        mine_c = m._contract_heads(memory)
+        ref_c = O.contract_heads(sd, cfg, memory, torch.float32)
+        assert (mine_c - ref_c).abs().max().item() < 1e-4
+        assert (m._line_heads(memory, None) - O.line_heads(sd, cfg, memory, None, torch.float32)).abs().max().item() < 1e-4
