@@ -43,15 +43,67 @@ struct AttnParams {
   float* dvec;           // [B, H, Lq]  D = rowsum(dO * O)
   __nv_bfloat16* o;      // forward output
   __nv_bfloat16 *dq, *dk, *dv;
-  uint64_t seed, offset;
-  uint32_t thresh16;
+  uint32_t key0, key1;   // dropout stream key, mixed from (seed, offset) on the host
+  uint32_t tmask[16];    // bit i of the 16-bit drop threshold, spread to a full word
+  uint32_t thresh16;     // 0 = dropout off
   float inv_keep;
 };
 
-__device__ __forceinline__ float drop_mult(const AttnParams& p, uint64_t idx) {
-  if (p.thresh16 == 0) return 1.f;
-  const uint32_t h = rng_pair(p.seed, p.offset, idx);
-  return ((h & 0xFFFFu) >= p.thresh16) ? p.inv_keep : 0.f;
+// ---- attention-probability dropout -------------------------------------------------------------
+// keep(b,h,q,k) <=> u16(b,h,q,k) >= thresh16.  The 16-bit uniforms of 32 consecutive keys of one query
+// row are generated bit-sliced: 16 cheap xorshift-multiply words off one strong hash of (stream key,
+// b*H+h, q, k/32); a 16-step bitwise comparator (one LOP3 per word) then yields the 32 keep bits at
+// once, ~2 integer instructions per element instead of one full hash each.  Forward and the dQ kernel
+// own query rows and use the word directly; the dK/dV kernel owns key rows and transposes 32x32 bit
+// tiles inside the warp, so all three regenerate the identical mask.
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
+__device__ __forceinline__ uint32_t keep_word(const AttnParams& p, uint32_t bh, uint32_t q, uint32_t kb) {
+  if (p.thresh16 == 0) return 0xFFFFFFFFu;
+  uint32_t x = fmix32(((bh * (uint32_t)p.Lq + q) * 0x9E3779B1u) ^ p.key0);
+  x = fmix32(x ^ (kb * 0x85EBCA77u) ^ p.key1);
+  uint32_t lt = 0u;  // lt bit = 1 <=> u16 < thresh16 (LSB-first ripple comparison)
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    x = (x ^ (x >> 15)) * 0x2C1B3C6Du;
+    const uint32_t nw = ~x, tm = p.tmask[i];
+    lt = (nw & lt) | (tm & (nw | lt));
+  }
+  return ~lt;
+}
+// 32x32 bit-matrix transpose across the warp: in: lane L holds row L; out: lane L holds column L.
+__device__ __forceinline__ uint32_t warp_bit_transpose(uint32_t x, int lane) {
+#pragma unroll
+  for (int sft = 16; sft > 0; sft >>= 1) {
+    const uint32_t m = sft == 16 ? 0x0000FFFFu : sft == 8 ? 0x00FF00FFu : sft == 4 ? 0x0F0F0F0Fu
+                       : sft == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, sft);
+    x = (lane & sft) ? (((y >> sft) & m) | (x & ~m)) : ((x & m) | ((y & m) << sft));
+  }
+  return x;
+}
+// last unmasked key + 1 of batch row b (keys past it are all masked: their tiles are skipped)
+__device__ __forceinline__ int kv_extent(const AttnParams& p, int b, int* smem_slot) {
+  if (p.kpm == nullptr) return p.Lk;
+  if (threadIdx.x == 0) *smem_slot = 0;
+  __syncthreads();
+  int loc = 0;
+  for (int i = threadIdx.x; i < p.Lk; i += blockDim.x)
+    if (p.kpm[(long long)b * p.Lk + i] == 0) loc = i + 1;
+  loc = max(loc, __shfl_xor_sync(0xffffffffu, loc, 16));
+  loc = max(loc, __shfl_xor_sync(0xffffffffu, loc, 8));
+  loc = max(loc, __shfl_xor_sync(0xffffffffu, loc, 4));
+  loc = max(loc, __shfl_xor_sync(0xffffffffu, loc, 2));
+  loc = max(loc, __shfl_xor_sync(0xffffffffu, loc, 1));
+  if ((threadIdx.x & 31) == 0) atomicMax(smem_slot, loc);
+  __syncthreads();
+  return *smem_slot;
 }
 
 // K-major descriptor of a swizzle-64 operand tile ([rows x 96], 3 blocks), k16 step `k` (0..5).
@@ -90,12 +142,16 @@ __device__ __forceinline__ void load_tile(const CUtensorMap* m, uint32_t bar, ui
 }
 
 // =================================================================================================
-// forward: one CTA (128 threads) per (q-tile, head, batch); two CTAs co-reside per SM so one CTA's
-// softmax overlaps the other's MMAs.
+// forward: one CTA (256 threads) per (q-tile, head, batch); two CTAs co-reside per SM so one CTA's
+// softmax overlaps the other's MMAs.  Thread (r, hf) owns columns [64hf, 64hf+64) of query row r: the
+// S tile is read from TMEM exactly once (64 registers), the two halves of a row exchange their partial
+// max through shared memory.  The running max is only raised when it grows by more than 2^8 (the
+// probabilities then stay below 2^8, harmless in fp32/bf16), so the O accumulator in TMEM is almost
+// never rescaled after the first tile.  Key tiles past the last unmasked key are skipped.
 // =================================================================================================
-constexpr int FWD_SMEM = 1024 + 3 * QKV_BYTES + P_BYTES + 1024;
+constexpr int FWD_SMEM = 1024 + 3 * QKV_BYTES + P_BYTES + 4096;
 
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(256, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -103,18 +159,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t sQ = base, sK = sQ + QKV_BYTES, sV = sK + QKV_BYTES, sP = sV + QKV_BYTES;
   const uint32_t aux = sP + P_BYTES;
-  float* bias_s = reinterpret_cast<float*>(gen + (aux - base));  // 128 floats
-  const uint32_t bar_q = aux + 512, bar_k = aux + 520, bar_v = aux + 528, bar_mma = aux + 536;
-  const uint32_t tmem_ptr_addr = aux + 544;
+  float* bias_s = reinterpret_cast<float*>(gen + (aux - base));  // [128]
+  float* mx_s = bias_s + 128;                                     // [2][128]
+  float* l_s = mx_s + 256;                                        // [2][128]
+  const uint32_t bar_q = aux + 3072, bar_k = aux + 3080, bar_v = aux + 3088, bar_mma = aux + 3096;
+  const uint32_t tmem_ptr_addr = aux + 3104;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen + (tmem_ptr_addr - base));
+  int* ext_slot = reinterpret_cast<int*>(gen + (aux + 3112 - base));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, hf = warp >> 2;
   const int nq_tiles = gridDim.x;
   const int qt = nq_tiles - 1 - blockIdx.x;  // heavy (late) causal tiles first
   const int h = blockIdx.y, b = blockIdx.z;
   const int q0 = qt * TILE;
-  int nkv = (p.Lk + TILE - 1) / TILE;
-  if (p.causal) nkv = min(nkv, qt + 1);
 
   if (tid == 0) {
     mbar_init(bar_q, 1);
@@ -124,17 +182,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_ptr_addr, 256);
+  const int kv_end = kv_extent(p, b, ext_slot);  // contains __syncthreads when a mask is given
+  int nkv = (kv_end + TILE - 1) / TILE;
+  if (p.causal) nkv = min(nkv, qt + 1);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_gen;
   const uint32_t tS = tmem, tO = tmem + 128;
-  const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
 
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
   constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, false, true);
 
-  if (tid == 0) {
+  if (tid == 0 && nkv > 0) {
     mbar_expect_tx(bar_q, QKV_BYTES);
     load_tile(&tmQ, bar_q, sQ, h * DH, q0, b);
     mbar_expect_tx(bar_k, QKV_BYTES);
@@ -149,20 +210,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_commit(bar_mma);
   }
 
-  const int r = tid;           // local q row
+  const int r = quad * 32 + lane;  // local q row
   const int q = q0 + r;
+  const int c_base = hf * 64;
+  const uint32_t bh = (uint32_t)(b * p.H + h);
   float m_run = -INFINITY, l_run = 0.f;
-  const uint64_t drop_row = ((uint64_t)(b * p.H + h) * p.Lq + (uint64_t)q) * (uint64_t)p.Lk;
 
   for (int j = 0; j < nkv; ++j) {
     const int kv0 = j * TILE;
-    {
+    bool masked = false;
+    if (tid < TILE) {
       const int kv = kv0 + tid;
-      bool masked = kv >= p.Lk;
+      masked = kv >= p.Lk;
       if (!masked && p.kpm) masked = p.kpm[(long long)b * p.Lk + kv] != 0;
       bias_s[tid] = masked ? -INFINITY : 0.f;
     }
-    __syncthreads();
+    const int any_mask = __syncthreads_or(masked ? 1 : 0);
     mbar_wait(bar_mma, j & 1);  // S_j ready; P V_{j-1} retired
     tc_fence_after();
     if (tid == 0) {
@@ -175,48 +238,55 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         load_tile(&tmV, bar_v, sV, h * DH, kv0, b);
       }
     }
+    __syncwarp();
     const bool diag = p.causal && (j == qt);
-    // pass 1: row max
-    float mx = -INFINITY;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t rr[32];
-      tmem_ld32(tS + lane_sel + c * 32, rr);
+    uint32_t sr[64];
+    {
+      uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sr[0]);
+      uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sr[32]);
+      tmem_ld32(tS + lane_sel + c_base, lo);
+      tmem_ld32(tS + lane_sel + c_base + 32, hi);
       tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float t = __uint_as_float(rr[i]) * p.scale_log2 + bias_s[c * 32 + i];
-        if (diag && (c * 32 + i > r)) t = -INFINITY;
-        mx = fmaxf(mx, t);
-      }
     }
-    const float m_new = fmaxf(m_run, mx);
-    const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-    const float alpha = exp2f(m_run - m_use);
-    // pass 2: probabilities -> bf16 P tile in smem (dropout applied to the stored copy only)
+    if (any_mask) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) sr[i] = __float_as_uint(__uint_as_float(sr[i]) + bias_s[c_base + i]);
+    }
+    if (diag) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i)
+        if (c_base + i > r) sr[i] = __float_as_uint(-INFINITY);
+    }
+    float mx = __uint_as_float(sr[0]);
+#pragma unroll
+    for (int i = 1; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sr[i]));
+    mx_s[hf * 128 + r] = mx;
+    named_bar_sync(1, 256);
+    mx = fmaxf(mx, mx_s[(hf ^ 1) * 128 + r]);
+    const float m_new = mx * p.scale_log2;  // scale > 0
+    float m_next = m_run;
+    if (m_run == -INFINITY || m_new > m_run + 8.0f) m_next = fmaxf(m_run, m_new);
+    const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_next);
+    const float m_eff = (m_next == -INFINITY) ? 0.f : m_next;
     float rs = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t rr[32];
-      tmem_ld32(tS + lane_sel + c * 32, rr);
-      tmem_ld_wait();
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb) {
+      const uint32_t kw = keep_word(p, bh, (uint32_t)q, (uint32_t)((kv0 + c_base) >> 5) + kb);
       float pv[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        float t = __uint_as_float(rr[i]) * p.scale_log2 + bias_s[c * 32 + i];
-        if (diag && (c * 32 + i > r)) t = -INFINITY;
-        const float e = exp2f(t - m_use);
+        const float e = exp2f(fmaf(__uint_as_float(sr[kb * 32 + i]), p.scale_log2, -m_eff));
         rs += e;
-        pv[i] = e * drop_mult(p, drop_row + (uint64_t)(kv0 + c * 32 + i));
+        pv[i] = (kw & (1u << i)) ? e : 0.f;
       }
-      store_row32_sw128(sP, r, c * 32, pv);
+      store_row32_sw128(sP, r, c_base + kb * 32, pv);
     }
     l_run = l_run * alpha + rs;
-    m_run = m_new;
-    // rescale the running output when any row of this warp moved its max
-    if (j > 0 && !__all_sync(0xffffffffu, alpha == 1.0f)) {
+    m_run = m_next;
+    // rescale the running output when some row of this warp raised its max (rare after tile 0)
+    if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll 1
-      for (int c = 0; c < 3; ++c) {
+      for (int c = (hf == 0 ? 0 : 2); c < (hf == 0 ? 2 : 3); ++c) {
         uint32_t rr[32];
         tmem_ld32(tO + lane_sel + c * 32, rr);
         tmem_ld_wait();
@@ -244,18 +314,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       tc_commit(bar_mma);
     }
+    __syncwarp();
   }
-  mbar_wait(bar_mma, nkv & 1);
-  tc_fence_after();
+  if (nkv > 0) {
+    mbar_wait(bar_mma, nkv & 1);
+    tc_fence_after();
+  }
+  l_s[hf * 128 + r] = l_run;
+  __syncthreads();
   {
-    const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
+    const float l_tot = l_s[r] + l_s[128 + r];
+    const float inv_l = l_tot > 0.f ? p.inv_keep / l_tot : 0.f;
     const bool valid = q < p.Lq;
     __nv_bfloat16* dst = p.o + ((long long)b * p.Lq + q) * p.ldo + h * DH;
 #pragma unroll 1
-    for (int c = 0; c < 3; ++c) {
+    for (int c = (hf == 0 ? 0 : 2); c < (hf == 0 ? 2 : 3); ++c) {
       uint32_t rr[32];
-      tmem_ld32(tO + lane_sel + c * 32, rr);
-      tmem_ld_wait();
+      if (nkv > 0) {
+        tmem_ld32(tO + lane_sel + c * 32, rr);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rr[i] = 0u;
+      }
       if (valid) {
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
@@ -268,8 +349,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
-    if (valid && p.lse2)
-      p.lse2[((long long)b * p.H + h) * p.Lq + q] = l_run > 0.f ? (m_run + log2f(l_run)) : INFINITY;
+    if (valid && hf == 0 && p.lse2)
+      p.lse2[((long long)b * p.H + h) * p.Lq + q] = l_tot > 0.f ? (m_run + log2f(l_tot)) : INFINITY;
   }
   tc_fence_before();
   __syncthreads();

@@ -191,35 +191,39 @@ small_linear_bwd_w_kernel(const float* __restrict__ dyf, const __nv_bfloat16* __
   if (lane == 0 && db) db[n] = sb;
 }
 
-// dx[m, :] = sum_n dy[m, n] * w[n, :]
+// dx[m, 128j .. 128j+127] = sum_n dy[m, n] * w[n, 128j ..]: one block per (m, 128-column chunk); the 8 warps
+// split the n loop (independent 512-byte row reads, 4 in flight per warp) and meet in shared memory.
 template <int NV>
 __global__ void __launch_bounds__(256)
 small_linear_bwd_x_kernel(const float* __restrict__ dyf, const __nv_bfloat16* __restrict__ dyb,
                           const float* __restrict__ w, float* __restrict__ dxf,
                           __nv_bfloat16* __restrict__ dxb, int M, int N) {
   constexpr int K = NV * 128;
-  const int lane = threadIdx.x & 31;
-  const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (m >= M) return;
-  float4 acc[NV];
-#pragma unroll
-  for (int j = 0; j < NV; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int n = 0; n < N; ++n) {
+  __shared__ float4 red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int m = blockIdx.x, j = blockIdx.y;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int n = warp; n < N; n += 8) {
     const float g = dyf ? dyf[(long long)m * N + n] : __bfloat162float(dyb[(long long)m * N + n]);
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const float4 wv = *reinterpret_cast<const float4*>(w + (long long)n * K + (j * 32 + lane) * 4);
-      acc[j].x += g * wv.x; acc[j].y += g * wv.y; acc[j].z += g * wv.z; acc[j].w += g * wv.w;
-    }
+    const float4 wv = *reinterpret_cast<const float4*>(w + (long long)n * K + (j * 32 + lane) * 4);
+    acc.x += g * wv.x; acc.y += g * wv.y; acc.z += g * wv.z; acc.w += g * wv.w;
   }
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    float4 s = red[0][lane];
 #pragma unroll
-  for (int j = 0; j < NV; ++j) {
+    for (int q = 1; q < 8; ++q) {
+      const float4 t = red[q][lane];
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
     const long long o = (long long)m * K + (j * 32 + lane) * 4;
-    if (dxf) *reinterpret_cast<float4*>(dxf + o) = acc[j];
+    if (dxf) *reinterpret_cast<float4*>(dxf + o) = s;
     if (dxb) {
       uint2 u;
-      u.x = pack_bf16(acc[j].x, acc[j].y);
-      u.y = pack_bf16(acc[j].z, acc[j].w);
+      u.x = pack_bf16(s.x, s.y);
+      u.y = pack_bf16(s.z, s.w);
       *reinterpret_cast<uint2*>(dxb + o) = u;
     }
   }
@@ -348,8 +352,7 @@ int32_t sct_small_linear_bwd(const float* dy_f32, const void* dy_bf16, const flo
     SCT_LAUNCH_CHECK();
   }
   if (dx_f32 || dx_bf16) {
-    const int blocks = (int)((M + 7) / 8);
-    DISPATCH_K(K, (small_linear_bwd_x_kernel<NV><<<blocks, 256, 0, st>>>(
+    DISPATCH_K(K, (small_linear_bwd_x_kernel<NV><<<dim3((unsigned)M, NV), 256, 0, st>>>(
                       dy_f32, (const __nv_bfloat16*)dy_bf16, w, dx_f32, (__nv_bfloat16*)dx_bf16, (int)M, (int)N)));
     SCT_LAUNCH_CHECK();
   }

@@ -483,24 +483,55 @@ gelu_dropout_bwd_kernel(const __nv_bfloat16* __restrict__ g_h, const __nv_bfloat
 }
 
 // =================================================================================================
-// colsum: out[n] += sum_m X[m, n]   (bias gradients), bf16 in, fp32 atomic accumulate
+// colsum: out[n] += scale * sum_m X[m, n]   (bias gradients), bf16 in, fp32 accumulate.
+// grid = (row splits, column slabs of 768); a warp streams whole rows of its slab (3 x 16 B per lane,
+// 1.5 kB contiguous per warp access), 8 warps of a block own interleaved rows, partial sums meet in
+// shared memory and leave as ONE atomicAdd per column per block.
 // =================================================================================================
+constexpr int kColsumSlab = 768;
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* __restrict__ out, int M,
                    int N, int rows_per_block, float scale) {
+  __shared__ float red[8][kColsumSlab];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.y * kColsumSlab;
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(r0 + rows_per_block, M);
-  for (int c8 = threadIdx.x; c8 * 8 < N; c8 += blockDim.x) {
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int r = r0; r < r1; ++r) {
-      const uint4 u = *reinterpret_cast<const uint4*>(x + (long long)r * ld + c8 * 8);
-      const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
-      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
-      acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
-    }
+  float acc[3][8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (c8 * 8 + k < N) atomicAdd(out + c8 * 8 + k, acc[k] * scale);
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[j][k] = 0.f;
+  bool live[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) live[j] = c0 + (j * 32 + lane) * 8 < N;  // N % 8 == 0
+#pragma unroll 4
+  for (int r = r0 + warp; r < r1; r += 8) {
+    const __nv_bfloat16* row = x + (long long)r * ld + c0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (live[j]) {
+        const uint4 u = *reinterpret_cast<const uint4*>(row + (j * 32 + lane) * 8);
+        const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+        acc[j][0] += a.x; acc[j][1] += a.y; acc[j][2] += b.x; acc[j][3] += b.y;
+        acc[j][4] += c.x; acc[j][5] += c.y; acc[j][6] += d.x; acc[j][7] += d.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    float* dst = &red[warp][(j * 32 + lane) * 8];
+    *reinterpret_cast<float4*>(dst) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < kColsumSlab; c += 256) {
+    if (c0 + c < N) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w][c];
+      atomicAdd(out + c0 + c, s * scale);
+    }
   }
 }
 
@@ -712,12 +743,15 @@ int32_t sct_colsum_bf16(const void* x, int64_t ld, float* out, int64_t M, int64_
                         void* stream) {
   SCT_CHECK(x && out, "null pointer");
   SCT_CHECK(ld % 8 == 0 && N % 8 == 0, "colsum needs ld and N multiples of 8 (ld=%lld N=%lld)", (long long)ld, (long long)N);
-  int blocks = num_sms() * 4;
-  int rpb = (int)((M + blocks - 1) / blocks);
-  if (rpb < 8) rpb = 8;
-  blocks = (int)((M + rpb - 1) / rpb);
-  colsum_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, out, (int)M,
-                                                             (int)N, rpb, scale);
+  SCT_CHECK(M > 0 && N > 0, "empty input");
+  const int slabs = (int)((N + kColsumSlab - 1) / kColsumSlab);
+  int splits = (2 * num_sms() + slabs - 1) / slabs;
+  int rpb = (int)((M + splits - 1) / splits);
+  if (rpb < 64) rpb = 64;
+  splits = (int)((M + rpb - 1) / rpb);
+  dim3 grid((unsigned)splits, (unsigned)slabs);
+  colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, out, (int)M,
+                                                            (int)N, rpb, scale);
   SCT_LAUNCH_CHECK();
   return 0;
 }

@@ -271,11 +271,23 @@ class SmartContractTransformer(nn.Module):
         return ops.small_linear(x, sh[4].weight, sh[4].bias)
 
     # ----------------------------------------------------------------- PyTorch (out-of-scope) heads
-    def _contract_heads(self, memory):
-        """model.py:455-476 (contract-level logits; [B, .] rows, PyTorch)."""
-        q = memory.mean(dim=1, keepdim=True)
-        att, _ = self.contract_vuln_attention(query=q, key=memory, value=memory, need_weights=False)
-        rep = torch.cat([memory.mean(dim=1), att.squeeze(1)], dim=-1)
+    def _contract_heads(self, memory, mem_b=None):
+        """model.py:455-476 (contract-level logits).  On the CUDA path the attention of the mean query over the
+        [B, S, d] memory uses the same kernels as the hot path (K/V projection = tcgen05 GEMM on the bf16
+        memory, K3 with Lq = 1); the [B, .] MLPs stay in PyTorch."""
+        B, S, d = memory.shape
+        att = self.contract_vuln_attention
+        if mem_b is None or not memory.is_cuda:
+            q = memory.mean(dim=1, keepdim=True)
+            a, _ = att(query=q, key=memory, value=memory, need_weights=False)
+            rep = torch.cat([memory.mean(dim=1), a.squeeze(1)], dim=-1)
+        else:
+            avg = ops.seq_mean(memory.reshape(B * S, d), None, B, S)
+            q = ops.small_linear(avg, att.in_proj_weight[:d], att.in_proj_bias[:d], True)
+            kv = self._lin_rows(mem_b, att.in_proj_weight, att.in_proj_bias, d, 3 * d)
+            o = ops.cross_attention(q, kv, B, self.nhead, 1, S, None, att.dropout if self.training else 0.0)
+            a = ops.small_linear(o, att.out_proj.weight, att.out_proj.bias)
+            rep = torch.cat([avg, a], dim=-1)
         return self.contract_vulnerability_head(self.contract_feature_aggregation(rep))
 
     def _line_position_encoding(self, n_lines, device):
@@ -347,7 +359,7 @@ class SmartContractTransformer(nn.Module):
         memory = mem.view(B, S, d)
 
         if compute_vuln_heads:
-            contract_logits = self._contract_heads(memory)
+            contract_logits = self._contract_heads(memory, mem_b)
             line_logits = self._line_heads(memory, token_to_line)
         else:
             contract_logits = line_logits = None
