@@ -418,7 +418,9 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int kv0 = jt * TILE;
   const int nq_tiles = (p.Lq + TILE - 1) / TILE;
   const int i_begin = p.causal ? jt : 0;
-  const int n_it = nq_tiles - i_begin;
+  int* ext_slot = reinterpret_cast<int*>(gen + (aux + 2088 - base));
+  // a key tile that lies entirely past the last unmasked key contributes nothing: dK = dV = 0
+  const int n_it = (kv0 < kv_extent(p, b, ext_slot)) ? nq_tiles - i_begin : 0;
 
   if (tid == 0) {
     mbar_init(bar_kv, 1);
@@ -486,24 +488,32 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       load_tile(&tmdO, nb, nQ + QKV_BYTES, h * DH, q0 + TILE, b);
     }
     const bool diag = p.causal && (qi == jt);
+    const uint32_t bh = (uint32_t)(b * p.H + h);
 #pragma unroll 1
     for (int cc = 0; cc < 2; ++cc) {
       const int c0 = half * 64 + cc * 32;
+      // keep bits of (q = q0+c0+i, k = this thread's key row) for i = 0..31: lane L makes the word of query
+      // q0+c0+L over this warp's 32 keys, then the warp transposes the 32x32 bit tile
+      uint32_t kw = keep_word(p, bh, (uint32_t)(q0 + c0 + lane), (uint32_t)((kv0 >> 5) + quad));
+      if (p.thresh16 != 0) kw = warp_bit_transpose(kw, lane);
       uint32_t rs[32], rp[32];
       tmem_ld32(tST + lane_sel + c0, rs);
       tmem_ld32(tDPT + lane_sel + c0, rp);
       tmem_ld_wait();
       float pd[32], ds[32];
+      if (row_valid) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int c = c0 + i;
-        float pr = 0.f;
-        if (row_valid && !(diag && r > c))
-          pr = exp2f(__uint_as_float(rs[i]) * p.scale_log2 - lse_s[s * 128 + c]);
-        const float dm = drop_mult(
-            p, (((uint64_t)(b * p.H + h) * p.Lq + (uint64_t)(q0 + c)) * (uint64_t)p.Lk) + (uint64_t)kv);
-        pd[i] = pr * dm;
-        ds[i] = pr * (__uint_as_float(rp[i]) * dm - dv_s[s * 128 + c]);
+        for (int i = 0; i < 32; ++i) {
+          const int c = c0 + i;
+          float pr = exp2f(fmaf(__uint_as_float(rs[i]), p.scale_log2, -lse_s[s * 128 + c]));
+          if (diag && r > c) pr = 0.f;
+          const float dm = (kw & (1u << i)) ? p.inv_keep : 0.f;
+          pd[i] = pr * dm;
+          ds[i] = pr * fmaf(__uint_as_float(rp[i]), dm, -dv_s[s * 128 + c]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) pd[i] = ds[i] = 0.f;
       }
       store_row32_sw128(sPT, r, c0, pd);
       store_row32_sw128(sDST, r, c0, ds);
@@ -586,7 +596,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int qt = nq_tiles - 1 - blockIdx.x;
   const int h = blockIdx.y, b = blockIdx.z;
   const int q0 = qt * TILE;
-  int nkv = (p.Lk + TILE - 1) / TILE;
+  int* ext_slot = reinterpret_cast<int*>(gen + (aux + 552 - base));
+  int nkv = (kv_extent(p, b, ext_slot) + TILE - 1) / TILE;  // key tiles past the last unmasked key are skipped
   if (p.causal) nkv = min(nkv, qt + 1);
 
   if (tid == 0) {
@@ -609,12 +620,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const long long stat_o = ((long long)b * p.H + h) * p.Lq + q;
   const float lse2 = q < p.Lq ? p.lse2[stat_o] : INFINITY;
   const float dvec = q < p.Lq ? p.dvec[stat_o] : 0.f;
-  const uint64_t drop_row = ((uint64_t)(b * p.H + h) * p.Lq + (uint64_t)q) * (uint64_t)p.Lk;
+  const uint32_t bh = (uint32_t)(b * p.H + h);
 
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
   constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, false, true);
 
-  if (tid == 0) {
+  if (tid == 0 && nkv > 0) {
     mbar_expect_tx(bar_q, 2 * QKV_BYTES);
     load_tile(&tmQ, bar_q, sQ, h * DH, q0, b);
     load_tile(&tmdO, bar_q, sdO, h * DH, q0, b);
@@ -637,13 +648,14 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int k = 0; k < 6; ++k) tc_mma_bf16(tDP, desc_k64(sdO, k), desc_k64(sV, k), idesc_s, k > 0);
       tc_commit(bar_mma);
     }
+    bool masked = false;
     if (tid < 128) {
       const int kv = kv0 + tid;
-      bool masked = kv >= p.Lk;
+      masked = kv >= p.Lk;
       if (!masked && p.kpm) masked = p.kpm[(long long)b * p.Lk + kv] != 0;
       bias_s[tid] = masked ? -INFINITY : 0.f;
     }
-    __syncthreads();
+    const int any_mask = __syncthreads_or(masked ? 1 : 0);
     mbar_wait(bar_mma, j & 1);
     tc_fence_after();
     if (tid == 0 && j + 1 < nkv) {
@@ -657,6 +669,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll 1
     for (int cc = 0; cc < 2; ++cc) {
       const int c0 = half * 64 + cc * 32;
+      const uint32_t kw = keep_word(p, bh, (uint32_t)q, (uint32_t)((kv0 + c0) >> 5));
       uint32_t rs[32], rp[32];
       tmem_ld32(tS + lane_sel + c0, rs);
       tmem_ld32(tDP + lane_sel + c0, rp);
@@ -665,11 +678,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const int c = c0 + i;
-        float t = __uint_as_float(rs[i]) * p.scale_log2 + bias_s[c] - lse2;
-        if (diag && c > r) t = -INFINITY;
-        const float pr = exp2f(t);
-        const float dm = drop_mult(p, drop_row + (uint64_t)(kv0 + c));
-        ds[i] = pr * (__uint_as_float(rp[i]) * dm - dvec);
+        float pr = exp2f(fmaf(__uint_as_float(rs[i]), p.scale_log2, -lse2));
+        if (any_mask) pr = (bias_s[c] != 0.f) ? 0.f : pr;
+        if (diag && c > r) pr = 0.f;
+        const float dm = (kw & (1u << i)) ? p.inv_keep : 0.f;
+        ds[i] = pr * fmaf(__uint_as_float(rp[i]), dm, -dvec);
       }
       store_row32_sw128(sDS, r, c0, ds);
     }
@@ -684,15 +697,22 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (j + 1 == nkv) tc_commit(bar_mma);
     }
   }
-  mbar_wait(bar_mma, nkv & 1);
-  tc_fence_after();
+  if (nkv > 0) {
+    mbar_wait(bar_mma, nkv & 1);
+    tc_fence_after();
+  }
   {
     __nv_bfloat16* dst = p.dq + ((long long)b * p.Lq + q) * p.ldq_out + h * DH;
 #pragma unroll 1
     for (int c = half * 2; c < (half == 0 ? 2 : 3); ++c) {
       uint32_t rr[32];
-      tmem_ld32(tDQ + lane_sel + c * 32, rr);
-      tmem_ld_wait();
+      if (nkv > 0) {
+        tmem_ld32(tDQ + lane_sel + c * 32, rr);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rr[i] = 0u;
+      }
       if (q < p.Lq) {
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
@@ -728,10 +748,20 @@ int fill_params(AttnParams& p, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int
   p.scale = scale;
   p.scale_log2 = scale * kLog2e;
   p.kpm = kpm;
-  p.seed = seed; p.offset = offset;
+  {
+    // stream key: splitmix64 of (seed, offset)
+    uint64_t z = seed * 0x9E3779B97F4A7C15ull + offset * 0xD1B54A32D192ED03ull + 0x2545F4914F6CDD1Dull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    p.key0 = (uint32_t)z;
+    p.key1 = (uint32_t)(z >> 32);
+  }
   double t = (double)p_drop * 65536.0 + 0.5;
   p.thresh16 = p_drop > 0.f ? (uint32_t)(t > 65535.0 ? 65535.0 : t) : 0u;
-  p.inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+  for (int i = 0; i < 16; ++i) p.tmask[i] = ((p.thresh16 >> i) & 1u) ? 0xFFFFFFFFu : 0u;
+  // the scale uses the realised keep probability (thresh16 / 65536 is p_drop to within 2^-17)
+  p.inv_keep = p_drop > 0.f ? (float)(65536.0 / (65536.0 - (double)p.thresh16)) : 1.0f;
   p.lse2 = nullptr; p.dvec = nullptr; p.o = nullptr; p.dq = p.dk = p.dv = nullptr;
   p.ldo = p.ldq_out = p.ldkv_out = 0;
   return 0;
@@ -779,7 +809,7 @@ int32_t sct_attn_fwd(const void* q, int64_t ldq, const void* k, const void* v, i
     attr = true;
   }
   dim3 grid((unsigned)((Lq + TILE - 1) / TILE), (unsigned)H, (unsigned)B);
-  attn_fwd_kernel<<<grid, 128, FWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  attn_fwd_kernel<<<grid, 256, FWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
   SCT_LAUNCH_CHECK();
   return 0;
 }

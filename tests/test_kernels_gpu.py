@@ -394,3 +394,59 @@ def test_gan_loss(cuda_dev, shift):
     (0.05 * d + 0.02 * adv).backward()
     dz = kn.gan_loss_bwd(z.detach(), out4[2:3], torch.tensor([0.05], device="cuda"), torch.tensor([0.02], device="cuda"))
     assert rel_l2(dz, z.grad) < 1e-4
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_attention_dropout_mask_fwd_bwd_identical(cuda_dev, causal):
+    """The three attention kernels regenerate the same dropout mask: extract it from the forward (V = identity
+    blocks make O = dropout(P)), then check dQ/dK/dV against PyTorch autograd with that explicit mask."""
+    from sct_gan_b200 import kernels as kn
+
+    B, H, dh, L, p_drop = 2, 8, 96, 192, 0.3
+    d = H * dh
+    g = torch.Generator(device="cuda").manual_seed(17)
+    q2 = (torch.randn(B * L, d, device="cuda", generator=g) * 0.5).to(BF16)
+    kv = (torch.randn(B * L, 2 * d, device="cuda", generator=g) * 0.5).to(BF16)  # packed k|v as the model has them
+    k2 = kv[:, :d]
+    eye = torch.eye(dh, device="cuda", dtype=BF16)
+    keep = torch.zeros(B, H, L, L, device="cuda", dtype=torch.bool)
+    for blk in range(L // dh):  # O = dropout(P)[:, :, :, blk*96:(blk+1)*96] when V is the identity on that block
+        v = torch.zeros(B, L, H, dh, device="cuda", dtype=BF16)
+        v[:, blk * dh:(blk + 1) * dh] = eye[None, :, None, :].expand(B, dh, H, dh)
+        kv[:, d:] = v.reshape(B * L, d)
+        o, _ = kn.attn_fwd(q2, k2, kv[:, d:], B, H, L, L, causal=causal, p_drop=p_drop, seed=3, offset=8)
+        keep[:, :, :, blk * dh:(blk + 1) * dh] = o.reshape(B, L, H, dh).permute(0, 2, 1, 3) != 0
+    if causal:
+        tri = torch.ones(L, L, device="cuda", dtype=torch.bool).tril()
+        assert not keep[:, :, ~tri].any()
+        rate = keep[:, :, tri].float().mean().item()
+    else:
+        rate = keep.float().mean().item()
+    assert abs(rate - 0.7) < 5e-3, rate
+    kv[:, d:] = torch.randn(B * L, d, device="cuda", generator=g).to(BF16)
+    v2 = kv[:, d:]
+    o, lse2 = kn.attn_fwd(q2, k2, v2, B, H, L, L, causal=causal, p_drop=p_drop, seed=3, offset=8)
+
+    def heads(t):
+        return t.float().reshape(B, L, H, dh).permute(0, 2, 1, 3).contiguous().requires_grad_(True)
+
+    qf, kf, vf = heads(q2), heads(k2), heads(v2)
+    sc = torch.einsum("bhqd,bhkd->bhqk", qf, kf) * dh ** -0.5
+    if causal:
+        sc = sc.masked_fill(~tri, float("-inf"))
+    pr = torch.softmax(sc, -1) * keep / (1 - p_drop)
+    ref = pr @ vf
+    assert rel_l2(o.float().reshape(B, L, H, dh).permute(0, 2, 1, 3), ref) < 1e-2
+    d_o = torch.randn(B * L, d, device="cuda", generator=g).to(BF16)
+    dq = torch.zeros(B * L, d, device="cuda", dtype=BF16)
+    dkv = torch.zeros(B * L, 2 * d, device="cuda", dtype=BF16)
+    dk, dv = dkv[:, :d], dkv[:, d:]
+    kn.attn_bwd(q2, k2, v2, o, d_o, lse2, B, H, L, L, dq, dk, dv, causal=causal, p_drop=p_drop, seed=3, offset=8)
+    ref.backward(d_o.float().reshape(B, L, H, dh).permute(0, 2, 1, 3))
+
+    def unheads(t):
+        return t.permute(0, 2, 1, 3).reshape(B * L, d)
+
+    assert rel_l2(dv, unheads(vf.grad)) < 1.5e-2
+    assert rel_l2(dk, unheads(kf.grad)) < 1.5e-2
+    assert rel_l2(dq, unheads(qf.grad)) < 1.5e-2
