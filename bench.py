@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--seq", type=int, default=CFG["S"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vuln-heads", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of replaying the captured step")
     ap.add_argument("--ncu-step", action="store_true",
                     help="warm up, then run ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     ap.add_argument("--torch-profile", default=None, help="write a torch.profiler table of one step to this file and exit")
@@ -217,7 +218,8 @@ def main():
     redraw_1d_params(model, 0)
     model = model.to(dev)
     trainer = SmartContractTrainer(model, use_augmentation=True, use_gan=True,
-                                   compute_vuln_heads=not args.no_vuln_heads)
+                                   compute_vuln_heads=not args.no_vuln_heads, use_cuda_graph=not args.no_graph)
+    n_lines = (S - 1) // CFG["lines_per"] + 1  # = token_to_line.max() + 1, known on the host by construction
     batch = synthetic_batch(B, S, P, model.vocab_size, 1234 + rank, CFG["lines_per"], device=dev)
 
     def barrier():
@@ -226,11 +228,11 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(W):
-        trainer.train_step(batch)
+        trainer.train_step(batch, n_lines=n_lines)
     barrier()
     if args.ncu_step:
         torch.cuda.cudart().cudaProfilerStart()
-        trainer.train_step(batch)
+        trainer.train_step(batch, n_lines=n_lines)
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
         print(json.dumps({"ncu_step": "done", "launches_per_step_through_cabi": _lib.Stats.launches // (W + 1)}))
@@ -240,7 +242,7 @@ def main():
 
         t0 = time.perf_counter()
         with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
-            trainer.train_step(batch)
+            trainer.train_step(batch, n_lines=n_lines)
             torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         with open(args.torch_profile, "w") as f:
@@ -253,8 +255,10 @@ def main():
     with ClockSampler(local) as clk:
         barrier()
         e0.record()
+        t_cpu = time.perf_counter()
         for _ in range(args.steps):
-            trainer.train_step(batch)
+            trainer.train_step(batch, n_lines=n_lines)
+        cpu_ms_per_step = (time.perf_counter() - t_cpu) * 1e3 / args.steps  # host time to enqueue (incl. its syncs)
         e1.record()
         barrier()
     launches = _lib.Stats.launches
@@ -268,12 +272,12 @@ def main():
     host = synthetic_batch(B, S, P, model.vocab_size, 4321 + rank, CFG["lines_per"], pin=True)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     for _ in range(1):
-        trainer.train_step({k: v.to(dev, non_blocking=True) for k, v in host.items()})
+        trainer.train_step(host, n_lines=n_lines)
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for _ in range(args.steps):
-        res = trainer.train_step({k: v.to(dev, non_blocking=True) for k, v in host.items()})
+        res = trainer.train_step(host, n_lines=n_lines)  # pinned host tensors -> H2D inside the step
         _ = res["total_loss"].item()
     e3.record()
     barrier()
@@ -288,9 +292,15 @@ def main():
                         "sct_add_dropout_ln_fwd")
     _lib.Stats.events = []
     e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    was_graph, trainer.use_cuda_graph = trainer.use_cuda_graph, False  # events need real (eager) launches
+    _lib.Stats.events = None
+    trainer.train_step(batch, n_lines=n_lines)  # untimed: lets the eager allocator pool grow next to the graph's
+    torch.cuda.synchronize()
+    _lib.Stats.events = []
     e4.record()
-    trainer.train_step(batch)
+    trainer.train_step(batch, n_lines=n_lines)
     e5.record()
+    trainer.use_cuda_graph = was_graph
     torch.cuda.synchronize()
     ev, _lib.Stats.events = _lib.Stats.events, None
     step_ms_instr = e4.elapsed_time(e5)
@@ -329,10 +339,11 @@ def main():
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(), "global_batch": world * B, "seq_len": S, "path_len": P,
                        "parallelism": f"dp{world}", "vuln_heads": not args.no_vuln_heads,
+                       "cuda_graph": not args.no_graph,
                        "l2": "no explicit flush: each step streams several GB of activations/weights (>> 126 MB L2)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu,
-            "tflops_per_step_model": None,
+            "host_enqueue_ms_per_step": round(cpu_ms_per_step, 2),
         }))
     if world > 1:
         dist.destroy_process_group()

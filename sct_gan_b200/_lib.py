@@ -45,6 +45,7 @@ SIGNATURES = {
     "sct_small_linear_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p],
     "sct_gan_loss_fwd": [_p, _i64, _p, _p, _p],
     "sct_gan_loss_bwd": [_p, _i64, _p, _p, _p, _p, _p],
+    "sct_set_dropout_epoch_ptr": [_p],
 }
 NOARG = {"sct_version": _i32, "sct_device_check": _i32, "sct_debug_timeouts": _i32, "sct_last_error": C.c_char_p}
 
@@ -82,7 +83,8 @@ def last_error() -> str:
 
 
 # kernels launched per C-ABI call (sct_attn_bwd = D-vector + dK/dV + dQ, sct_seq_mean_fwd = memset + reduce, ...)
-KERNELS_PER_CALL = {"sct_attn_bwd": 3, "sct_small_linear_bwd": 2, "sct_seq_mean_fwd": 2}
+KERNELS_PER_CALL = {"sct_attn_bwd": 3, "sct_small_linear_bwd": 2, "sct_seq_mean_fwd": 2,
+                    "sct_set_dropout_epoch_ptr": 0}
 
 
 class Stats:

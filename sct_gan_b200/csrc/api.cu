@@ -104,6 +104,9 @@ int make_tmap_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0
   return 0;
 }
 
+static const unsigned long long* g_epoch_ptr = nullptr;
+const unsigned long long* dropout_epoch_ptr() { return g_epoch_ptr; }
+
 // per-translation-unit bounded-wait flags (see common.cuh)
 int gemm_timeout_flag();
 int attn_timeout_flag();
@@ -123,6 +126,11 @@ int32_t sct_device_check(void) {
   SCT_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   SCT_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
   SCT_CHECK(major == 10, "sct_b200 needs an sm_100-class device (B200); found sm_%d%d", major, minor);
+  return 0;
+}
+
+int32_t sct_set_dropout_epoch_ptr(const uint64_t* dev_epoch) {
+  sct::g_epoch_ptr = reinterpret_cast<const unsigned long long*>(dev_epoch);
   return 0;
 }
 

@@ -43,6 +43,7 @@ struct AttnParams {
   float* dvec;           // [B, H, Lq]  D = rowsum(dO * O)
   __nv_bfloat16* o;      // forward output
   __nv_bfloat16 *dq, *dk, *dv;
+  const unsigned long long* epoch;  // device-resident dropout epoch (nullable), folded into the key at run time
   uint32_t key0, key1;   // dropout stream key, mixed from (seed, offset) on the host
   uint32_t tmask[16];    // bit i of the 16-bit drop threshold, spread to a full word
   uint32_t thresh16;     // 0 = dropout off
@@ -64,10 +65,23 @@ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
   h ^= h >> 16;
   return h;
 }
-__device__ __forceinline__ uint32_t keep_word(const AttnParams& p, uint32_t bh, uint32_t q, uint32_t kb) {
+struct DropKey {
+  uint32_t k0, k1;
+};
+__device__ __forceinline__ DropKey drop_key(const AttnParams& p) {
+  DropKey k = {p.key0, p.key1};
+  if (p.thresh16 != 0 && p.epoch != nullptr) {
+    const unsigned long long e = *p.epoch;
+    k.k0 ^= fmix32((uint32_t)e * 0x9E3779B1u + 0x68E31DA4u);
+    k.k1 += fmix32((uint32_t)(e >> 32) ^ 0xB5297A4Du) + (uint32_t)e;
+  }
+  return k;
+}
+__device__ __forceinline__ uint32_t keep_word(const AttnParams& p, const DropKey& dk, uint32_t bh, uint32_t q,
+                                              uint32_t kb) {
   if (p.thresh16 == 0) return 0xFFFFFFFFu;
-  uint32_t x = fmix32(((bh * (uint32_t)p.Lq + q) * 0x9E3779B1u) ^ p.key0);
-  x = fmix32(x ^ (kb * 0x85EBCA77u) ^ p.key1);
+  uint32_t x = fmix32(((bh * (uint32_t)p.Lq + q) * 0x9E3779B1u) ^ dk.k0);
+  x = fmix32(x ^ (kb * 0x85EBCA77u) ^ dk.k1);
   uint32_t lt = 0u;  // lt bit = 1 <=> u16 < thresh16 (LSB-first ripple comparison)
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
@@ -214,6 +228,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int q = q0 + r;
   const int c_base = hf * 64;
   const uint32_t bh = (uint32_t)(b * p.H + h);
+  const DropKey dkey = drop_key(p);
   float m_run = -INFINITY, l_run = 0.f;
 
   for (int j = 0; j < nkv; ++j) {
@@ -271,7 +286,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     float rs = 0.f;
 #pragma unroll
     for (int kb = 0; kb < 2; ++kb) {
-      const uint32_t kw = keep_word(p, bh, (uint32_t)q, (uint32_t)((kv0 + c_base) >> 5) + kb);
+      const uint32_t kw = keep_word(p, dkey, bh, (uint32_t)q, (uint32_t)((kv0 + c_base) >> 5) + kb);
       float pv[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -454,6 +469,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     load_tile(&tmdO, bar_qdo0, sQ0 + QKV_BYTES, h * DH, i_begin * TILE, b);
   }
 
+  const uint32_t bh = (uint32_t)(b * p.H + h);
+  const DropKey dkey = drop_key(p);
   for (int it = 0; it < n_it; ++it) {
     const int s = it & 1;
     const int qi = i_begin + it;
@@ -488,13 +505,12 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       load_tile(&tmdO, nb, nQ + QKV_BYTES, h * DH, q0 + TILE, b);
     }
     const bool diag = p.causal && (qi == jt);
-    const uint32_t bh = (uint32_t)(b * p.H + h);
 #pragma unroll 1
     for (int cc = 0; cc < 2; ++cc) {
       const int c0 = half * 64 + cc * 32;
       // keep bits of (q = q0+c0+i, k = this thread's key row) for i = 0..31: lane L makes the word of query
       // q0+c0+L over this warp's 32 keys, then the warp transposes the 32x32 bit tile
-      uint32_t kw = keep_word(p, bh, (uint32_t)(q0 + c0 + lane), (uint32_t)((kv0 >> 5) + quad));
+      uint32_t kw = keep_word(p, dkey, bh, (uint32_t)(q0 + c0 + lane), (uint32_t)((kv0 >> 5) + quad));
       if (p.thresh16 != 0) kw = warp_bit_transpose(kw, lane);
       uint32_t rs[32], rp[32];
       tmem_ld32(tST + lane_sel + c0, rs);
@@ -621,6 +637,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const float lse2 = q < p.Lq ? p.lse2[stat_o] : INFINITY;
   const float dvec = q < p.Lq ? p.dvec[stat_o] : 0.f;
   const uint32_t bh = (uint32_t)(b * p.H + h);
+  const DropKey dkey = drop_key(p);
 
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
   constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, false, true);
@@ -669,7 +686,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll 1
     for (int cc = 0; cc < 2; ++cc) {
       const int c0 = half * 64 + cc * 32;
-      const uint32_t kw = keep_word(p, bh, (uint32_t)q, (uint32_t)((kv0 + c0) >> 5));
+      const uint32_t kw = keep_word(p, dkey, bh, (uint32_t)q, (uint32_t)((kv0 + c0) >> 5));
       uint32_t rs[32], rp[32];
       tmem_ld32(tS + lane_sel + c0, rs);
       tmem_ld32(tDP + lane_sel + c0, rp);
@@ -757,6 +774,7 @@ int fill_params(AttnParams& p, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int
     p.key0 = (uint32_t)z;
     p.key1 = (uint32_t)(z >> 32);
   }
+  p.epoch = dropout_epoch_ptr();
   double t = (double)p_drop * 65536.0 + 0.5;
   p.thresh16 = p_drop > 0.f ? (uint32_t)(t > 65535.0 ? 65535.0 : t) : 0u;
   for (int i = 0; i < 16; ++i) p.tmask[i] = ((p.thresh16 >> i) & 1u) ? 0xFFFFFFFFu : 0u;

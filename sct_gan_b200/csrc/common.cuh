@@ -17,6 +17,7 @@ namespace sct {
 // ---------------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 int num_sms();
+const unsigned long long* dropout_epoch_ptr();  // device counter added to every dropout offset (nullable)
 
 #define SCT_CHECK(cond, ...)                                                                       \
   do {                                                                                             \

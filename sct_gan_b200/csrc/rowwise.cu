@@ -22,14 +22,21 @@ constexpr float kLnEps = 1e-5f;
 
 struct DropCfg {
   uint64_t seed, offset;
+  const unsigned long long* epoch;  // device-resident epoch added to offset at run time (nullable)
   uint32_t thresh16;  // drop if u16 < thresh16
   float inv_keep;     // 1/(1-p)
 };
+
+__device__ __forceinline__ DropCfg resolve_epoch(DropCfg dc) {
+  if (dc.thresh16 != 0 && dc.epoch != nullptr) dc.offset += *dc.epoch * 0x100000ull;
+  return dc;
+}
 
 __host__ inline DropCfg make_drop(float p, uint64_t seed, uint64_t offset) {
   DropCfg c;
   c.seed = seed;
   c.offset = offset;
+  c.epoch = dropout_epoch_ptr();
   double t = (double)p * 65536.0 + 0.5;
   if (t < 0) t = 0;
   if (t > 65535.0) t = 65535.0;
@@ -109,7 +116,8 @@ embed_ln_pe_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict_
                        const float* __restrict__ gamma, const float* __restrict__ beta,
                        const float* __restrict__ pe, float* __restrict__ out_f32,
                        __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ stats, int n_tok,
-                       int seq_len, int vocab, float scale, DropCfg dc) {
+                       int seq_len, int vocab, float scale, DropCfg dc_in) {
+  const DropCfg dc = resolve_epoch(dc_in);
   constexpr int D = NV * 128;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -156,7 +164,8 @@ embed_ln_pe_bwd_kernel(const float* __restrict__ g_f32, const __nv_bfloat16* __r
                        const int64_t* __restrict__ ids, const float* __restrict__ table,
                        const float* __restrict__ gamma, const float* __restrict__ stats,
                        float* __restrict__ dtable, float* __restrict__ dgamma,
-                       float* __restrict__ dbeta, int n_tok, int vocab, float scale, DropCfg dc) {
+                       float* __restrict__ dbeta, int n_tok, int vocab, float scale, DropCfg dc_in) {
+  const DropCfg dc = resolve_epoch(dc_in);
   constexpr int D = NV * 128;
   constexpr float inv_d = 1.0f / D;
   __shared__ float red[kWarpsPerBlock * D];
@@ -219,7 +228,8 @@ add_dropout_ln_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __re
                           float alpha, const float* __restrict__ gamma,
                           const float* __restrict__ beta, float* __restrict__ x_out,
                           __nv_bfloat16* __restrict__ y_ln, __nv_bfloat16* __restrict__ y_cast,
-                          float* __restrict__ stats, int n_rows, DropCfg dc) {
+                          float* __restrict__ stats, int n_rows, DropCfg dc_in) {
+  const DropCfg dc = resolve_epoch(dc_in);
   constexpr int D = NV * 128;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -271,7 +281,8 @@ add_dropout_ln_bwd_kernel(const float* __restrict__ g_xout, const __nv_bfloat16*
                           const float* __restrict__ xprime, const float* __restrict__ stats,
                           const float* __restrict__ gamma, float alpha, float* __restrict__ g_x,
                           __nv_bfloat16* __restrict__ g_branch, float* __restrict__ dgamma,
-                          float* __restrict__ dbeta, int n_rows, DropCfg dc) {
+                          float* __restrict__ dbeta, int n_rows, DropCfg dc_in) {
+  const DropCfg dc = resolve_epoch(dc_in);
   constexpr int D = NV * 128;
   constexpr float inv_d = 1.0f / D;
   __shared__ float red[kWarpsPerBlock * D];
@@ -348,7 +359,8 @@ template <int NV>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 ln_act_fwd_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ gamma,
                   const float* __restrict__ beta, __nv_bfloat16* __restrict__ h,
-                  float* __restrict__ stats, int n_rows, DropCfg dc) {
+                  float* __restrict__ stats, int n_rows, DropCfg dc_in) {
+  const DropCfg dc = resolve_epoch(dc_in);
   constexpr int D = NV * 128;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -383,7 +395,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 ln_act_bwd_kernel(const __nv_bfloat16* __restrict__ g_h, const __nv_bfloat16* __restrict__ z,
                   const float* __restrict__ stats, const float* __restrict__ gamma,
                   const float* __restrict__ beta, __nv_bfloat16* __restrict__ g_z,
-                  float* __restrict__ dgamma, float* __restrict__ dbeta, int n_rows, DropCfg dc) {
+                  float* __restrict__ dgamma, float* __restrict__ dbeta, int n_rows, DropCfg dc_in) {
+  const DropCfg dc = resolve_epoch(dc_in);
   constexpr int D = NV * 128;
   constexpr float inv_d = 1.0f / D;
   __shared__ float red[kWarpsPerBlock * D];
@@ -439,7 +452,8 @@ ln_act_bwd_kernel(const __nv_bfloat16* __restrict__ g_h, const __nv_bfloat16* __
 // =================================================================================================
 __global__ void __launch_bounds__(256)
 gelu_dropout_fwd_kernel(const __nv_bfloat16* __restrict__ z, __nv_bfloat16* __restrict__ h,
-                        long long n8, DropCfg dc) {
+                        long long n8, DropCfg dc_in) {
+  const DropCfg dc = resolve_epoch(dc_in);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
        i += (long long)gridDim.x * blockDim.x) {
     const uint4 u = *reinterpret_cast<const uint4*>(z + i * 8);
@@ -460,7 +474,8 @@ gelu_dropout_fwd_kernel(const __nv_bfloat16* __restrict__ z, __nv_bfloat16* __re
 
 __global__ void __launch_bounds__(256)
 gelu_dropout_bwd_kernel(const __nv_bfloat16* __restrict__ g_h, const __nv_bfloat16* __restrict__ z,
-                        __nv_bfloat16* __restrict__ g_z, long long n8, DropCfg dc) {
+                        __nv_bfloat16* __restrict__ g_z, long long n8, DropCfg dc_in) {
+  const DropCfg dc = resolve_epoch(dc_in);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
        i += (long long)gridDim.x * blockDim.x) {
     const uint4 uz = *reinterpret_cast<const uint4*>(z + i * 8);

@@ -180,7 +180,9 @@ def seq_mean_bwd(g, B, S, d, want_f32=False, want_bf16=True):
 
 # ---------------------------------------------------------------------------------------------- K2
 def _pick_bn(N):
-    return 256 if N >= 1024 else 128
+    # measured on B200 (tools/gemm_bench.py, M = 32768): the 128x256 tile wins from N = 768 up (880 vs 804
+    # TFLOP/s at N = K = 768, 1045 vs 917 at N = 2304); the 128x128 tile only for the narrow N = 384 GEMMs
+    return 256 if N >= 512 else 128
 
 
 def gemm_nt(a, w, bias=None, alpha=1.0, out=None, bn=None):

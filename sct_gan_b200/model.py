@@ -131,6 +131,7 @@ class SmartContractTransformer(nn.Module):
             p.register_hook(self.hook_fn)
         self._shadow = ops.ShadowCache()
         self._step_counter = 0
+        self.heads_autocast = True  # bf16 matmuls for the PyTorch vulnerability heads on the GPU
 
     # ------------------------------------------------------------------------------------ init
     def _init_weights(self):
@@ -299,13 +300,16 @@ class SmartContractTransformer(nn.Module):
         pe[:, 1::2] = torch.cos(pos * div)
         return pe
 
-    def _line_heads(self, memory, token_to_line):
+    def _line_heads(self, memory, token_to_line, n_lines=None):
         """model.py:480-759 with the two Python loops (batch x lines, lines x types) batched: every line
-        goes through the same weights, so [B, L, .] tensors give the same result."""
+        goes through the same weights, so [B, L, .] tensors give the same result.  `n_lines` (=
+        token_to_line.max() + 1, model.py:484) may be passed by a caller that already knows it on the host;
+        otherwise it is read back from the device like the reference does."""
         B, S, d = memory.shape
         if token_to_line is not None:
             t2l = token_to_line if token_to_line.dim() == 2 else token_to_line.unsqueeze(0).expand(B, -1)
-            n_lines = int(t2l.max().item()) + 1
+            if n_lines is None:
+                n_lines = int(t2l.max().item()) + 1
             idx = torch.where((t2l >= 0) & (t2l < n_lines), t2l, torch.full_like(t2l, n_lines)).long()
             sums = torch.zeros(B, n_lines + 1, d, device=memory.device, dtype=memory.dtype)
             sums.scatter_add_(1, idx.unsqueeze(-1).expand(-1, -1, d), memory)
@@ -318,16 +322,19 @@ class SmartContractTransformer(nn.Module):
         else:
             line_features = memory
         original = line_features
-        lf = self.line_feature_extractor(line_features)
-        lf = torch.where(lf.std() < 1e-6, original * 0.1, lf)
-        att1, _ = self.line_vuln_attention(lf, lf, lf, need_weights=False)
-        lf = lf + 0.05 * att1
-        att2, _ = self.vuln_type_attention(lf, lf, lf, need_weights=False)
-        lf = lf + 0.05 * att2
-        main = self.line_vulnerability_head_1(torch.cat([lf, att1], dim=-1))
-        spec = self.line_specific_processor(original)
-        typed = torch.cat([proc(spec) for proc in self.vuln_type_processor], dim=-1)
-        logits = main + 0.1 * typed
+        # On the GPU these [B, lines, .] PyTorch heads run their matmuls in bf16 (autocast), like the rest of the
+        # step; LayerNorm / softmax statistics stay fp32.  On CPU (tests against the oracle) they are plain fp32.
+        with torch.autocast("cuda", dtype=BF16, enabled=memory.is_cuda and self.heads_autocast):
+            lf = self.line_feature_extractor(line_features)
+            lf = torch.where(lf.float().std() < 1e-6, (original * 0.1).to(lf.dtype), lf)
+            att1, _ = self.line_vuln_attention(lf, lf, lf, need_weights=False)
+            lf = lf + 0.05 * att1
+            att2, _ = self.vuln_type_attention(lf, lf, lf, need_weights=False)
+            lf = lf + 0.05 * att2
+            main = self.line_vulnerability_head_1(torch.cat([lf, att1], dim=-1))
+            spec = self.line_specific_processor(original)
+            typed = torch.cat([proc(spec) for proc in self.vuln_type_processor], dim=-1)
+            logits = (main + 0.1 * typed).float()
         n = logits.shape[1]
         if n < 1024:
             logits = torch.cat([logits, logits.new_zeros(B, 1024 - n, logits.shape[2])], dim=1)
@@ -338,14 +345,15 @@ class SmartContractTransformer(nn.Module):
     # --------------------------------------------------------------------------------- forward
     def forward(self, input_ids, attention_mask=None, ast_input_ids=None, ast_attention_mask=None,
                 target_ids=None, token_to_line=None, apply_syntax_constraints=True, *, fused_loss=False,
-                return_logits=True, compute_vuln_heads=True, greedy=False, max_new_tokens=None):
+                return_logits=True, compute_vuln_heads=True, greedy=False, max_new_tokens=None, n_lines=None):
         if not input_ids.is_cuda:
             raise RuntimeError("sct_gan_b200 runs on a B200 only (no CPU fallback): move the batch to cuda")
         B, S = input_ids.shape
         d = self.d_model
+        self._shadow.begin_step(refresh=self.training)
         if self.training:
             self._step_counter += 1
-            ops.DropoutRng.reseed(torch.initial_seed() * 1000003 + self._step_counter)
+            ops.DropoutRng.begin_step(self, input_ids.device)
         x, _ = self._embed(input_ids, self.embedding, self.embedding_norm, True, False)
         src_mask = attention_mask.bool() if attention_mask is not None else \
             torch.ones((B, S), dtype=torch.bool, device=input_ids.device)
@@ -360,7 +368,7 @@ class SmartContractTransformer(nn.Module):
 
         if compute_vuln_heads:
             contract_logits = self._contract_heads(memory, mem_b)
-            line_logits = self._line_heads(memory, token_to_line)
+            line_logits = self._line_heads(memory, token_to_line, n_lines)
         else:
             contract_logits = line_logits = None
 

@@ -21,13 +21,36 @@ BF16, F32 = torch.bfloat16, torch.float32
 
 # ------------------------------------------------------------------------------------------------
 class DropoutRng:
-    """(seed, offset) source for the counter-based dropout of the kernels."""
+    """(seed, offset) source for the counter-based dropout of the kernels.
+
+    `seed` is fixed per process (from torch's seed), `offset` numbers the dropout sites of one forward pass
+    (reset by begin_step), and a device-resident epoch counter — bumped once per training forward ON THE
+    DEVICE, so that it also advances when the step is replayed from a CUDA graph — is added to the offset by
+    the kernels at run time (sct_set_dropout_epoch_ptr).  One forward -> backward at a time: the backward
+    must run before the next training forward bumps the epoch."""
     seed = 0x5C7B200
     counter = 0
 
     @classmethod
     def reseed(cls, seed: int):
         cls.seed = int(seed) & 0x7FFFFFFFFFFFFFFF
+        cls.counter = 0
+
+    @classmethod
+    def begin_step(cls, owner, device):
+        """Start a training forward of `owner` (the module): site counter to 0, its device epoch += 1.  The
+        epoch counter and the seed (torch.initial_seed() when the module first trains) belong to the module,
+        so a freshly built model under the same torch seed reproduces the same masks."""
+        from . import _lib
+
+        ep = getattr(owner, "_drop_epoch", None)
+        if ep is None or ep.device != device:
+            ep = torch.zeros(2, dtype=torch.int64, device=device)  # [0] = epoch (16-byte allocation)
+            owner._drop_epoch = ep
+            owner._drop_seed = (torch.initial_seed() * 1000003 + 0x5C7B200) & 0x7FFFFFFFFFFFFFFF
+        cls.seed = owner._drop_seed
+        _lib.call("sct_set_dropout_epoch_ptr", ep.data_ptr())
+        ep[:1].add_(1)
         cls.counter = 0
 
     @classmethod
@@ -41,12 +64,25 @@ class ShadowCache:
 
     def __init__(self):
         self._store = {}
+        # Fused optimisers update parameters without bumping Tensor._version, so a training forward re-casts
+        # every weight it touches once (always_refresh; ~1.2 GB of traffic for the full model).  Inference keeps
+        # the cached shadow until the parameter's version or storage changes (load_state_dict, .to()).
+        self.always_refresh = False
+        self._fresh = set()
+
+    def begin_step(self, refresh: bool):
+        self.always_refresh = refresh
+        self._fresh.clear()
 
     def get(self, p: torch.Tensor) -> torch.Tensor:
         key = id(p)
         ent = self._store.get(key)
-        if ent is not None and ent[0] == p._version and ent[1].device == p.device and ent[2] == p.data_ptr():
-            return ent[1]
+        if ent is not None and ent[1].device == p.device and ent[2] == p.data_ptr():
+            if self.always_refresh:
+                if key in self._fresh:
+                    return ent[1]
+            elif ent[0] == p._version:
+                return ent[1]
         src = p.detach()
         src2 = src if src.dim() == 2 else src.view(1, -1)
         assert src2.is_contiguous()
@@ -54,6 +90,7 @@ class ShadowCache:
             torch.empty(src.shape, dtype=BF16, device=p.device)
         kn.cast_scale(src2, buf.view(src2.shape), 0, 1.0)
         self._store[key] = (p._version, buf, p.data_ptr())
+        self._fresh.add(key)
         return buf
 
     def clear(self):

@@ -35,7 +35,7 @@ def contract_level_focal_loss(pred, target, alpha=0.05, gamma=4.0):
     return (focal * penalty).mean()
 
 
-def spatial_penalty(pred, target, token_to_line):
+def spatial_penalty(pred, target, token_to_line, n_lines=None):
     """SpatialAwareFocalLoss._compute_spatial_penalty (train.py:174-245) without the B*1024-iteration
     Python loop.  The reference treats the flattened batch as ONE sequence when token_to_line has as many
     entries as pred has rows (i.e. S == 1024) and returns zeros otherwise; row i then gets
@@ -45,9 +45,12 @@ def spatial_penalty(pred, target, token_to_line):
     if token_to_line is None or token_to_line.numel() != total:
         return torch.zeros_like(pred)
     tl = token_to_line.reshape(-1).long()
-    lo = int(tl.min().item())
-    tl = tl - lo
-    L = int(tl.max().item()) + 1
+    if n_lines is None:  # read the line range back like the reference's .item() calls
+        lo = int(tl.min().item())
+        tl = tl - lo
+        L = int(tl.max().item()) + 1
+    else:  # caller knows token_to_line.max() + 1 on the host (lines are numbered from 0): no device sync
+        L = int(n_lines)
     sig = torch.sigmoid(pred)
     cnt = torch.zeros(L + 4, device=pred.device, dtype=pred.dtype).index_add_(0, tl + 2, torch.ones_like(tl, dtype=pred.dtype))
     s_sig = torch.zeros(L + 4, C, device=pred.device, dtype=pred.dtype).index_add_(0, tl + 2, sig)
@@ -64,15 +67,15 @@ def spatial_penalty(pred, target, token_to_line):
     return torch.where(live.unsqueeze(1), mean * 0.1, torch.zeros_like(mean))
 
 
-def spatial_aware_focal_loss(pred, target, token_to_line, alpha, gamma, spatial_weight):
+def spatial_aware_focal_loss(pred, target, token_to_line, alpha, gamma, spatial_weight, n_lines=None):
     """SpatialAwareFocalLoss.forward (train.py:128-172)."""
     probs = torch.sigmoid(pred)
     bce = _bce(pred, target)
     focal = alpha * (1 - torch.exp(-bce)) ** gamma * bce
     focal = focal + torch.where(target == 1.0, torch.relu(0.3 - probs) * 0.5, torch.zeros_like(probs))
     focal = focal + torch.where(target == 0.0, torch.relu(probs - 0.5) * 0.2, torch.zeros_like(probs))
-    if token_to_line is not None and spatial_weight > 0:
-        focal = focal + spatial_weight * spatial_penalty(pred, target, token_to_line)
+    if token_to_line is not None:  # spatial_weight is 0.2 / 0.1 / 0.05, never 0 (train.py:568-573, 1174-1184)
+        focal = focal + spatial_weight * spatial_penalty(pred, target, token_to_line, n_lines)
     return focal.mean()
 
 
@@ -123,13 +126,19 @@ def allreduce_mean_grads(params, world, group=None, bucket_bytes=32 << 20):
 
 class SmartContractTrainer:
     """Step-level mirror of the reference trainer (constructor keywords of train.py:481-494 that matter for
-    the step).  `train_step(batch)` is the body of the reference's batch loop."""
+    the step).  `train_step(batch)` is the body of the reference's batch loop.
+
+    No host synchronisation inside the step: the NaN / norm > 1000 skip rule (train.py:1301-1309) is a device
+    flag honoured by the fused AdamW, the focal-loss switch (train.py:1174-1184) and the GAN confidence
+    branches are device predicates.  With `use_cuda_graph=True` the whole step (forward, losses, backward,
+    gradient exchange, clips, AdamW) is captured once per input signature and replayed; dropout masks still
+    change every replay through the device-resident dropout epoch."""
 
     LR_MULT = (1.0, 2.0, 3.0, 0.5)
 
     def __init__(self, model, learning_rate=1e-6, weight_decay=0.1, max_grad_norm=1.0, use_augmentation=False,
                  use_gan=False, line_vuln_weight=2.0, contract_vuln_weight=3.0, warmup_epochs=5,
-                 compute_vuln_heads=True, process_group=None, bucket_mb=32):
+                 compute_vuln_heads=True, process_group=None, bucket_mb=32, use_cuda_graph=False):
         self.model = model
         self.use_augmentation = use_augmentation
         self.use_gan = use_gan
@@ -140,16 +149,24 @@ class SmartContractTrainer:
         self.current_epoch = 0
         self.stability_factor = 1.0
         self.line_loss_scale = 1.0
-        self.focal_cfg = (0.25, 2.0, 0.2)  # SpatialAwareFocalLoss constructor values (train.py:568-573)
         self.compute_vuln_heads = compute_vuln_heads
+        dev = next(model.parameters()).device
+        # SpatialAwareFocalLoss (alpha, gamma, spatial_weight): constructor values (train.py:568-573), switched
+        # after every batch on whether it held any vulnerable line (train.py:1174-1184) — kept on the device
+        self.focal = torch.tensor([0.25, 2.0, 0.2], device=dev)
+        self._focal_has = torch.tensor([0.1, 1.5, 0.1], device=dev)
+        self._focal_none = torch.tensor([0.05, 1.0, 0.05], device=dev)
         groups = [[], [], [], []]
-        self._names = {}
         for n, p in model.named_parameters():
             groups[param_group_of(n, use_gan)].append(p)
-            self._names[p] = n
         lr = min(learning_rate, 1e-4)  # train.py:598-601
         pg = [{"params": g, "lr": lr * m} for g, m in zip(groups, self.LR_MULT) if g]
-        self.optimizer = torch.optim.AdamW(pg, weight_decay=weight_decay, betas=(0.9, 0.98), eps=1e-9, fused=True)
+        on_gpu = dev.type == "cuda"
+        self.optimizer = torch.optim.AdamW(pg, weight_decay=weight_decay, betas=(0.9, 0.98), eps=1e-9,
+                                           fused=on_gpu, capturable=on_gpu and use_cuda_graph)
+        self._found_inf = torch.zeros((), device=dev)  # 1.0 => the fused AdamW leaves parameters and step count alone
+        if on_gpu:
+            self.optimizer.found_inf = self._found_inf
         self.disc_params = [p for n, p in model.named_parameters() if "disc_" in n]
         self.vuln_params = [p for n, p in model.named_parameters()
                             if "vulnerability_head" in n or "line_feature_extractor" in n
@@ -157,10 +174,12 @@ class SmartContractTrainer:
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.bucket_bytes = bucket_mb << 20
+        self.use_cuda_graph = use_cuda_graph and on_gpu
+        self._graphs = {}
         self.last = {}
 
     # ------------------------------------------------------------------------------------------
-    def compute_losses(self, out, batch, syntax_penalty=0.0):
+    def compute_losses(self, out, batch, syntax_penalty=0.0, n_lines=None):
         dev = out["gen_ce_loss"].device
         gen = out["gen_ce_loss"] + 0.5 * syntax_penalty
         res = {"gen_loss": gen}
@@ -171,12 +190,10 @@ class SmartContractTrainer:
             if lvl.shape != vl.shape and lvl.shape[1] == vl.shape[2] and lvl.shape[2] == vl.shape[1]:
                 vl = vl.transpose(1, 2).contiguous()
             t2l = batch.get("token_to_line")
-            a, g, sw = self.focal_cfg
             lv = spatial_aware_focal_loss(lvl.reshape(-1, lvl.shape[-1]), vl.reshape(-1, lvl.shape[-1]).float(),
-                                          t2l.reshape(-1) if t2l is not None else None, a, g, sw)
-            # train.py:1174-1184: the focal settings switch AFTER this batch's loss, on the batch's label count
-            has_line = vl.sum() > 0
-            self._pending_focal = has_line
+                                          t2l.reshape(-1) if t2l is not None else None, self.focal[0], self.focal[1],
+                                          self.focal[2], n_lines)
+            self._pending_has_line = vl.sum() > 0  # applied after the optimiser step, like train.py:1174-1184
             cv = torch.clamp(cv, min=0.0001)
             lv = torch.clamp(lv, min=0.000001)
             lv = torch.where(lv > 5.0, lv * 0.1, torch.where(lv > 1.0, lv * 0.5, lv))  # train.py:1189-1194
@@ -209,16 +226,14 @@ class SmartContractTrainer:
         if self.world > 1:
             allreduce_mean_grads(list(self.model.parameters()), self.world, self.pg, self.bucket_bytes)
 
-    def train_step(self, batch, syntax_penalty=0.0):
-        """One optimisation step; returns a dict of device scalars (no host sync except the skip rule)."""
+    def _step_body(self, batch, syntax_penalty, n_lines):
         model = self.model
-        model.train()
         target_ids = batch["target_ids"] if self.use_augmentation else batch["input_ids"]
         out = model(input_ids=batch["input_ids"], attention_mask=batch["attention_mask"],
                     ast_input_ids=batch["ast_input_ids"], ast_attention_mask=batch["ast_attention_mask"],
                     target_ids=target_ids, token_to_line=batch.get("token_to_line"), fused_loss=True,
-                    return_logits=False, compute_vuln_heads=self.compute_vuln_heads)
-        losses = self.compute_losses(out, batch, syntax_penalty)
+                    return_logits=False, compute_vuln_heads=self.compute_vuln_heads, n_lines=n_lines)
+        losses = self.compute_losses(out, batch, syntax_penalty, n_lines)
         self.optimizer.zero_grad(set_to_none=True)
         losses["total_loss"].backward()
         self._allreduce_grads()
@@ -234,14 +249,55 @@ class SmartContractTrainer:
         norms = torch._foreach_norm([p.grad for p in params])
         total_norm = torch.linalg.vector_norm(torch.stack(norms))
         ok = torch.isfinite(losses["total_loss"]) & torch.isfinite(total_norm) & (total_norm <= 1000)
-        stepped = bool(ok.item())  # the reference's skip rule is a host decision (train.py:1301-1309)
-        if stepped:
-            self.optimizer.step()
-        else:
+        # skip rule of train.py:1301-1309 without a host decision: the fused AdamW skips when found_inf == 1
+        self._found_inf.copy_((~ok).to(self._found_inf.dtype).reshape(()))
+        if not self._found_inf.is_cuda and not bool(ok):
             self.optimizer.zero_grad(set_to_none=True)
+        else:
+            self.optimizer.step()
         if self.compute_vuln_heads:  # train.py:1174-1184
-            self.focal_cfg = (0.1, 1.5, 0.1) if bool(self._pending_focal.item()) else (0.05, 1.0, 0.05)
+            self.focal.copy_(torch.where(self._pending_has_line, self._focal_has, self._focal_none))
         losses["grad_norm"] = total_norm
-        losses["stepped"] = stepped
-        self.last = losses
-        return losses
+        losses["stepped"] = ok
+        # detached: nothing returned keeps the autograd graph (and its AccumulateGrad nodes) alive
+        return {k: (v.detach() if torch.is_tensor(v) else v) for k, v in losses.items()}
+
+    def train_step(self, batch, syntax_penalty=0.0, n_lines=None):
+        """One optimisation step; returns a dict of DEVICE scalars (`stepped` included) — nothing in here waits
+        for the GPU.  `n_lines` = token_to_line.max() + 1 if the caller knows it on the host (the data loader
+        does); without it the line heads read it back from the device as the reference does."""
+        self.model.train()
+        dev = self._found_inf.device
+        if not self.use_cuda_graph:
+            batch = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in batch.items()}
+            self.last = self._step_body(batch, syntax_penalty, n_lines)
+            return self.last
+        if n_lines is None and self.compute_vuln_heads and batch.get("token_to_line") is not None:
+            n_lines = int(batch["token_to_line"].max().item()) + 1
+        tens = {k: v for k, v in batch.items() if torch.is_tensor(v)}
+        key = tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(tens.items())) + (n_lines, float(syntax_penalty))
+        ent = self._graphs.get(key)
+        if ent is None:  # first step of a signature runs eagerly (it is also the warm-up for lazy initialisation)
+            self._graphs[key] = "warm"
+            tens = {k: v.to(dev, non_blocking=True) for k, v in tens.items()}
+            self.last = self._step_body(tens, syntax_penalty, n_lines)
+            return self.last
+        from . import _lib
+
+        if ent == "warm":
+            static = {k: v.to(dev, copy=True) for k, v in tens.items()}
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            n0 = _lib.Stats.launches
+            with torch.cuda.graph(graph):
+                res = self._step_body(static, syntax_penalty, n_lines)
+            ent = self._graphs[key] = (graph, static, res, _lib.Stats.launches - n0)
+            _lib.Stats.launches = n0
+        graph, static, res, n_launch = ent
+        for k, v in tens.items():  # pinned host tensors land directly in the graph's input buffers
+            if static[k].data_ptr() != v.data_ptr():
+                static[k].copy_(v, non_blocking=True)
+        graph.replay()
+        _lib.Stats.launches += n_launch
+        self.last = res
+        return res

@@ -190,9 +190,52 @@ def test_dropout_training_step_runs_and_is_seeded(cuda_dev):
         tr = SmartContractTrainer(m, learning_rate=1e-4, use_augmentation=True, use_gan=True)
         batch = O.make_batch(2, 64, 32, 512, seed=3, device="cuda")
         res = tr.train_step(batch)
-        return res["total_loss"].item(), res["grad_norm"].item(), res["stepped"]
+        return res["total_loss"].item(), res["grad_norm"].item(), bool(res["stepped"])
 
     a, b, c = run(5), run(5), run(6)
     # same seed -> same masks; fp32 atomics (pooling, LayerNorm parameter grads) reorder sums, so equal to ~1e-6
     assert abs(a[0] - b[0]) < 1e-4 * abs(a[0]) and abs(a[1] - b[1]) < 1e-2 * abs(a[1]) and a[2] is True
     assert abs(c[0] - a[0]) > 1e-3 * abs(a[0]) and all(map(lambda v: v == v and abs(v) < 1e6, a[:2]))
+
+
+def test_cuda_graph_step_matches_eager_and_redraws_dropout(cuda_dev):
+    """The captured step replays the same arithmetic as the eager step (same seeds => same masks, equal up to
+    fp32-atomic reordering), the device-resident dropout epoch gives every replay fresh masks, and the
+    device-side skip rule leaves parameters untouched when the loss is not finite."""
+    from oracle import sct_oracle as O
+    from sct_gan_b200 import SmartContractTrainer, SmartContractTransformer, ops
+
+    cfg = {**O.DEFAULT_CFG, **dict(num_encoder_layers=1, num_decoder_layers=1, dim_feedforward=256,
+                                   max_length=128, vocab_size=512, dropout=0.3)}
+    batch = O.make_batch(2, 64, 32, 512, seed=3, device="cuda")
+    n_lines = int(batch["token_to_line"].max()) + 1
+
+    def run(use_graph, lr, steps=4):
+        torch.manual_seed(5)
+        m = SmartContractTransformer(**cfg)
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        m.load_state_dict(O.synth_state_dict(shapes, 3))
+        m = m.cuda()
+        tr = SmartContractTrainer(m, learning_rate=lr, use_augmentation=True, use_gan=True, use_cuda_graph=use_graph)
+        out = []
+        for _ in range(steps):
+            res = tr.train_step(batch, n_lines=n_lines)
+            out.append((res["total_loss"].item(), bool(res["stepped"])))
+        return out, m, tr
+
+    eager, _, _ = run(False, 1e-4)
+    graph, m, tr = run(True, 1e-4)
+    for (a, sa), (b, sb) in zip(eager, graph):
+        assert sa and sb and abs(a - b) < 2e-3 * abs(a), (eager, graph)
+    # device-side skip rule: a non-finite loss leaves the parameters (and AdamW's step count) untouched
+    bias0 = O.synth_state_dict({"output_layer.bias": (512,)}, 3)["output_layer.bias"].cuda()
+    assert not torch.equal(m.output_layer.bias.detach(), bias0)  # the earlier replays did update it
+    before = m.output_layer.bias.detach().clone()
+    with torch.no_grad():
+        m.output_norm.weight.fill_(float("nan"))
+    res = tr.train_step(batch, n_lines=n_lines)
+    assert not bool(res["stepped"])
+    assert torch.equal(m.output_layer.bias.detach(), before)
+    frozen, _, _ = run(True, 0.0, steps=5)  # lr = 0: weights fixed, so the loss only moves with the masks
+    losses = [v for v, _ in frozen]
+    assert len({round(v, 6) for v in losses[2:]}) == len(losses[2:]), losses  # replays draw different masks
