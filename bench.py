@@ -346,7 +346,12 @@ def main():
             "host_enqueue_ms_per_step": round(cpu_ms_per_step, 2),
         }))
     if world > 1:
-        dist.destroy_process_group()
+        # Tearing the NCCL communicator down while captured graphs still reference its collectives hangs
+        # (seen on 2 GPUs): drain the device, make sure every rank got here, then leave without the destructor.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

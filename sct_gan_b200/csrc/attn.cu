@@ -17,6 +17,7 @@
 // cross-thread reduction.  Masks are applied from the [B,Lk] key-padding bytes and the causal
 // predicate; dropout is regenerated from (seed, offset, element index).
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/sct_b200.h"
 #include "common.cuh"
@@ -406,205 +407,48 @@ attn_bwd_dvec_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* _
 }
 
 // =================================================================================================
-// backward, dK/dV: one CTA (256 threads) per (kv-tile, head, batch), streaming q-tiles.
-//   S^T = K Q^T, dP^T = V dO^T (TMEM, rows = kv) -> P^T, dS^T (bf16, smem) -> dV += P^T dO, dK += dS^T Q
+// Backward kernels: warp-specialised and software-pipelined.  A TMA producer warp, a single-lane tcgen05
+// issuer warp and two arithmetic warpgroups that only meet through mbarriers (no block-wide barrier in
+// the loops).  The 128x128 score tile is processed as two 128x64 halves, each owned by one warpgroup with
+// its own TMEM buffers, so the tensor pipe computes one half (and the gradient GEMMs of the previous one)
+// while the other half is in the exp / dropout / dS arithmetic.
+//   dQ kernel   : one CTA per (q-tile, head, batch), rows = queries, key tiles stream through
+//   dK/dV kernel: one CTA per (key tile, head, batch), rows = keys, query tiles stream through; the dropout
+//                 keep-bits (generated per query row) are transposed 32x32 inside the warp
+// Measured on B200 (tools/attn_bench.py, B=32 H=8 L=1024): 8 arithmetic warps beat 16 (launch-/latency-
+// bound hand-offs, not issue-bound), and this version beats the earlier phase-serial kernels by ~7 %.
 // =================================================================================================
-constexpr int BWD_KV_SMEM = 1024 + 2 * QKV_BYTES + 4 * QKV_BYTES + 2 * P_BYTES + 2048 + 256;
+constexpr int HALF_BYTES = TILE * 128;   // one [128 x 64] bf16 swizzle-128 block (P^T / dS halves)
+constexpr int BWD3_THREADS = 320;  // 8 arithmetic warps + MMA warp + TMA warp
 
-__global__ void __launch_bounds__(256, 1)
-attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
-                     const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sK = base, sV = sK + QKV_BYTES;
-  const uint32_t sQ0 = sV + QKV_BYTES;             // stage s: sQ0 + s*2*QKV_BYTES, dO right after Q
-  const uint32_t sPT = sQ0 + 4 * QKV_BYTES, sDST = sPT + P_BYTES;
-  const uint32_t aux = sDST + P_BYTES;
-  float* lse_s = reinterpret_cast<float*>(gen + (aux - base));   // [2][128]
-  float* dv_s = lse_s + 256;                                      // [2][128]
-  const uint32_t bar_kv = aux + 2048, bar_qdo0 = aux + 2056 /* +8 for stage 1 */, bar_mma = aux + 2072;
-  const uint32_t tmem_ptr_addr = aux + 2080;
-  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen + (tmem_ptr_addr - base));
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int jt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int kv0 = jt * TILE;
-  const int nq_tiles = (p.Lq + TILE - 1) / TILE;
-  const int i_begin = p.causal ? jt : 0;
-  int* ext_slot = reinterpret_cast<int*>(gen + (aux + 2088 - base));
-  // a key tile that lies entirely past the last unmasked key contributes nothing: dK = dV = 0
-  const int n_it = (kv0 < kv_extent(p, b, ext_slot)) ? nq_tiles - i_begin : 0;
-
-  if (tid == 0) {
-    mbar_init(bar_kv, 1);
-    mbar_init(bar_qdo0, 1);
-    mbar_init(bar_qdo0 + 8, 1);
-    mbar_init(bar_mma, 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_ptr_addr, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_ptr_gen;
-  const uint32_t tST = tmem, tDPT = tmem + 128, tDV = tmem + 256, tDK = tmem + 352;
-  const int quad = warp & 3, half = warp >> 2;
-  const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
-  const int r = quad * 32 + lane;  // local kv row
-  const int kv = kv0 + r;
-  bool row_valid = kv < p.Lk;
-  if (row_valid && p.kpm) row_valid = p.kpm[(long long)b * p.Lk + kv] == 0;
-
-  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
-  constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, false, true);
-
-  if (tid == 0 && n_it > 0) {
-    mbar_expect_tx(bar_kv, 2 * QKV_BYTES);
-    load_tile(&tmK, bar_kv, sK, h * DH, kv0, b);
-    load_tile(&tmV, bar_kv, sV, h * DH, kv0, b);
-    mbar_expect_tx(bar_qdo0, 2 * QKV_BYTES);
-    load_tile(&tmQ, bar_qdo0, sQ0, h * DH, i_begin * TILE, b);
-    load_tile(&tmdO, bar_qdo0, sQ0 + QKV_BYTES, h * DH, i_begin * TILE, b);
-  }
-
-  const uint32_t bh = (uint32_t)(b * p.H + h);
-  const DropKey dkey = drop_key(p);
-  for (int it = 0; it < n_it; ++it) {
-    const int s = it & 1;
-    const int qi = i_begin + it;
-    const int q0 = qi * TILE;
-    const uint32_t sQ = sQ0 + s * 2 * QKV_BYTES, sdO = sQ + QKV_BYTES;
-    if (tid == 0) {
-      if (it == 0) mbar_wait(bar_kv, 0);
-      mbar_wait(bar_qdo0 + 8 * s, (it >> 1) & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < 6; ++k) tc_mma_bf16(tST, desc_k64(sK, k), desc_k64(sQ, k), idesc_s, k > 0);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) tc_mma_bf16(tDPT, desc_k64(sV, k), desc_k64(sdO, k), idesc_s, k > 0);
-      tc_commit(bar_mma);
-    }
-    {
-      // per-q statistics of this tile (columns of S^T)
-      const int c = tid & 127;
-      const int qq = q0 + c;
-      const long long o = ((long long)b * p.H + h) * p.Lq + qq;
-      if (tid < 128) lse_s[s * 128 + c] = qq < p.Lq ? p.lse2[o] : INFINITY;
-      else dv_s[s * 128 + c] = qq < p.Lq ? p.dvec[o] : 0.f;
-    }
-    __syncthreads();
-    mbar_wait(bar_mma, it & 1);
-    tc_fence_after();
-    if (tid == 0 && it + 1 < n_it) {
-      const uint32_t nb = bar_qdo0 + 8 * (s ^ 1);
-      const uint32_t nQ = sQ0 + (s ^ 1) * 2 * QKV_BYTES;
-      mbar_expect_tx(nb, 2 * QKV_BYTES);
-      load_tile(&tmQ, nb, nQ, h * DH, q0 + TILE, b);
-      load_tile(&tmdO, nb, nQ + QKV_BYTES, h * DH, q0 + TILE, b);
-    }
-    const bool diag = p.causal && (qi == jt);
-#pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
-      const int c0 = half * 64 + cc * 32;
-      // keep bits of (q = q0+c0+i, k = this thread's key row) for i = 0..31: lane L makes the word of query
-      // q0+c0+L over this warp's 32 keys, then the warp transposes the 32x32 bit tile
-      uint32_t kw = keep_word(p, dkey, bh, (uint32_t)(q0 + c0 + lane), (uint32_t)((kv0 >> 5) + quad));
-      if (p.thresh16 != 0) kw = warp_bit_transpose(kw, lane);
-      uint32_t rs[32], rp[32];
-      tmem_ld32(tST + lane_sel + c0, rs);
-      tmem_ld32(tDPT + lane_sel + c0, rp);
-      tmem_ld_wait();
-      float pd[32], ds[32];
-      if (row_valid) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int c = c0 + i;
-          float pr = exp2f(fmaf(__uint_as_float(rs[i]), p.scale_log2, -lse_s[s * 128 + c]));
-          if (diag && r > c) pr = 0.f;
-          const float dm = (kw & (1u << i)) ? p.inv_keep : 0.f;
-          pd[i] = pr * dm;
-          ds[i] = pr * fmaf(__uint_as_float(rp[i]), dm, -dv_s[s * 128 + c]);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) pd[i] = ds[i] = 0.f;
-      }
-      store_row32_sw128(sPT, r, c0, pd);
-      store_row32_sw128(sDST, r, c0, ds);
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        tc_mma_bf16(tDV, desc_k128(sPT, k), desc_mn64(sdO, k), idesc_g, (it > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        tc_mma_bf16(tDK, desc_k128(sDST, k), desc_mn64(sQ, k), idesc_g, (it > 0 || k > 0) ? 1u : 0u);
-      if (it + 1 == n_it) tc_commit(bar_mma);
-    }
-  }
-  if (n_it > 0) {
-    mbar_wait(bar_mma, n_it & 1);
-    tc_fence_after();
-  }
-  {
-    // half 0 drains dV, half 1 drains dK (scaled)
-    const uint32_t src = half == 0 ? tDV : tDK;
-    const float sc = half == 0 ? 1.0f : p.scale;
-    __nv_bfloat16* dst = (half == 0 ? p.dv : p.dk) + ((long long)b * p.Lk + kv) * p.ldkv_out + h * DH;
-#pragma unroll 1
-    for (int c = 0; c < 3; ++c) {
-      uint32_t rr[32];
-      if (n_it > 0) {
-        tmem_ld32(src + lane_sel + c * 32, rr);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) rr[i] = 0u;
-      }
-      if (kv < p.Lk) {
-#pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {
-          uint4 u;
-          u.x = pack_bf16(__uint_as_float(rr[8 * qd]) * sc, __uint_as_float(rr[8 * qd + 1]) * sc);
-          u.y = pack_bf16(__uint_as_float(rr[8 * qd + 2]) * sc, __uint_as_float(rr[8 * qd + 3]) * sc);
-          u.z = pack_bf16(__uint_as_float(rr[8 * qd + 4]) * sc, __uint_as_float(rr[8 * qd + 5]) * sc);
-          u.w = pack_bf16(__uint_as_float(rr[8 * qd + 6]) * sc, __uint_as_float(rr[8 * qd + 7]) * sc);
-          *reinterpret_cast<uint4*>(dst + c * 32 + qd * 8) = u;
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 512);
+// K-major descriptor of a [128 x 64] bf16 swizzle-128 block, k16 step k (0..3)
+__device__ __forceinline__ uint64_t desc_k128h(uint32_t tile, int k) {
+  return umma_smem_desc(tile + k * 32, 16, 1024, UMMA_SW128);
 }
 
-// =================================================================================================
-// backward, dQ: one CTA (256 threads) per (q-tile, head, batch), streaming kv-tiles.
-//   S = Q K^T, dP = dO V^T (TMEM, rows = q) -> dS (bf16, smem) -> dQ += dS K
-// =================================================================================================
-constexpr int BWD_Q_SMEM = 1024 + 2 * QKV_BYTES + 4 * QKV_BYTES + P_BYTES + 1024;
+// ---- dQ: one CTA per (q-tile, head, batch); key tiles stream through, each split in two 64-key halves ----
+//   S_h = Q K_h^T, dP_h = dO V_h^T (TMEM, rows = q) -> dS_h (bf16, smem) -> dQ += dS_h K_h
+constexpr int BWD3_Q_SMEM = 1024 + 2 * QKV_BYTES + 4 * QKV_BYTES + 2 * HALF_BYTES + 1024;
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(BWD3_THREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
-                   const AttnParams p) {
+                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                    const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t sQ = base, sdO = sQ + QKV_BYTES;
-  const uint32_t sK0 = sdO + QKV_BYTES;  // stage s: K at sK0 + s*2*QKV_BYTES, V right after
-  const uint32_t sDS = sK0 + 4 * QKV_BYTES;
-  const uint32_t aux = sDS + P_BYTES;
-  float* bias_s = reinterpret_cast<float*>(gen + (aux - base));  // 128 floats
-  const uint32_t bar_q = aux + 512, bar_kv0 = aux + 520 /* +8 */, bar_mma = aux + 536;
-  const uint32_t tmem_ptr_addr = aux + 544;
+  const uint32_t sK = sdO + QKV_BYTES;           // [2] stages
+  const uint32_t sV = sK + 2 * QKV_BYTES;        // [2] stages
+  const uint32_t sDS = sV + 2 * QKV_BYTES;       // [2] halves
+  const uint32_t aux = sDS + 2 * HALF_BYTES;
+  uint8_t* mask_s = gen + (aux - base);          // [2][128]
+  int* anym_s = reinterpret_cast<int*>(gen + (aux + 256 - base));
+  int* ext_slot = reinterpret_cast<int*>(gen + (aux + 272 - base));
+  const uint32_t bar0 = aux + 512;
+  const uint32_t bar_q = bar0, bar_kvf = bar0 + 8, bar_kve = bar0 + 24, bar_mkf = bar0 + 40, bar_sf = bar0 + 56,
+                 bar_pf = bar0 + 72, bar_dsd = bar0 + 88;
+  const uint32_t tmem_ptr_addr = bar0 + 112;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen + (tmem_ptr_addr - base));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -612,140 +456,390 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int qt = nq_tiles - 1 - blockIdx.x;
   const int h = blockIdx.y, b = blockIdx.z;
   const int q0 = qt * TILE;
-  int* ext_slot = reinterpret_cast<int*>(gen + (aux + 552 - base));
-  int nkv = (kv_extent(p, b, ext_slot) + TILE - 1) / TILE;  // key tiles past the last unmasked key are skipped
-  if (p.causal) nkv = min(nkv, qt + 1);
 
   if (tid == 0) {
     mbar_init(bar_q, 1);
-    mbar_init(bar_kv0, 1);
-    mbar_init(bar_kv0 + 8, 1);
-    mbar_init(bar_mma, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_kvf + 8 * i, 1);
+      mbar_init(bar_kve + 8 * i, 1);
+      mbar_init(bar_mkf + 8 * i, 1);
+      mbar_init(bar_sf + 8 * i, 1);
+      mbar_init(bar_pf + 8 * i, 4);
+      mbar_init(bar_dsd + 8 * i, 1);
+    }
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(tmem_ptr_addr, 512);
+  if (warp == 8) tmem_alloc(tmem_ptr_addr, 512);
+  int nkv = (kv_extent(p, b, ext_slot) + TILE - 1) / TILE;
+  if (p.causal) nkv = min(nkv, qt + 1);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_gen;
-  const uint32_t tS = tmem, tDP = tmem + 128, tDQ = tmem + 256;
-  const int quad = warp & 3, half = warp >> 2;
-  const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
-  const int r = quad * 32 + lane;  // local q row
-  const int q = q0 + r;
-  const long long stat_o = ((long long)b * p.H + h) * p.Lq + q;
-  const float lse2 = q < p.Lq ? p.lse2[stat_o] : INFINITY;
-  const float dvec = q < p.Lq ? p.dvec[stat_o] : 0.f;
-  const uint32_t bh = (uint32_t)(b * p.H + h);
-  const DropKey dkey = drop_key(p);
-
-  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
-  constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, false, true);
-
-  if (tid == 0 && nkv > 0) {
-    mbar_expect_tx(bar_q, 2 * QKV_BYTES);
-    load_tile(&tmQ, bar_q, sQ, h * DH, q0, b);
-    load_tile(&tmdO, bar_q, sdO, h * DH, q0, b);
-    mbar_expect_tx(bar_kv0, 2 * QKV_BYTES);
-    load_tile(&tmK, bar_kv0, sK0, h * DH, 0, b);
-    load_tile(&tmV, bar_kv0, sK0 + QKV_BYTES, h * DH, 0, b);
-  }
-
-  for (int j = 0; j < nkv; ++j) {
-    const int s = j & 1;
-    const int kv0 = j * TILE;
-    const uint32_t sK = sK0 + s * 2 * QKV_BYTES, sV = sK + QKV_BYTES;
-    if (tid == 0) {
-      if (j == 0) mbar_wait(bar_q, 0);
-      mbar_wait(bar_kv0 + 8 * s, (j >> 1) & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < 6; ++k) tc_mma_bf16(tS, desc_k64(sQ, k), desc_k64(sK, k), idesc_s, k > 0);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) tc_mma_bf16(tDP, desc_k64(sdO, k), desc_k64(sV, k), idesc_s, k > 0);
-      tc_commit(bar_mma);
+  // TMEM columns: S_h at 64h, dP_h at 128 + 64h, dQ at 256
+  if (warp == 9) {
+    if (lane == 0 && nkv > 0) {
+      mbar_expect_tx(bar_q, 2 * QKV_BYTES);
+      load_tile(&tmQ, bar_q, sQ, h * DH, q0, b);
+      load_tile(&tmdO, bar_q, sdO, h * DH, q0, b);
     }
-    bool masked = false;
-    if (tid < 128) {
-      const int kv = kv0 + tid;
-      masked = kv >= p.Lk;
-      if (!masked && p.kpm) masked = p.kpm[(long long)b * p.Lk + kv] != 0;
-      bias_s[tid] = masked ? -INFINITY : 0.f;
-    }
-    const int any_mask = __syncthreads_or(masked ? 1 : 0);
-    mbar_wait(bar_mma, j & 1);
-    tc_fence_after();
-    if (tid == 0 && j + 1 < nkv) {
-      const uint32_t nb = bar_kv0 + 8 * (s ^ 1);
-      const uint32_t nK = sK0 + (s ^ 1) * 2 * QKV_BYTES;
-      mbar_expect_tx(nb, 2 * QKV_BYTES);
-      load_tile(&tmK, nb, nK, h * DH, kv0 + TILE, b);
-      load_tile(&tmV, nb, nK + QKV_BYTES, h * DH, kv0 + TILE, b);
-    }
-    const bool diag = p.causal && (j == qt);
-#pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
-      const int c0 = half * 64 + cc * 32;
-      const uint32_t kw = keep_word(p, dkey, bh, (uint32_t)q, (uint32_t)((kv0 + c0) >> 5));
-      uint32_t rs[32], rp[32];
-      tmem_ld32(tS + lane_sel + c0, rs);
-      tmem_ld32(tDP + lane_sel + c0, rp);
-      tmem_ld_wait();
-      float ds[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int c = c0 + i;
-        float pr = exp2f(fmaf(__uint_as_float(rs[i]), p.scale_log2, -lse2));
-        if (any_mask) pr = (bias_s[c] != 0.f) ? 0.f : pr;
-        if (diag && c > r) pr = 0.f;
-        const float dm = (kw & (1u << i)) ? p.inv_keep : 0.f;
-        ds[i] = pr * fmaf(__uint_as_float(rp[i]), dm, -dvec);
+    for (int j = 0; j < nkv; ++j) {
+      const int st = j & 1, u = j >> 1;
+      if (u > 0) mbar_wait(bar_kve + 8 * st, (u - 1) & 1);
+      if (lane == 0) {
+        mbar_expect_tx(bar_kvf + 8 * st, 2 * QKV_BYTES);
+        load_tile(&tmK, bar_kvf + 8 * st, sK + st * QKV_BYTES, h * DH, j * TILE, b);
+        load_tile(&tmV, bar_kvf + 8 * st, sV + st * QKV_BYTES, h * DH, j * TILE, b);
       }
-      store_row32_sw128(sDS, r, c0, ds);
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
+      uint32_t any = 0;
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        tc_mma_bf16(tDQ, desc_k128(sDS, k), desc_mn64(sK, k), idesc_g, (j > 0 || k > 0) ? 1u : 0u);
-      if (j + 1 == nkv) tc_commit(bar_mma);
+      for (int i = 0; i < 4; ++i) {
+        const int c = lane * 4 + i, kv = j * TILE + c;
+        uint8_t m = kv >= p.Lk ? 1 : 0;
+        if (!m && p.kpm) m = p.kpm[(long long)b * p.Lk + kv] != 0;
+        mask_s[st * 128 + c] = m;
+        any |= m;
+      }
+      any = __any_sync(0xffffffffu, any != 0);
+      if (lane == 0) anym_s[st] = any;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_mkf + 8 * st);
     }
-  }
-  if (nkv > 0) {
-    mbar_wait(bar_mma, nkv & 1);
-    tc_fence_after();
-  }
-  {
-    __nv_bfloat16* dst = p.dq + ((long long)b * p.Lq + q) * p.ldq_out + h * DH;
+  } else if (warp == 8) {
+    if (lane == 0 && nkv > 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);
+      constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, false, true);
+      auto issue_s = [&](int hh, int st) {  // S_h and dP_h of the key tile staged in `st`
+        const uint32_t kh = sK + st * QKV_BYTES + hh * 4096, vh = sV + st * QKV_BYTES + hh * 4096;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) tc_mma_bf16(tmem + 64 * hh, desc_k64(sQ, k), desc_k64(kh, k), idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) tc_mma_bf16(tmem + 128 + 64 * hh, desc_k64(sdO, k), desc_k64(vh, k), idesc_s, k > 0);
+        tc_commit(bar_sf + 8 * hh);
+      };
+      mbar_wait(bar_q, 0);
+      mbar_wait(bar_kvf, 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j & 1;
+        if (j + 1 < nkv) {
+          mbar_wait(bar_kvf + 8 * (st ^ 1), ((j + 1) >> 1) & 1);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          mbar_wait(bar_pf + 8 * hh, j & 1);  // dS_h(j) in smem; S_h / dP_h consumed
+          tc_fence_after();
+          const uint32_t kh = sK + st * QKV_BYTES + hh * 4096;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_bf16(tmem + 256, desc_k128h(sDS + hh * HALF_BYTES, k), desc_mn64(kh, k), idesc_g,
+                        (j > 0 || hh > 0 || k > 0) ? 1u : 0u);
+          tc_commit(bar_dsd + 8 * hh);
+          if (j + 1 < nkv) issue_s(hh, st ^ 1);
+        }
+        tc_commit(bar_kve + 8 * st);
+      }
+    }
+  } else {
+    const int hh = warp >> 2, quad = warp & 3;  // warpgroup hh owns key columns [64 hh, 64 hh + 64) of every tile
+    const int r = quad * 32 + lane;
+    const int q = q0 + r;
+    const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tS = tmem + 64 * hh, tDP = tmem + 128 + 64 * hh;
+    const uint32_t sDSh = sDS + hh * HALF_BYTES;
+    const long long stat_o = ((long long)b * p.H + h) * p.Lq + q;
+    const float lse2 = q < p.Lq ? p.lse2[stat_o] : INFINITY;
+    const float dvec = q < p.Lq ? p.dvec[stat_o] : 0.f;
+    const uint32_t bh = (uint32_t)(b * p.H + h);
+    const DropKey dkey = drop_key(p);
+    for (int j = 0; j < nkv; ++j) {
+      const int st = j & 1;
+      const int kv0 = j * TILE + hh * 64;
+      const uint32_t kw0 = keep_word(p, dkey, bh, (uint32_t)q, (uint32_t)(kv0 >> 5));  // index-only: before the waits
+      const uint32_t kw1 = keep_word(p, dkey, bh, (uint32_t)q, (uint32_t)(kv0 >> 5) + 1);
+      mbar_wait(bar_mkf + 8 * st, (j >> 1) & 1);
+      const bool any_mask = anym_s[st] != 0;
+      mbar_wait(bar_sf + 8 * hh, j & 1);
+      tc_fence_after();
+      const bool diag = p.causal && (j == qt);
+      if (j > 0) mbar_wait(bar_dsd + 8 * hh, (j - 1) & 1);  // dS_h buffer free again
 #pragma unroll 1
-    for (int c = half * 2; c < (half == 0 ? 2 : 3); ++c) {
-      uint32_t rr[32];
-      if (nkv > 0) {
-        tmem_ld32(tDQ + lane_sel + c * 32, rr);
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c0 = cc * 32;
+        const uint32_t kw = cc == 0 ? kw0 : kw1;
+        uint32_t rs[32], rp[32];
+        tmem_ld32(tS + lane_sel + c0, rs);
+        tmem_ld32(tDP + lane_sel + c0, rp);
         tmem_ld_wait();
-      } else {
+        float ds[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) rr[i] = 0u;
+        for (int i = 0; i < 32; ++i) {
+          const int c = hh * 64 + c0 + i;  // key column inside the 128-key tile
+          float pr = exp2f(fmaf(__uint_as_float(rs[i]), p.scale_log2, -lse2));
+          if (any_mask) pr = mask_s[st * 128 + c] ? 0.f : pr;
+          if (diag && c > r) pr = 0.f;
+          const float dm = (kw & (1u << i)) ? p.inv_keep : 0.f;
+          ds[i] = pr * fmaf(__uint_as_float(rp[i]), dm, -dvec);
+        }
+        store_row32_sw128(sDSh, r, c0, ds);
       }
-      if (q < p.Lq) {
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pf + 8 * hh);
+    }
+    // epilogue: dQ * scale -> bf16; warpgroup 0 stores columns [0,64), warpgroup 1 columns [64,96)
+    if (nkv > 0) {
+      mbar_wait(bar_dsd + 8, (nkv - 1) & 1);  // the last gradient GEMM (half 1 of the last key tile)
+      tc_fence_after();
+    }
+    {
+      __nv_bfloat16* dst = p.dq + ((long long)b * p.Lq + q) * p.ldq_out + h * DH;
+#pragma unroll 1
+      for (int c = hh * 2; c < (hh == 0 ? 2 : 3); ++c) {
+        uint32_t rr[32];
+        if (nkv > 0) {
+          tmem_ld32(tmem + 256 + lane_sel + c * 32, rr);
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {
-          uint4 u;
-          u.x = pack_bf16(__uint_as_float(rr[8 * qd]) * p.scale, __uint_as_float(rr[8 * qd + 1]) * p.scale);
-          u.y = pack_bf16(__uint_as_float(rr[8 * qd + 2]) * p.scale, __uint_as_float(rr[8 * qd + 3]) * p.scale);
-          u.z = pack_bf16(__uint_as_float(rr[8 * qd + 4]) * p.scale, __uint_as_float(rr[8 * qd + 5]) * p.scale);
-          u.w = pack_bf16(__uint_as_float(rr[8 * qd + 6]) * p.scale, __uint_as_float(rr[8 * qd + 7]) * p.scale);
-          *reinterpret_cast<uint4*>(dst + c * 32 + qd * 8) = u;
+          for (int i = 0; i < 32; ++i) rr[i] = 0u;
+        }
+        if (q < p.Lq) {
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            uint4 u;
+            u.x = pack_bf16(__uint_as_float(rr[8 * qd]) * p.scale, __uint_as_float(rr[8 * qd + 1]) * p.scale);
+            u.y = pack_bf16(__uint_as_float(rr[8 * qd + 2]) * p.scale, __uint_as_float(rr[8 * qd + 3]) * p.scale);
+            u.z = pack_bf16(__uint_as_float(rr[8 * qd + 4]) * p.scale, __uint_as_float(rr[8 * qd + 5]) * p.scale);
+            u.w = pack_bf16(__uint_as_float(rr[8 * qd + 6]) * p.scale, __uint_as_float(rr[8 * qd + 7]) * p.scale);
+            *reinterpret_cast<uint4*>(dst + c * 32 + qd * 8) = u;
+          }
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 512);
+  if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+// ---- dK/dV: one CTA per (key tile, head, batch); query tiles stream through in 64-query halves ----
+//   S^T_h = K Q_h^T, dP^T_h = V dO_h^T (TMEM, rows = keys) -> P^T_h, dS^T_h (bf16, smem)
+//   -> dV += P^T_h dO_h, dK += dS^T_h Q_h
+constexpr int BWD3_KV_SMEM = 1024 + 2 * QKV_BYTES + 4 * QKV_BYTES + 4 * HALF_BYTES + 4096;
+
+__global__ void __launch_bounds__(BWD3_THREADS, 1)
+attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                      const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sK = base, sV = sK + QKV_BYTES;
+  const uint32_t sQ = sV + QKV_BYTES;            // [2] stages
+  const uint32_t sdO = sQ + 2 * QKV_BYTES;       // [2] stages
+  const uint32_t sPT = sdO + 2 * QKV_BYTES;      // [2] halves
+  const uint32_t sDST = sPT + 2 * HALF_BYTES;    // [2] halves
+  const uint32_t aux = sDST + 2 * HALF_BYTES;
+  float* lse_s = reinterpret_cast<float*>(gen + (aux - base));  // [2][128]
+  float* dv_s = lse_s + 256;                                     // [2][128]
+  int* ext_slot = reinterpret_cast<int*>(gen + (aux + 2048 - base));
+  const uint32_t bar0 = aux + 2560;
+  const uint32_t bar_kv = bar0, bar_qf = bar0 + 8, bar_qe = bar0 + 24, bar_stf = bar0 + 40, bar_sf = bar0 + 56,
+                 bar_pf = bar0 + 72, bar_gd = bar0 + 88;
+  const uint32_t tmem_ptr_addr = bar0 + 112;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen + (tmem_ptr_addr - base));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int jt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int kv0 = jt * TILE;
+  const int nq_tiles = (p.Lq + TILE - 1) / TILE;
+  const int i_begin = p.causal ? jt : 0;
+
+  if (tid == 0) {
+    mbar_init(bar_kv, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_qf + 8 * i, 1);
+      mbar_init(bar_qe + 8 * i, 1);
+      mbar_init(bar_stf + 8 * i, 1);
+      mbar_init(bar_sf + 8 * i, 1);
+      mbar_init(bar_pf + 8 * i, 4);
+      mbar_init(bar_gd + 8 * i, 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_ptr_addr, 512);
+  const int n_it = (kv0 < kv_extent(p, b, ext_slot)) ? nq_tiles - i_begin : 0;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_gen;
+  // TMEM columns: S^T_h at 64h, dP^T_h at 128 + 64h, dV at 256, dK at 352
+  if (warp == 9) {
+    if (lane == 0 && n_it > 0) {
+      mbar_expect_tx(bar_kv, 2 * QKV_BYTES);
+      load_tile(&tmK, bar_kv, sK, h * DH, kv0, b);
+      load_tile(&tmV, bar_kv, sV, h * DH, kv0, b);
+    }
+    for (int it = 0; it < n_it; ++it) {
+      const int st = it & 1, u = it >> 1;
+      const int q0 = (i_begin + it) * TILE;
+      if (u > 0) mbar_wait(bar_qe + 8 * st, (u - 1) & 1);
+      if (lane == 0) {
+        mbar_expect_tx(bar_qf + 8 * st, 2 * QKV_BYTES);
+        load_tile(&tmQ, bar_qf + 8 * st, sQ + st * QKV_BYTES, h * DH, q0, b);
+        load_tile(&tmdO, bar_qf + 8 * st, sdO + st * QKV_BYTES, h * DH, q0, b);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = lane * 4 + i, qq = q0 + c;
+        const long long o = ((long long)b * p.H + h) * p.Lq + qq;
+        lse_s[st * 128 + c] = qq < p.Lq ? p.lse2[o] : INFINITY;
+        dv_s[st * 128 + c] = qq < p.Lq ? p.dvec[o] : 0.f;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_stf + 8 * st);
+    }
+  } else if (warp == 8) {
+    if (lane == 0 && n_it > 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);
+      constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, false, true);
+      auto issue_s = [&](int hh, int st) {
+        const uint32_t qh = sQ + st * QKV_BYTES + hh * 4096, doh = sdO + st * QKV_BYTES + hh * 4096;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) tc_mma_bf16(tmem + 64 * hh, desc_k64(sK, k), desc_k64(qh, k), idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) tc_mma_bf16(tmem + 128 + 64 * hh, desc_k64(sV, k), desc_k64(doh, k), idesc_s, k > 0);
+        tc_commit(bar_sf + 8 * hh);
+      };
+      mbar_wait(bar_kv, 0);
+      mbar_wait(bar_qf, 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it & 1;
+        if (it + 1 < n_it) {
+          mbar_wait(bar_qf + 8 * (st ^ 1), ((it + 1) >> 1) & 1);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          mbar_wait(bar_pf + 8 * hh, it & 1);
+          tc_fence_after();
+          const uint32_t qh = sQ + st * QKV_BYTES + hh * 4096, doh = sdO + st * QKV_BYTES + hh * 4096;
+          const uint32_t acc = (it > 0 || hh > 0) ? 1u : 0u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_bf16(tmem + 256, desc_k128h(sPT + hh * HALF_BYTES, k), desc_mn64(doh, k), idesc_g, (acc || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_bf16(tmem + 352, desc_k128h(sDST + hh * HALF_BYTES, k), desc_mn64(qh, k), idesc_g, (acc || k > 0) ? 1u : 0u);
+          tc_commit(bar_gd + 8 * hh);
+          if (it + 1 < n_it) issue_s(hh, st ^ 1);
+        }
+        tc_commit(bar_qe + 8 * st);
+      }
+    }
+  } else {
+    const int hh = warp >> 2, quad = warp & 3;  // warpgroup hh owns query columns [64 hh, 64 hh + 64) of every tile
+    const int r = quad * 32 + lane;  // local key row
+    const int kv = kv0 + r;
+    const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tST = tmem + 64 * hh, tDPT = tmem + 128 + 64 * hh;
+    const uint32_t sPTh = sPT + hh * HALF_BYTES, sDSTh = sDST + hh * HALF_BYTES;
+    bool row_valid = kv < p.Lk;
+    if (row_valid && p.kpm) row_valid = p.kpm[(long long)b * p.Lk + kv] == 0;
+    const uint32_t bh = (uint32_t)(b * p.H + h);
+    const DropKey dkey = drop_key(p);
+    for (int it = 0; it < n_it; ++it) {
+      const int st = it & 1;
+      const int qi = i_begin + it;
+      const int q0 = qi * TILE + hh * 64;  // first query of this half
+      // keep bits of (q = q0 + c0 + i, k = this thread's key row): lane L makes the word of query q0 + c0 + L over the
+      // warp's 32 keys, then the warp transposes the 32x32 bit tile (index-only work, done before the waits)
+      uint32_t kw0 = keep_word(p, dkey, bh, (uint32_t)(q0 + lane), (uint32_t)((kv0 >> 5) + quad));
+      uint32_t kw1 = keep_word(p, dkey, bh, (uint32_t)(q0 + 32 + lane), (uint32_t)((kv0 >> 5) + quad));
+      if (p.thresh16 != 0) {
+        kw0 = warp_bit_transpose(kw0, lane);
+        kw1 = warp_bit_transpose(kw1, lane);
+      }
+      mbar_wait(bar_stf + 8 * st, (it >> 1) & 1);
+      mbar_wait(bar_sf + 8 * hh, it & 1);
+      tc_fence_after();
+      const bool diag = p.causal && (qi == jt);
+      if (it > 0) mbar_wait(bar_gd + 8 * hh, (it - 1) & 1);  // P^T_h / dS^T_h buffers free again
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c0 = cc * 32;
+        const uint32_t kw = cc == 0 ? kw0 : kw1;
+        uint32_t rs[32], rp[32];
+        tmem_ld32(tST + lane_sel + c0, rs);
+        tmem_ld32(tDPT + lane_sel + c0, rp);
+        tmem_ld_wait();
+        float pd[32], ds[32];
+        if (row_valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c = hh * 64 + c0 + i;  // query column inside the 128-query tile
+            float pr = exp2f(fmaf(__uint_as_float(rs[i]), p.scale_log2, -lse_s[st * 128 + c]));
+            if (diag && r > c) pr = 0.f;
+            const float dm = (kw & (1u << i)) ? p.inv_keep : 0.f;
+            pd[i] = pr * dm;
+            ds[i] = pr * fmaf(__uint_as_float(rp[i]), dm, -dv_s[st * 128 + c]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pd[i] = ds[i] = 0.f;
+        }
+        store_row32_sw128(sPTh, r, c0, pd);
+        store_row32_sw128(sDSTh, r, c0, ds);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pf + 8 * hh);
+    }
+    if (n_it > 0) {
+      mbar_wait(bar_gd + 8, (n_it - 1) & 1);
+      tc_fence_after();
+    }
+    {
+      // warpgroup 0 drains dV, warpgroup 1 drains dK (scaled)
+      const uint32_t src = tmem + (hh == 0 ? 256 : 352);
+      const float sc = hh == 0 ? 1.0f : p.scale;
+      __nv_bfloat16* dst = (hh == 0 ? p.dv : p.dk) + ((long long)b * p.Lk + kv) * p.ldkv_out + h * DH;
+#pragma unroll 1
+      for (int c = 0; c < 3; ++c) {
+        uint32_t rr[32];
+        if (n_it > 0) {
+          tmem_ld32(src + lane_sel + c * 32, rr);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) rr[i] = 0u;
+        }
+        if (kv < p.Lk) {
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            uint4 u;
+            u.x = pack_bf16(__uint_as_float(rr[8 * qd]) * sc, __uint_as_float(rr[8 * qd + 1]) * sc);
+            u.y = pack_bf16(__uint_as_float(rr[8 * qd + 2]) * sc, __uint_as_float(rr[8 * qd + 3]) * sc);
+            u.z = pack_bf16(__uint_as_float(rr[8 * qd + 4]) * sc, __uint_as_float(rr[8 * qd + 5]) * sc);
+            u.w = pack_bf16(__uint_as_float(rr[8 * qd + 6]) * sc, __uint_as_float(rr[8 * qd + 7]) * sc);
+            *reinterpret_cast<uint4*>(dst + c * 32 + qd * 8) = u;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
 // -----------------------------------------------------------------------------------------------
@@ -862,18 +956,18 @@ int32_t sct_attn_bwd(const void* q, int64_t ldq, const void* k, const void* v, i
   if (int rc = make_qkv_map(&tdo, d_o, ldo, B, Lq, H)) return rc;
   static bool attr = false;
   if (!attr) {
-    SCT_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_KV_SMEM));
-    SCT_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_Q_SMEM));
+    SCT_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD3_KV_SMEM));
+    SCT_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD3_Q_SMEM));
     attr = true;
   }
   {
     dim3 grid((unsigned)((Lk + TILE - 1) / TILE), (unsigned)H, (unsigned)B);
-    attn_bwd_dkdv_kernel<<<grid, 256, BWD_KV_SMEM, st>>>(tq, tk, tv, tdo, p);
+    attn_bwd_dkdv_kernel<<<grid, BWD3_THREADS, BWD3_KV_SMEM, st>>>(tq, tk, tv, tdo, p);
     SCT_LAUNCH_CHECK();
   }
   {
     dim3 grid((unsigned)((Lq + TILE - 1) / TILE), (unsigned)H, (unsigned)B);
-    attn_bwd_dq_kernel<<<grid, 256, BWD_Q_SMEM, st>>>(tq, tk, tv, tdo, p);
+    attn_bwd_dq_kernel<<<grid, BWD3_THREADS, BWD3_Q_SMEM, st>>>(tq, tk, tv, tdo, p);
     SCT_LAUNCH_CHECK();
   }
   return 0;

@@ -104,21 +104,28 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return done;
 }
-// Bounded wait: returns false (and raises g_timeout_flag) after ~2 s instead of hanging.
-static __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity) {
-  const uint64_t t0 = globaltimer_ns();
-  while (true) {
-    if (mbar_try_wait(bar, parity)) return true;
-    if (*reinterpret_cast<volatile int*>(&g_timeout_flag)) return false;
-    if (globaltimer_ns() - t0 > 2000000000ull) {
-      atomicExch(&g_timeout_flag, 1);
-      return false;
-    }
+// Bounded wait.  mbarrier.try_wait suspends the thread in hardware until the phase completes or an internal
+// time limit expires, so the loop itself is cheap; the safety net (a descriptor or phase bug then yields garbage
+// plus a flag instead of a hung GPU) only looks at the wall clock / the shared flag every 2^14 wake-ups —
+// reading %globaltimer and a global flag on every iteration costs ~1k cycles per hand-off.
+static __device__ __noinline__ bool mbar_wait_timeout_check(uint64_t& t0) {
+  if (*reinterpret_cast<volatile int*>(&g_timeout_flag)) return true;
+  const uint64_t now = globaltimer_ns();
+  if (t0 == 0) {
+    t0 = now;
+  } else if (now - t0 > 4000000000ull) {
+    atomicExch(&g_timeout_flag, 1);
+    return true;
   }
+  return false;
 }
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return true;
-  return mbar_wait_slow(bar, parity);
+  uint64_t t0 = 0;
+#pragma unroll 1
+  for (uint32_t spins = 1;; ++spins) {
+    if (mbar_try_wait(bar, parity)) return true;
+    if ((spins & 0x3FFFu) == 0 && mbar_wait_timeout_check(t0)) return false;
+  }
 }
 
 // ---- proxy / tcgen05 fences -----------------------------------------------------------------
