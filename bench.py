@@ -288,7 +288,7 @@ def main():
 
     # ---- roofline: one extra instrumented step, CUDA events around every launch of the dominant kernels
     tf_peak, hbm_peak, peak_src = peaks()
-    _lib.Stats.timed = ("sct_gemm_bf16_nt", "sct_gemm_bf16_nn", "sct_gemm_bf16_tn", "sct_attn_fwd", "sct_attn_bwd",
+    _lib.Stats.timed = ("sct_gemm_bf16_nt", "sct_gemm_bf16_nn", "sct_gemm_bf16_tn", "sct_attn_fwd_strided", "sct_attn_bwd",
                         "sct_add_dropout_ln_fwd")
     _lib.Stats.events = []
     e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

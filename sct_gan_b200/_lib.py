@@ -38,6 +38,8 @@ SIGNATURES = {
     "sct_gemm_bf16_tn": [_p, _i64, _p, _i64, _p, _i64, _f, _i64, _i64, _i64, _i32, _p],
     "sct_attn_fwd": [_p, _i64, _p, _p, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _f, _f,
                      _u64, _u64, _p],
+    "sct_attn_fwd_strided": [_p, _i64, _p, _p, _i64, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _f,
+                             _f, _u64, _u64, _p],
     "sct_attn_bwd": [_p, _i64, _p, _p, _i64, _p, _p, _i64, _p, _p, _p, _i64, _p, _p, _i64, _p, _i64, _i64,
                      _i64, _i64, _i64, _i32, _f, _f, _u64, _u64, _p],
     "sct_ce_rows": [_p, _p, _p, _p, _i64, _i64, _i64, _f, _i32, _p],

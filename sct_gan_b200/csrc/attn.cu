@@ -843,9 +843,11 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 }
 
 // -----------------------------------------------------------------------------------------------
-int make_qkv_map(CUtensorMap* m, const void* ptr, int64_t ld, int64_t B, int64_t L, int64_t H) {
-  return make_tmap_3d(m, ptr, 2, (uint64_t)(H * DH), (uint64_t)L, (uint64_t)B, (uint64_t)ld * 2,
-                      (uint64_t)L * ld * 2, 32, TILE, SWZ_64);
+int make_qkv_map(CUtensorMap* m, const void* ptr, int64_t ld, int64_t B, int64_t L, int64_t H,
+                 int64_t batch_stride = 0) {
+  const uint64_t bs = batch_stride > 0 ? (uint64_t)batch_stride : (uint64_t)L * ld;
+  return make_tmap_3d(m, ptr, 2, (uint64_t)(H * DH), (uint64_t)L, (uint64_t)B, (uint64_t)ld * 2, bs * 2, 32, TILE,
+                      SWZ_64);
 }
 
 int fill_params(AttnParams& p, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int32_t causal, float scale,
@@ -899,10 +901,10 @@ using namespace sct;
 
 extern "C" {
 
-int32_t sct_attn_fwd(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* o,
-                     int64_t ldo, float* lse2, const uint8_t* kpm, int64_t B, int64_t H, int64_t Lq,
-                     int64_t Lk, int64_t head_dim, int32_t causal, float scale, float p_drop,
-                     uint64_t seed, uint64_t offset, void* stream) {
+int32_t sct_attn_fwd_strided(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                             int64_t kv_batch_stride, void* o, int64_t ldo, float* lse2, const uint8_t* kpm,
+                             int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t head_dim, int32_t causal,
+                             float scale, float p_drop, uint64_t seed, uint64_t offset, void* stream) {
   SCT_CHECK(q && k && v && o, "null pointer");
   SCT_CHECK(head_dim == DH, "head_dim %lld unsupported (kernel is specialised for 96)", (long long)head_dim);
   SCT_CHECK(ldo % 8 == 0, "ldo must be a multiple of 8");
@@ -913,8 +915,10 @@ int32_t sct_attn_fwd(const void* q, int64_t ldq, const void* k, const void* v, i
   p.lse2 = lse2;
   CUtensorMap tq, tk, tv;
   if (int rc = make_qkv_map(&tq, q, ldq, B, Lq, H)) return rc;
-  if (int rc = make_qkv_map(&tk, k, ldkv, B, Lk, H)) return rc;
-  if (int rc = make_qkv_map(&tv, v, ldkv, B, Lk, H)) return rc;
+  SCT_CHECK(kv_batch_stride == 0 || (kv_batch_stride >= Lk * ldkv && kv_batch_stride % 8 == 0),
+            "kv_batch_stride must be 0 or a multiple of 8 >= Lk * ldkv");
+  if (int rc = make_qkv_map(&tk, k, ldkv, B, Lk, H, kv_batch_stride)) return rc;
+  if (int rc = make_qkv_map(&tv, v, ldkv, B, Lk, H, kv_batch_stride)) return rc;
   static bool attr = false;
   if (!attr) {
     SCT_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
@@ -924,6 +928,14 @@ int32_t sct_attn_fwd(const void* q, int64_t ldq, const void* k, const void* v, i
   attn_fwd_kernel<<<grid, 256, FWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
   SCT_LAUNCH_CHECK();
   return 0;
+}
+
+int32_t sct_attn_fwd(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* o,
+                     int64_t ldo, float* lse2, const uint8_t* kpm, int64_t B, int64_t H, int64_t Lq,
+                     int64_t Lk, int64_t head_dim, int32_t causal, float scale, float p_drop,
+                     uint64_t seed, uint64_t offset, void* stream) {
+  return sct_attn_fwd_strided(q, ldq, k, v, ldkv, 0, o, ldo, lse2, kpm, B, H, Lq, Lk, head_dim, causal, scale, p_drop,
+                              seed, offset, stream);
 }
 
 int32_t sct_attn_bwd(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,

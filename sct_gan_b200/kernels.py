@@ -236,8 +236,9 @@ def gemm_tn(a, b, out, alpha=1.0, k_splits=0):
 
 # ---------------------------------------------------------------------------------------------- K3
 def attn_fwd(q, k, v, B, H, Lq, Lk, kpm=None, causal=False, scale=None, p_drop=0.0, seed=0, offset=0,
-             head_dim=96):
-    """q [B*Lq, ld], k/v [B*Lk, ld] 2-D bf16 views (may be column slices of a packed projection)."""
+             head_dim=96, kv_batch_stride=0):
+    """q [B*Lq, ld], k/v [B*Lk, ld] 2-D bf16 views (may be column slices of a packed projection).
+    kv_batch_stride (elements) > 0: k/v are views into a [B, T_max, ld] cache of which rows [0, Lk) are used."""
     q, ldq = _rows2d(q, BF16, "q")
     k, ldk = _rows2d(k, BF16, "k")
     v, ldv = _rows2d(v, BF16, "v")
@@ -249,7 +250,8 @@ def attn_fwd(q, k, v, B, H, Lq, Lk, kpm=None, causal=False, scale=None, p_drop=0
     if kpm is not None:
         assert kpm.dtype in (torch.uint8, torch.bool) and kpm.is_contiguous() and kpm.shape == (B, Lk)
     _lib.Stats.annotate(4.0 * B * H * Lq * Lk * head_dim * (0.5 if causal else 1.0))
-    _lib.call("sct_attn_fwd", _ptr(q), ldq, _ptr(k), _ptr(v), ldk, _ptr(o), o.stride(0), _ptr(lse2),
+    _lib.call("sct_attn_fwd_strided", _ptr(q), ldq, _ptr(k), _ptr(v), ldk, int(kv_batch_stride), _ptr(o), o.stride(0),
+              _ptr(lse2),
               kpm.data_ptr() if kpm is not None else None, B, H, Lq, Lk, head_dim, int(causal),
               float(scale), float(p_drop), seed, offset, _stream())
     return o, lse2

@@ -9,7 +9,7 @@ cross-entropy (K4b) and the integrated discriminator (K5) — runs in the sm_100
 libsct_b200.so.  There is no CPU path: tensors must live on a B200.
 
 Additive, keyword-only extensions (reference-preserving defaults): `fused_loss`, `return_logits`,
-`compute_vuln_heads`, `greedy`, `max_new_tokens`.
+`compute_vuln_heads`, `greedy`, `max_new_tokens`, `n_lines`, `use_kv_cache`.
 """
 from __future__ import annotations
 
@@ -345,7 +345,8 @@ class SmartContractTransformer(nn.Module):
     # --------------------------------------------------------------------------------- forward
     def forward(self, input_ids, attention_mask=None, ast_input_ids=None, ast_attention_mask=None,
                 target_ids=None, token_to_line=None, apply_syntax_constraints=True, *, fused_loss=False,
-                return_logits=True, compute_vuln_heads=True, greedy=False, max_new_tokens=None, n_lines=None):
+                return_logits=True, compute_vuln_heads=True, greedy=False, max_new_tokens=None, n_lines=None,
+                use_kv_cache=True):
         if not input_ids.is_cuda:
             raise RuntimeError("sct_gan_b200 runs on a B200 only (no CPU fallback): move the batch to cuda")
         B, S = input_ids.shape
@@ -373,7 +374,7 @@ class SmartContractTransformer(nn.Module):
             contract_logits = line_logits = None
 
         if target_ids is None:
-            seq = self._generate(mem_b, B, S, src_kpm, apply_syntax_constraints, greedy, max_new_tokens)
+            seq = self._generate(mem_b, B, S, src_kpm, apply_syntax_constraints, greedy, max_new_tokens, use_kv_cache)
             return {"generated_sequence": seq, "contract_vulnerability_logits": contract_logits,
                     "line_vulnerability_logits": line_logits}
 
@@ -412,9 +413,76 @@ class SmartContractTransformer(nn.Module):
             logits[:, 59] = torch.where(hit, logits[:, 59] * 2.0, logits[:, 59])
         return logits
 
+    def _sample(self, logits, tgt, apply_syntax_constraints, greedy):
+        """model.py:892-918: temperature 0.7, syntax tweak, top-k 50, top-p 0.95, multinomial (or argmax)."""
+        logits = logits.float() / 0.7
+        if apply_syntax_constraints:
+            logits = self._apply_syntax_constraints(logits, tgt)
+        if greedy:
+            return logits.argmax(dim=-1, keepdim=True)
+        topv, topi = torch.topk(logits, 50, dim=-1)
+        probs = torch.softmax(topv, dim=-1)
+        remove = torch.cumsum(probs, dim=-1) > 0.95
+        remove[:, 1:] = remove[:, :-1].clone()
+        remove[:, 0] = False
+        probs = torch.softmax(topv.masked_fill(remove, float("-inf")), dim=-1)
+        return topi.gather(1, torch.multinomial(probs, 1))
+
+    def _stop(self, nxt, i):
+        """model.py:923-930 (batch-wide early stop; a host decision in the reference as well)."""
+        stop = ((nxt == 2).any() | (nxt == 0).any()).item()
+        return (stop and i > 50) or (i > 20 and bool((nxt == 2).all().item()))
+
     @torch.no_grad()
-    def _generate(self, mem_b, B, S, src_kpm, apply_syntax_constraints, greedy, max_new_tokens):
-        """model.py:862-930: BOS = 1, temperature 0.7, top-k 50, top-p 0.95, multinomial; same stop rules."""
+    def _generate(self, mem_b, B, S, src_kpm, apply_syntax_constraints, greedy, max_new_tokens, use_kv_cache=True):
+        """The sampling loop of model.py:862-930 (BOS = 1) with a KV cache: the reference re-embeds and re-decodes the
+        whole prefix for every new token (O(T^2) decoder passes); here each step runs the decoder on ONE position,
+        attending to cached self-attention K/V ([B, T_max, 2d] per layer) and to cross-attention K/V of the encoder
+        memory projected once.  Same arithmetic per position, so greedy tokens match the reference."""
+        if not use_kv_cache:
+            return self._generate_recompute(mem_b, B, S, src_kpm, apply_syntax_constraints, greedy, max_new_tokens)
+        dev, d, H = mem_b.device, self.d_model, self.nhead
+        max_len = min(self.max_length, 1024)
+        steps = max_len - 1 if max_new_tokens is None else min(max_len - 1, max_new_tokens)
+        layers = self.decoder.layers
+        ol = self.output_layer
+        pe = self.pos_encoder.pe.view(-1, d)
+        t_max = (steps + 127) // 128 * 128
+        self_kv = [torch.zeros((B, t_max, 2 * d), dtype=BF16, device=dev) for _ in layers]
+        mem_kv = [self._lin_rows(mem_b, l.multihead_attn.in_proj_weight, l.multihead_attn.in_proj_bias, d, 3 * d)
+                  for l in layers]  # [B*S, 2d] each, projected once
+        tgt = torch.ones((B, steps + 1), dtype=torch.long, device=dev)
+        n_out = 1
+        for i in range(steps):
+            ids = tgt[:, i:i + 1].contiguous()
+            x, _ = ops.embed_ln_pe(ids, self.embedding.weight, self.embedding_norm.weight, self.embedding_norm.bias,
+                                   pe[i:], 1, math.sqrt(d), 0.0, True, False)
+            _, y = ops.residual_ln(x, None, layers[0].norm1.weight, layers[0].norm1.bias, mode="ln", want_x=False)
+            for li, layer in enumerate(layers):
+                sa = layer.self_attn
+                qkv = ops.linear(y, sa.in_proj_weight, sa.in_proj_bias, self._w(sa.in_proj_weight))
+                self_kv[li][:, i, :] = qkv[:, d:]
+                a = ops.cached_attention(qkv[:, :d], self_kv[li], B, H, i + 1)
+                x, y = ops.residual_ln(x, self._lin(a, sa.out_proj), layer.norm2.weight, layer.norm2.bias, 1.0, 0.0, "ln")
+                ca = layer.multihead_attn
+                q = self._lin_rows(y, ca.in_proj_weight, ca.in_proj_bias, 0, d)
+                c = ops.cross_attention(q, mem_kv[li], B, H, 1, S, src_kpm, 0.0)
+                x, y = ops.residual_ln(x, self._lin(c, ca.out_proj), layer.norm3.weight, layer.norm3.bias, 1.0, 0.0, "ln")
+                f = self._ffn(y, layer)
+                nxt_norm = layers[li + 1].norm1 if li + 1 < len(layers) else self.output_norm
+                x, y = ops.residual_ln(x, f, nxt_norm.weight, nxt_norm.bias, 1.0, 0.0, "ln")
+            logits = ops.linear(y, ol.weight, ol.bias, self._w(ol.weight))
+            nxt = self._sample(logits, tgt[:, :i + 1], apply_syntax_constraints, greedy)
+            tgt[:, i + 1] = nxt.view(-1)
+            n_out = i + 2
+            if max_new_tokens is None and self._stop(nxt, i):
+                break
+        return tgt[:, :n_out].contiguous()
+
+    @torch.no_grad()
+    def _generate_recompute(self, mem_b, B, S, src_kpm, apply_syntax_constraints, greedy, max_new_tokens):
+        """The reference's own schedule (whole prefix re-decoded per token) on the fused decoder; kept as the
+        cross-check of the KV-cached path."""
         dev = mem_b.device
         tgt = torch.ones((B, 1), dtype=torch.long, device=dev)
         max_len = min(self.max_length, 1024)
@@ -425,23 +493,9 @@ class SmartContractTransformer(nn.Module):
             tx, _ = self._embed(tgt, self.embedding, self.embedding_norm, True, False)
             h = self._decode(tx, mem_b, B, T, S, src_kpm)
             last = h.view(B, T, -1)[:, -1, :].contiguous()
-            logits = ops.linear(last, ol.weight, ol.bias, self._w(ol.weight)).float() / 0.7
-            if apply_syntax_constraints:
-                logits = self._apply_syntax_constraints(logits, tgt)
-            if greedy:
-                nxt = logits.argmax(dim=-1, keepdim=True)
-            else:
-                topv, topi = torch.topk(logits, 50, dim=-1)
-                probs = torch.softmax(topv, dim=-1)
-                cum = torch.cumsum(probs, dim=-1)
-                remove = cum > 0.95
-                remove[:, 1:] = remove[:, :-1].clone()
-                remove[:, 0] = False
-                probs = torch.softmax(topv.masked_fill(remove, float("-inf")), dim=-1)
-                nxt = topi.gather(1, torch.multinomial(probs, 1))
+            logits = ops.linear(last, ol.weight, ol.bias, self._w(ol.weight))
+            nxt = self._sample(logits, tgt, apply_syntax_constraints, greedy)
             tgt = torch.cat([tgt, nxt], dim=1)
-            if max_new_tokens is None:
-                stop = ((nxt == 2).any() | (nxt == 0).any()).item()
-                if (stop and i > 50) or (i > 20 and bool((nxt == 2).all().item())):
-                    break
+            if max_new_tokens is None and self._stop(nxt, i):
+                break
         return tgt

@@ -361,6 +361,18 @@ def cross_attention(q, kv, B, H, Lq, Lk, kpm=None, p_drop=0.0):
     return CrossAttention.apply(q, kv, B, H, Lq, Lk, kpm, p_drop)
 
 
+@torch.no_grad()
+def cached_attention(q, kv_cache, B, H, Lk, kpm=None):
+    """Decode-step attention (inference only): q [B, d] (one new position per sequence) against rows [0, Lk) of a
+    [B, T_max, 2d] k|v cache; no dropout, no autograd."""
+    d = q.shape[1]
+    t_max = kv_cache.shape[1]
+    flat = kv_cache.view(B * t_max, 2 * d)
+    o, _ = kn.attn_fwd(q, flat[:, :d], flat[:, d:], B, H, 1, Lk, kpm=kpm, causal=False, head_dim=d // H,
+                       kv_batch_stride=t_max * 2 * d)
+    return o
+
+
 # ------------------------------------------------------------------------------------------------
 class VocabCE(torch.autograd.Function):
     """K4b: mean token cross-entropy of (h W^T + b) against targets without materialising [rows, V].

@@ -1,0 +1,48 @@
+"""cfg5: autoregressive generation with the KV cache, batch 128, S = 512 source tokens, 512 new tokens, greedy.
+    python tools/decode_bench.py [--batch 128] [--new 512] [--recompute]"""
+import argparse
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from sct_gan_b200 import SmartContractTransformer  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--src", type=int, default=512)
+    ap.add_argument("--new", type=int, default=512)
+    ap.add_argument("--recompute", action="store_true")
+    a = ap.parse_args()
+    torch.manual_seed(0)
+    m = SmartContractTransformer(use_gan=True)
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if p.dim() == 1:
+                noise = torch.randn(p.shape, generator=g)
+                p.copy_(1.0 + 0.1 * noise if n.endswith("weight") else 0.02 * noise)
+    m = m.cuda().eval()
+    B, S = a.batch, a.src
+    ids = torch.randint(3, m.vocab_size, (B, S), device="cuda")
+    ast = torch.randint(3, m.vocab_size, (B, 128), device="cuda")
+    am = torch.ones(B, S, dtype=torch.long, device="cuda")
+    pm = torch.ones(B, 128, dtype=torch.long, device="cuda")
+    kw = dict(input_ids=ids, attention_mask=am, ast_input_ids=ast, ast_attention_mask=pm, target_ids=None,
+              greedy=True, compute_vuln_heads=False, use_kv_cache=not a.recompute)
+    m(**kw, max_new_tokens=8)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = m(**kw, max_new_tokens=a.new)["generated_sequence"]
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print(f"B={B} S={S} new={out.shape[1] - 1} {'recompute' if a.recompute else 'kv-cache'}: {dt:.2f} s, "
+          f"{B * (out.shape[1] - 1) / dt:.0f} new tokens/s, {dt / (out.shape[1] - 1) * 1e3:.2f} ms/step")
+
+
+if __name__ == "__main__":
+    main()
