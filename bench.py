@@ -172,8 +172,10 @@ def run_reference_arm(args):
 
 
 def workload_name():
-    return (f"cfg3 per-GPU shard: full adversarial train step (generator+discriminator losses, backward, clips, AdamW), "
-            f"B={CFG['B']}/GPU, S=P=T={CFG['S']}, default SmartContractTransformer (262.6M params, dropout 0.3, use_gan)")
+    tag = "cfg3 per-GPU shard" if (CFG["B"], CFG["S"], CFG["P"]) == (32, 1024, 1024) else "custom shape"
+    return (f"{tag}: full adversarial train step (generator+discriminator losses, backward, clips, AdamW), "
+            f"B={CFG['B']}/GPU, S=T={CFG['S']}, P={CFG['P']}, default SmartContractTransformer (262.6M params, dropout 0.3, "
+            f"use_gan)")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -185,6 +187,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--batch", type=int, default=CFG["B"])
     ap.add_argument("--seq", type=int, default=CFG["S"])
+    ap.add_argument("--path", type=int, default=None, help="execution-path sequence length (default: --seq)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vuln-heads", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of replaying the captured step")
@@ -192,7 +195,7 @@ def main():
                     help="warm up, then run ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     ap.add_argument("--torch-profile", default=None, help="write a torch.profiler table of one step to this file and exit")
     args = ap.parse_args()
-    CFG["B"], CFG["S"], CFG["P"] = args.batch, args.seq, args.seq
+    CFG["B"], CFG["S"], CFG["P"] = args.batch, args.seq, (args.path or args.seq)
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -208,6 +211,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("SCT_NCCL_DEBUG", "WARN")  # keep NCCL's banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     assert _lib.load().sct_device_check() == 0, _lib.last_error()
     W = max(3, args.warmup)

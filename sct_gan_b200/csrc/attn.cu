@@ -121,18 +121,20 @@ __device__ __forceinline__ int kv_extent(const AttnParams& p, int b, int* smem_s
   return *smem_slot;
 }
 
-// K-major descriptor of a swizzle-64 operand tile ([rows x 96], 3 blocks), k16 step `k` (0..5).
-__device__ __forceinline__ uint64_t desc_k64(uint32_t tile, int k) {
-  return umma_smem_desc(tile + (k >> 1) * BLK + (k & 1) * 32, 16, 512, UMMA_SW64);
+// Descriptor low words (see common.cuh: the high word is a compile-time constant, the single issuing thread only
+// adds immediates).  kHi64 / kHi128: 8-row groups 512 B / 1024 B apart, swizzle 64 / 128.
+constexpr uint32_t kHi64 = umma_desc_hi(512, UMMA_SW64);
+constexpr uint32_t kHi128 = umma_desc_hi(1024, UMMA_SW128);
+// K-major swizzle-64 operand tile ([rows x 96], 3 blocks), k16 step k (0..5)
+__device__ __forceinline__ uint32_t lo_k64(uint32_t tile, int k) {
+  return umma_desc_lo(tile + (k >> 1) * BLK + (k & 1) * 32, 16);
 }
-// MN-major descriptor of the same tile (rows = contraction index), k16 step `k` (0..7): N = 96 spans the
-// three column blocks (LBO = BLK), 8-row groups are 512 B apart (SBO), 16 rows per step = 1024 B.
-__device__ __forceinline__ uint64_t desc_mn64(uint32_t tile, int k) {
-  return umma_smem_desc(tile + k * 1024, BLK, 512, UMMA_SW64);
-}
-// K-major descriptor of a [128 x 128] bf16 swizzle-128 tile (P / dS), k16 step `k` (0..7).
-__device__ __forceinline__ uint64_t desc_k128(uint32_t tile, int k) {
-  return umma_smem_desc(tile + (k >> 2) * (TILE * 128) + (k & 3) * 32, 16, 1024, UMMA_SW128);
+// MN-major view of the same tile (rows = contraction index), k16 step k (0..7): N = 96 spans the three column
+// blocks (LBO = BLK), 8-row groups are 512 B apart (SBO), 16 rows per step = 1024 B.
+__device__ __forceinline__ uint32_t lo_mn64(uint32_t tile, int k) { return umma_desc_lo(tile + k * 1024, BLK); }
+// K-major [128 x 128] bf16 swizzle-128 tile (P / dS), k16 step k (0..7)
+__device__ __forceinline__ uint32_t lo_k128(uint32_t tile, int k) {
+  return umma_desc_lo(tile + (k >> 2) * (TILE * 128) + (k & 3) * 32, 16);
 }
 // MN-major descriptor of the same [128(k) x 128(mn)] tile (used for dQ-style products if ever needed).
 
@@ -221,7 +223,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(bar_k, 0);
     tc_fence_after();
 #pragma unroll
-    for (int k = 0; k < 6; ++k) tc_mma_bf16(tS, desc_k64(sQ, k), desc_k64(sK, k), idesc_s, k > 0);
+    for (int k = 0; k < 6; ++k) tc_mma_bf16_lh(tS, lo_k64(sQ, k), kHi64, lo_k64(sK, k), kHi64, idesc_s, k > 0);
     tc_commit(bar_mma);
   }
 
@@ -321,12 +323,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < 8; ++k)
-        tc_mma_bf16(tO, desc_k128(sP, k), desc_mn64(sV, k), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        tc_mma_bf16_lh(tO, lo_k128(sP, k), kHi128, lo_mn64(sV, k), kHi64, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
       if (j + 1 < nkv) {
         mbar_wait(bar_k, (j + 1) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 6; ++k) tc_mma_bf16(tS, desc_k64(sQ, k), desc_k64(sK, k), idesc_s, k > 0);
+        for (int k = 0; k < 6; ++k) tc_mma_bf16_lh(tS, lo_k64(sQ, k), kHi64, lo_k64(sK, k), kHi64, idesc_s, k > 0);
       }
       tc_commit(bar_mma);
     }
@@ -421,10 +423,8 @@ attn_bwd_dvec_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* _
 constexpr int HALF_BYTES = TILE * 128;   // one [128 x 64] bf16 swizzle-128 block (P^T / dS halves)
 constexpr int BWD3_THREADS = 320;  // 8 arithmetic warps + MMA warp + TMA warp
 
-// K-major descriptor of a [128 x 64] bf16 swizzle-128 block, k16 step k (0..3)
-__device__ __forceinline__ uint64_t desc_k128h(uint32_t tile, int k) {
-  return umma_smem_desc(tile + k * 32, 16, 1024, UMMA_SW128);
-}
+// K-major [128 x 64] bf16 swizzle-128 block, k16 step k (0..3)
+__device__ __forceinline__ uint32_t lo_k128h(uint32_t tile, int k) { return umma_desc_lo(tile + k * 32, 16); }
 
 // ---- dQ: one CTA per (q-tile, head, batch); key tiles stream through, each split in two 64-key halves ----
 //   S_h = Q K_h^T, dP_h = dO V_h^T (TMEM, rows = q) -> dS_h (bf16, smem) -> dQ += dS_h K_h
@@ -512,9 +512,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       auto issue_s = [&](int hh, int st) {  // S_h and dP_h of the key tile staged in `st`
         const uint32_t kh = sK + st * QKV_BYTES + hh * 4096, vh = sV + st * QKV_BYTES + hh * 4096;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) tc_mma_bf16(tmem + 64 * hh, desc_k64(sQ, k), desc_k64(kh, k), idesc_s, k > 0);
+        for (int k = 0; k < 6; ++k) tc_mma_bf16_lh(tmem + 64 * hh, lo_k64(sQ, k), kHi64, lo_k64(kh, k), kHi64, idesc_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) tc_mma_bf16(tmem + 128 + 64 * hh, desc_k64(sdO, k), desc_k64(vh, k), idesc_s, k > 0);
+        for (int k = 0; k < 6; ++k) tc_mma_bf16_lh(tmem + 128 + 64 * hh, lo_k64(sdO, k), kHi64, lo_k64(vh, k), kHi64, idesc_s, k > 0);
         tc_commit(bar_sf + 8 * hh);
       };
       mbar_wait(bar_q, 0);
@@ -535,7 +535,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const uint32_t kh = sK + st * QKV_BYTES + hh * 4096;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            tc_mma_bf16(tmem + 256, desc_k128h(sDS + hh * HALF_BYTES, k), desc_mn64(kh, k), idesc_g,
+            tc_mma_bf16_lh(tmem + 256, lo_k128h(sDS + hh * HALF_BYTES, k), kHi128, lo_mn64(kh, k), kHi64, idesc_g,
                         (j > 0 || hh > 0 || k > 0) ? 1u : 0u);
           tc_commit(bar_dsd + 8 * hh);
           if (j + 1 < nkv) issue_s(hh, st ^ 1);
@@ -711,9 +711,9 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       auto issue_s = [&](int hh, int st) {
         const uint32_t qh = sQ + st * QKV_BYTES + hh * 4096, doh = sdO + st * QKV_BYTES + hh * 4096;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) tc_mma_bf16(tmem + 64 * hh, desc_k64(sK, k), desc_k64(qh, k), idesc_s, k > 0);
+        for (int k = 0; k < 6; ++k) tc_mma_bf16_lh(tmem + 64 * hh, lo_k64(sK, k), kHi64, lo_k64(qh, k), kHi64, idesc_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) tc_mma_bf16(tmem + 128 + 64 * hh, desc_k64(sV, k), desc_k64(doh, k), idesc_s, k > 0);
+        for (int k = 0; k < 6; ++k) tc_mma_bf16_lh(tmem + 128 + 64 * hh, lo_k64(sV, k), kHi64, lo_k64(doh, k), kHi64, idesc_s, k > 0);
         tc_commit(bar_sf + 8 * hh);
       };
       mbar_wait(bar_kv, 0);
@@ -735,10 +735,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const uint32_t acc = (it > 0 || hh > 0) ? 1u : 0u;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            tc_mma_bf16(tmem + 256, desc_k128h(sPT + hh * HALF_BYTES, k), desc_mn64(doh, k), idesc_g, (acc || k > 0) ? 1u : 0u);
+            tc_mma_bf16_lh(tmem + 256, lo_k128h(sPT + hh * HALF_BYTES, k), kHi128, lo_mn64(doh, k), kHi64, idesc_g, (acc || k > 0) ? 1u : 0u);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            tc_mma_bf16(tmem + 352, desc_k128h(sDST + hh * HALF_BYTES, k), desc_mn64(qh, k), idesc_g, (acc || k > 0) ? 1u : 0u);
+            tc_mma_bf16_lh(tmem + 352, lo_k128h(sDST + hh * HALF_BYTES, k), kHi128, lo_mn64(qh, k), kHi64, idesc_g, (acc || k > 0) ? 1u : 0u);
           tc_commit(bar_gd + 8 * hh);
           if (it + 1 < n_it) issue_s(hh, st ^ 1);
         }

@@ -162,6 +162,16 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint32_t bar, 
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// Multicast load: the box lands at the same CTA-relative smem offset in every CTA of `cta_mask`, and each
+// destination CTA's mbarrier (same offset) receives the complete_tx for the bytes it got.
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], "
+      "[%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
@@ -181,6 +191,9 @@ __device__ __forceinline__ void tma_commit_group() {
 }
 __device__ __forceinline__ void tma_wait_group_read0() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_wait_group_read1() {
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 }
 __device__ __forceinline__ void tma_wait_group0() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -202,6 +215,22 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
+}
+// Same, arriving on the barrier at this smem offset in every CTA of `cta_mask` (cluster-wide stage release).
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate.
 __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
@@ -258,6 +287,28 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= 1ull << 46;
   d |= layout << 61;
   return d;
+}
+// The single MMA-issuing thread is on the critical path of every pipeline, so descriptors are not rebuilt with
+// 64-bit shifts for every instruction (~90 cycles each, measured): the high word (stride / version / swizzle) is a
+// compile-time constant and the low word is a 32-bit base + immediate offset (1 IADD per MMA).
+//   lo = (addr >> 4) & 0x3FFF | (lbo >> 4) << 16      hi = (sbo >> 4) & 0x3FFF | 1 << 14 | layout << 29
+__host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes, uint64_t layout) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (static_cast<uint32_t>(layout) << 29);
+}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+// advance a descriptor low word by `bytes` (stays inside the 14-bit address field: smem is < 256 KB)
+__device__ __forceinline__ uint32_t umma_lo_add(uint32_t lo, uint32_t bytes) { return lo + (bytes >> 4); }
+__device__ __forceinline__ void tc_mma_bf16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                               uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool a_mn_major,

@@ -20,6 +20,14 @@
 // Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
 // warps 2-5 = epilogue (TMEM -> registers -> swizzled smem -> TMA store / TMA reduce-add).
 // Two TMEM accumulator stages let the epilogue of tile i overlap the mainloop of tile i+1.
+//
+// CLUSTER = 2: two CTAs of a thread-block cluster work on vertically adjacent output tiles (same N block,
+// M blocks 2i and 2i+1).  Each loads its own A tile and HALF of the shared B tile, multicast by TMA into
+// both CTAs' shared memory, which halves the L2 -> SM traffic of the B operand (a 128x256 tile is otherwise
+// L2-bound near 12 TB/s).  A pipeline stage is released cluster-wide: each CTA's tcgen05.commit arrives on
+// the `empty` barrier of both CTAs (count 2), so nobody multicasts into a buffer a peer is still reading.
+#include <stdlib.h>
+
 #include "../../include/sct_b200.h"
 #include "common.cuh"
 
@@ -45,7 +53,10 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int C_BYTES = BM * BN * (OUT_F32 ? 4 : 2);
+  // Epilogue staging: two [128 rows x 128 B] blocks (64 bf16 / 32 fp32 columns each), ping-ponged chunk by chunk.
+  // A full-tile staging buffer (64 KB at BN = 256) would leave only 3 pipeline stages, and the mainloop is
+  // bound by the bytes it can keep in flight (measured: the MMA thread waited on `full` 44 % of the time).
+  static constexpr int C_BYTES = 2 * BM * 128;
   static constexpr int AUX_BYTES = 1024;  // barriers + tmem ptr + bias tile
   static constexpr int STAGES_RAW = (kSmemLimit - 1024 - C_BYTES - AUX_BYTES - BN * 4) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -74,7 +85,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t) {
   return c;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32, int CLUSTER>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
@@ -98,7 +109,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // work items: with CLUSTER = 2 an item is a PAIR of vertically adjacent tiles (p.m_tiles then counts pairs)
   const int total_tiles = p.m_tiles * p.n_tiles * p.k_splits;
+  const int crank = CLUSTER > 1 ? (int)cluster_ctarank() : 0;
+  const int item0 = CLUSTER > 1 ? (int)(blockIdx.x / CLUSTER) : (int)blockIdx.x;
+  const int item_stride = CLUSTER > 1 ? (int)(gridDim.x / CLUSTER) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -106,7 +121,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmD);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, CLUSTER);  // one arrival per CTA of the cluster
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
@@ -117,6 +132,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 1) tmem_alloc(tmem_ptr_addr, C::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();  // peers' barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
@@ -125,8 +141,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(p, t);
+      for (int t = item0; t < total_tiles; t += item_stride) {
+        TileCoord tc = decode_tile(p, t);
+        if (CLUSTER > 1) tc.m_blk = tc.m_blk * CLUSTER + crank;
         for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           const uint32_t full = bar_full + 8 * s;
@@ -140,12 +157,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int c = 0; c < BM / 64; ++c)
               tma_load_2d(&tmA, full, sA + c * (BK * 128), tc.m_blk * BM + c * 64, kb * BK);
           }
-          if (!B_MN) {
-            tma_load_2d(&tmB, full, sB, kb * BK, tc.n_blk * BN);
-          } else {
+          if (CLUSTER == 1) {
+            if (!B_MN) {
+              tma_load_2d(&tmB, full, sB, kb * BK, tc.n_blk * BN);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              tma_load_2d(&tmB, full, sB + c * (BK * 128), tc.n_blk * BN + c * 64, kb * BK);
+              for (int c = 0; c < BN / 64; ++c)
+                tma_load_2d(&tmB, full, sB + c * (BK * 128), tc.n_blk * BN + c * 64, kb * BK);
+            }
+          } else {
+            // this CTA fetches its half of the B tile and multicasts it to both CTAs of the cluster
+            constexpr uint16_t kMask = (1u << CLUSTER) - 1;
+            if (!B_MN) {
+              constexpr int HR = BN / CLUSTER;  // rows of the [BN x 64] K-major tile per CTA
+              tma_load_2d_mc(&tmB, full, sB + crank * (HR * 128), kb * BK, tc.n_blk * BN + crank * HR, kMask);
+            } else {
+              constexpr int HC = BN / 64 / CLUSTER;  // 64-wide MN blocks per CTA
+#pragma unroll
+              for (int c = 0; c < HC; ++c) {
+                const int cb = crank * HC + c;
+                tma_load_2d_mc(&tmB, full, sB + cb * (BK * 128), tc.n_blk * BN + cb * 64, kb * BK, kMask);
+              }
+            }
           }
           if (++s == STAGES) {
             s = 0;
@@ -162,11 +195,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // MN-major: 8-k-row groups are 1024 B apart (SBO); 64-wide MN blocks are BK*128 B apart (LBO).
       constexpr uint32_t A_LBO = A_MN ? BK * 128 : 16, B_LBO = B_MN ? BK * 128 : 16;
       constexpr uint32_t A_KSTEP = A_MN ? 2048 : 32, B_KSTEP = B_MN ? 2048 : 32;
+      constexpr uint32_t kDescHi = umma_desc_hi(1024, UMMA_SW128);
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = item0; t < total_tiles; t += item_stride) {
         const TileCoord tc = decode_tile(p, t);
         mbar_wait(bar_tempty + 8 * as, aph ^ 1);
         tc_fence_after();
@@ -176,13 +210,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tc_fence_after();
           const uint32_t sA = smem_base + s * C::STAGE_BYTES;
           const uint32_t sB = sA + C::A_BYTES;
+          const uint32_t a_lo = umma_desc_lo(sA, A_LBO), b_lo = umma_desc_lo(sB, B_LBO);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ad = umma_smem_desc(sA + k * A_KSTEP, A_LBO, 1024, UMMA_SW128);
-            const uint64_t bd = umma_smem_desc(sB + k * B_KSTEP, B_LBO, 1024, UMMA_SW128);
-            tc_mma_bf16(d_tmem, ad, bd, idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
-          }
-          tc_commit(bar_empty + 8 * s);  // frees the smem stage once these MMAs retire
+          for (int k = 0; k < BK / 16; ++k)
+            tc_mma_bf16_lh(d_tmem, umma_lo_add(a_lo, k * A_KSTEP), kDescHi, umma_lo_add(b_lo, k * B_KSTEP), kDescHi,
+                           idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
+          // frees the smem stage once these MMAs retire — in every CTA of the cluster (B halves are shared)
+          if (CLUSTER == 1) tc_commit(bar_empty + 8 * s);
+          else tc_commit_mc(bar_empty + 8 * s, (uint16_t)((1u << CLUSTER) - 1));
           if (++s == STAGES) {
             s = 0;
             ph ^= 1;
@@ -203,68 +238,78 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const bool store_thread = (etid == 0);
     int as = 0;
     uint32_t aph = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const TileCoord tc = decode_tile(p, t);
+    for (int t = item0; t < total_tiles; t += item_stride) {
+      TileCoord tc = decode_tile(p, t);
+      if (CLUSTER > 1) tc.m_blk = tc.m_blk * CLUSTER + crank;
       const int n0 = tc.n_blk * BN;
       mbar_wait(bar_tfull + 8 * as, aph);
       tc_fence_after();
-      if (store_thread) tma_wait_group_read0();  // previous tile's staging has been read out
       for (int i = etid; i < BN; i += 128) {
         const int n = n0 + i;
         bias_s[i] = (p.bias != nullptr && n < p.N && tc.kb0 == 0) ? p.bias[n] : 0.f;
       }
       named_bar_sync(1, 128);
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+      constexpr int CW = OUT_F32 ? 32 : 64;    // output columns per 128-byte staging block
+      constexpr int NCHUNK = BN / CW;
 #pragma unroll 1
-      for (int c32 = 0; c32 < BN / 32; ++c32) {
-        uint32_t r[32];
-        tmem_ld32(t_addr + c32 * 32, r);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha + bias_s[c32 * 32 + j];
+      for (int cb = 0; cb < NCHUNK; ++cb) {
+        const uint32_t blk = sC + (cb & 1) * (BM * 128) + row * 128;
+        // the TMA store that last read this staging block (two chunks ago) must have finished reading it
+        if (store_thread) tma_wait_group_read1();
+        named_bar_sync(1, 128);
         if (OUT_F32) {
-          const uint32_t blk = sC + c32 * (BM * 128) + row * 128;
+          uint32_t r[32];
+          tmem_ld32(t_addr + cb * 32, r);
+          tmem_ld_wait();
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const uint32_t dst = blk + (((q ^ (row & 7)) & 7) << 4);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(v[4 * q]),
-                         "f"(v[4 * q + 1]), "f"(v[4 * q + 2]), "f"(v[4 * q + 3])
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
+                         "f"(__uint_as_float(r[4 * q]) * p.alpha + bias_s[cb * 32 + 4 * q]),
+                         "f"(__uint_as_float(r[4 * q + 1]) * p.alpha + bias_s[cb * 32 + 4 * q + 1]),
+                         "f"(__uint_as_float(r[4 * q + 2]) * p.alpha + bias_s[cb * 32 + 4 * q + 2]),
+                         "f"(__uint_as_float(r[4 * q + 3]) * p.alpha + bias_s[cb * 32 + 4 * q + 3])
                          : "memory");
           }
         } else {
-          const uint32_t blk = sC + (c32 >> 1) * (BM * 128) + row * 128;
+          uint32_t r0[32], r1[32];
+          tmem_ld32(t_addr + cb * 64, r0);
+          tmem_ld32(t_addr + cb * 64 + 32, r1);
+          tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int chunk = (c32 & 1) * 4 + q;
-            const uint32_t dst = blk + (((chunk ^ (row & 7)) & 7) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
-                         "r"(pack_bf16(v[8 * q], v[8 * q + 1])),
-                         "r"(pack_bf16(v[8 * q + 2], v[8 * q + 3])),
-                         "r"(pack_bf16(v[8 * q + 4], v[8 * q + 5])),
-                         "r"(pack_bf16(v[8 * q + 6], v[8 * q + 7]))
-                         : "memory");
+          for (int hf = 0; hf < 2; ++hf) {
+            const uint32_t(&r)[32] = hf == 0 ? r0 : r1;
+            const float* bs = bias_s + cb * 64 + hf * 32;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int chunk = hf * 4 + q;
+              const uint32_t dst = blk + (((chunk ^ (row & 7)) & 7) << 4);
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * q + e]) * p.alpha + bs[8 * q + e];
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack_bf16(v[0], v[1])),
+                           "r"(pack_bf16(v[2], v[3])), "r"(pack_bf16(v[4], v[5])), "r"(pack_bf16(v[6], v[7]))
+                           : "memory");
+            }
           }
         }
-      }
-      // TMEM stage drained: hand it back to the MMA warp.
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
-      fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (store_thread) {
-        constexpr int CW = OUT_F32 ? 32 : 64;  // columns per 128-byte staging block
-#pragma unroll 1
-        for (int cb = 0; cb < BN / CW; ++cb) {
+        if (cb == NCHUNK - 1) {  // TMEM stage drained: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (store_thread) {
           if (n0 + cb * CW < p.N) {
             if (OUT_F32)
-              tma_reduce_add_2d(&tmD, sC + cb * (BM * 128), n0 + cb * CW, tc.m_blk * BM);
+              tma_reduce_add_2d(&tmD, sC + (cb & 1) * (BM * 128), n0 + cb * CW, tc.m_blk * BM);
             else
-              tma_store_2d(&tmD, sC + cb * (BM * 128), n0 + cb * CW, tc.m_blk * BM);
+              tma_store_2d(&tmD, sC + (cb & 1) * (BM * 128), n0 + cb * CW, tc.m_blk * BM);
           }
+          tma_commit_group();  // (an empty group when the chunk lies past N keeps the wait_group arithmetic uniform)
         }
-        tma_commit_group();
       }
       if (++as == 2) {
         as = 0;
@@ -276,18 +321,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();  // no CTA leaves while a peer may still signal / multicast into it
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
 // -----------------------------------------------------------------------------------------------
 // host launcher
 // -----------------------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
-int launch(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd,
-           const float* bias, float alpha, int64_t M, int64_t N, int64_t K, int k_splits_req,
-           cudaStream_t stream) {
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32, int CLUSTER>
+int launch_impl(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd,
+                const float* bias, float alpha, int64_t M, int64_t N, int64_t K, int k_splits_req,
+                cudaStream_t stream) {
   using C = Cfg<BN, OUT_F32>;
-  auto kern = gemm_kernel<BN, A_MN, B_MN, OUT_F32>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, OUT_F32, CLUSTER>;
   static bool attr_set = false;  // benign race: idempotent call
   if (!attr_set) {
     SCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -301,7 +347,7 @@ int launch(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int6
     rc = make_tmap_2d(&tmA, A, 2, false, M, K, lda * 2, 64, BK, SWZ_128);
   if (rc) return rc;
   if (!B_MN)
-    rc = make_tmap_2d(&tmB, B, 2, false, K, N, ldb * 2, BK, BN, SWZ_128);
+    rc = make_tmap_2d(&tmB, B, 2, false, K, N, ldb * 2, BK, BN / CLUSTER, SWZ_128);  // per-CTA share of the tile
   else
     rc = make_tmap_2d(&tmB, B, 2, false, N, K, ldb * 2, 64, BK, SWZ_128);
   if (rc) return rc;
@@ -315,14 +361,34 @@ int launch(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int6
   p.M = (int)M;
   p.N = (int)N;
   p.K = (int)K;
-  p.m_tiles = (int)((M + BM - 1) / BM);
+  p.m_tiles = (int)((M + BM * CLUSTER - 1) / (BM * CLUSTER));  // CLUSTER = 2: pairs of vertically adjacent tiles
   p.n_tiles = (int)((N + BN - 1) / BN);
   p.kb_total = (int)((K + BK - 1) / BK);
   const int sms = num_sms();
   int ks = 1;
   if (OUT_F32) {
-    // split-K so that a small [N_out x K_in] weight-gradient still fills the machine
-    ks = k_splits_req > 0 ? k_splits_req : (2 * sms) / (p.m_tiles * p.n_tiles);
+    // split-K so that a small [N_out x K_in] weight gradient still fills the machine: the smallest split count
+    // whose work items fill >= 92 % of the last wave of 148 CTAs (108 tiles x 2 splits = 1.46 waves ran at 779
+    // TFLOP/s, x 4 = 2.9 waves at 917), keeping >= 8 k-blocks per item; every extra split adds reduce-add traffic.
+    const int tiles = p.m_tiles * p.n_tiles;
+    if (k_splits_req > 0) {
+      ks = k_splits_req;
+    } else {
+      int best = 1;
+      double best_eff = 0.0;
+      const int ks_max = p.kb_total / 8 > 0 ? p.kb_total / 8 : 1;
+      for (int c = 1; c <= 32 && c <= ks_max; ++c) {
+        const int total = tiles * c;
+        const int waves = (total + sms - 1) / sms;
+        const double eff = (double)total / ((double)waves * sms);
+        if (eff > best_eff + 1e-9) {
+          best_eff = eff;
+          best = c;
+        }
+        if (eff >= 0.92) break;
+      }
+      ks = best;
+    }
     if (ks < 1) ks = 1;
     if (ks > p.kb_total) ks = p.kb_total;
   }
@@ -332,10 +398,43 @@ int launch(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int6
   p.bias = bias;
   p.alpha = alpha;
   const int total = p.m_tiles * p.n_tiles * p.k_splits;
-  const int grid = total < sms ? total : sms;
-  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, tmD, p);
+  if (CLUSTER == 1) {
+    const int grid = total < sms ? total : sms;
+    kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, tmD, p);
+  } else {
+    const int clusters = total < sms / CLUSTER ? total : sms / CLUSTER;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * CLUSTER));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SCT_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, p));
+  }
   SCT_LAUNCH_CHECK();
   return 0;
+}
+
+// Measured on B200 (tools/gemm_bench.py, M = 32768): the multicast pairs halve the B-operand L2 traffic but do
+// not change throughput (1071 vs 1056 TFLOP/s at N = 2304, 843 vs 901 at N = K = 768): the 128x256 tile is not
+// L2-bound.  Off by default; SCT_GEMM_CLUSTER=1 enables it (kept: correct, tested, the base for cta_group::2).
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
+int launch(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd, const float* bias,
+           float alpha, int64_t M, int64_t N, int64_t K, int k_splits_req, cudaStream_t stream) {
+  static int use_cluster = -1;
+  if (use_cluster < 0) {
+    const char* e = getenv("SCT_GEMM_CLUSTER");
+    use_cluster = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  if (use_cluster && M >= 4 * BM)
+    return launch_impl<BN, A_MN, B_MN, OUT_F32, 2>(A, lda, B, ldb, D, ldd, bias, alpha, M, N, K, k_splits_req, stream);
+  return launch_impl<BN, A_MN, B_MN, OUT_F32, 1>(A, lda, B, ldb, D, ldd, bias, alpha, M, N, K, k_splits_req, stream);
 }
 
 int check_common(const void* A, const void* B, const void* D, int64_t M, int64_t N, int64_t K) {

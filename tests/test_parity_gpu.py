@@ -267,3 +267,33 @@ def test_kv_cache_decode_matches_recompute_long(cuda_dev):
     agree = (a == r).float().mean().item()
     first_diff = [int((a[i] != r[i]).nonzero()[0]) if (a[i] != r[i]).any() else 151 for i in range(3)]
     assert agree > 0.9 and min(first_diff) > 20, (agree, first_diff)
+
+
+def test_long_context_4096_against_oracle(cuda_dev):
+    """cfg4 shape (contract/target seq 4096, path seq 1024, max_length 4096) on a 1+1-layer model: 32 key tiles
+    per attention row, causal + ragged key-padding, the chunked vocab cross-entropy over 4096 rows."""
+    from oracle import sct_oracle as O
+    from sct_gan_b200 import SmartContractTransformer
+
+    cfg = {**O.DEFAULT_CFG, **dict(num_encoder_layers=1, num_decoder_layers=1, dim_feedforward=512,
+                                   max_length=4096, vocab_size=1000, dropout=0.0)}
+    m = SmartContractTransformer(**cfg)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = O.synth_state_dict(shapes, 4)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    batch = O.make_batch(1, 4096, 1024, cfg["vocab_size"], seed=4)
+    with torch.no_grad():
+        ref = O.forward_train(sd, cfg, batch, torch.float32, with_line_heads=False)
+    lse = torch.logsumexp(ref["logits"], dim=-1)
+    ce_ref = (lse - ref["logits"].gather(1, ref["target_ids"][:, None]).squeeze(1)).mean()
+    cb = {k: v.cuda() for k, v in batch.items()}
+    out = m(input_ids=cb["input_ids"], attention_mask=cb["attention_mask"], ast_input_ids=cb["ast_input_ids"],
+            ast_attention_mask=cb["ast_attention_mask"], target_ids=cb["target_ids"], fused_loss=True,
+            return_logits=True, compute_vuln_heads=False)
+    assert torch.equal(out["target_ids"].cpu(), ref["target_ids"])
+    assert rel_l2(out["logits"], ref["logits"]) < 2e-2
+    assert abs(out["gen_ce_loss"].item() - ce_ref.item()) < 1e-2 * ce_ref.item()
+    assert rel_l2(out["encoder_output"], ref["encoder_output"]) < 2e-2
+    out["gen_ce_loss"].backward()
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
