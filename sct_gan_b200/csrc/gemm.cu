@@ -485,6 +485,13 @@ int32_t sct_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int64_t ldb,
                          float alpha, int64_t M, int64_t N, int64_t K, int32_t k_splits, void* stream) {
   if (int rc = sct::check_common(A, B, D, M, N, K)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static int tn_bn = -1;  // SCT_GEMM_TN_BN=128 forces the narrow tile (A/B timing)
+  if (tn_bn < 0) {
+    const char* e = getenv("SCT_GEMM_TN_BN");
+    tn_bn = e ? atoi(e) : 256;
+  }
+  if (tn_bn == 256 && N >= 512)
+    return sct::launch<256, true, true, true>(A, lda, B, ldb, D, ldd, nullptr, alpha, M, N, K, k_splits, st);
   return sct::launch<128, true, true, true>(A, lda, B, ldb, D, ldd, nullptr, alpha, M, N, K, k_splits, st);
 }
 
