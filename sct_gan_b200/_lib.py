@@ -48,8 +48,9 @@ SIGNATURES = {
     "sct_gan_loss_fwd": [_p, _i64, _p, _p, _p],
     "sct_gan_loss_bwd": [_p, _i64, _p, _p, _p, _p, _p],
     "sct_set_dropout_epoch_ptr": [_p],
+    "sct_clip_adamw_step": [_p, _i32, _p, _i32, _p, _p, _p, _f, _f, _f, _f, _f, _f, _p],
 }
-NOARG = {"sct_version": _i32, "sct_device_check": _i32, "sct_debug_timeouts": _i32, "sct_last_error": C.c_char_p}
+NOARG = {"sct_opt_chunk_elems": _i32, "sct_version": _i32, "sct_device_check": _i32, "sct_debug_timeouts": _i32, "sct_last_error": C.c_char_p}
 
 _lib = None
 
@@ -85,7 +86,7 @@ def last_error() -> str:
 
 
 # kernels launched per C-ABI call (sct_attn_bwd = D-vector + dK/dV + dQ, sct_seq_mean_fwd = memset + reduce, ...)
-KERNELS_PER_CALL = {"sct_attn_bwd": 3, "sct_small_linear_bwd": 2, "sct_seq_mean_fwd": 2,
+KERNELS_PER_CALL = {"sct_clip_adamw_step": 4, "sct_attn_bwd": 3, "sct_small_linear_bwd": 2, "sct_seq_mean_fwd": 2,
                     "sct_set_dropout_epoch_ptr": 0}
 
 

@@ -334,3 +334,12 @@ def gan_loss_bwd(z, c, g_d, g_adv):
     dz = torch.empty_like(z)
     _lib.call("sct_gan_loss_bwd", _sptr(z), z.numel(), _sptr(c), _sptr(g_d), _sptr(g_adv), _sptr(dz), _stream())
     return dz
+
+
+# ------------------------------------------------------------------------------------- optimiser tail
+def clip_adamw_step(table, n_tensors, chunks, n_chunks, loss, sqnorm3, out2, max_norm, disc_mult, vuln_mult,
+                    beta1, beta2, eps):
+    """table: uint8 device tensor of n_tensors sct_opt_tensor records; chunks: int32 [n_chunks, 2]."""
+    _lib.call("sct_clip_adamw_step", _ptr(table), n_tensors, _ptr(chunks, 8), n_chunks, _sptr(loss), _sptr(sqnorm3),
+              _sptr(out2), float(max_norm), float(disc_mult), float(vuln_mult), float(beta1), float(beta2),
+              float(eps), _stream())

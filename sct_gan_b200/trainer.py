@@ -124,6 +124,114 @@ def allreduce_mean_grads(params, world, group=None, bucket_bytes=32 << 20):
             off += n
 
 
+class FusedClipAdamW:
+    """The optimiser tail of train.py:1277-1311 as three multi-tensor kernel launches (csrc/optim.cu): squared
+    gradient norms per clip scope, then the three nested clips + skip rule + AdamW in one pass over the fp32 master
+    weights.  It works directly on torch.optim.AdamW's own state tensors (step / exp_avg / exp_avg_sq), so
+    `optimizer.state_dict()` checkpoints stay interchangeable with the reference's."""
+
+    _DT = None
+
+    def __init__(self, optimizer, named_params, use_gan, max_grad_norm):
+        import numpy as np
+
+        from . import _lib
+
+        if FusedClipAdamW._DT is None:
+            FusedClipAdamW._DT = np.dtype([("p", "<u8"), ("g", "<u8"), ("m", "<u8"), ("v", "<u8"), ("step", "<u8"),
+                                           ("numel", "<i8"), ("lr", "<f4"), ("wd", "<f4"), ("seg", "<i4"),
+                                           ("pad", "<i4")])
+        self.np = np
+        self.opt = optimizer
+        self.max_norm = max_grad_norm
+        self.chunk = _lib.load().sct_opt_chunk_elems()
+        self.seg = {}
+        for n, p in named_params:
+            if "disc_" in n and use_gan:
+                self.seg[p] = 1
+            elif ("vulnerability_head" in n or "line_feature_extractor" in n or "line_vuln_attention" in n
+                  or "vuln_type_attention" in n):
+                self.seg[p] = 2
+            else:
+                self.seg[p] = 0
+        self._sig = None
+        self._keep = []  # tables referenced by captured graphs must outlive them
+        self.bufs = None
+        self._eager, self._flip = [], 0
+        self.all_params = [p for g in optimizer.param_groups for p in g["params"]]
+        self.max_chunks = sum((p.numel() + self.chunk - 1) // self.chunk for p in self.all_params)
+        self.n_tensors = self.n_chunks = 0
+
+    def _alloc(self):
+        """Pinned host + device buffers sized for every parameter (filled by _fill; no allocation afterwards)."""
+        dev = self.all_params[0].device
+        tab_h = torch.zeros(len(self.all_params) * 64, dtype=torch.uint8).pin_memory()
+        ck_h = torch.zeros((self.max_chunks, 2), dtype=torch.int32).pin_memory()
+        return (tab_h, ck_h, torch.empty_like(tab_h, device=dev), torch.empty_like(ck_h, device=dev),
+                torch.zeros(8, dtype=torch.float32, device=dev))  # scratch: [0:3] squared norms, [4:6] out2
+
+    def prepare_for_capture(self):
+        """A CUDA graph replays the host->device table copy, so every captured graph gets buffers of its own,
+        allocated before the capture starts and kept alive with it."""
+        for p in self.all_params:  # optimiser state must exist before the capture (allocations are fine, but keep
+            self._state(p)         # them out of the graph's private pool)
+        self.bufs = self._alloc()
+        self._keep.append(self.bufs)
+        self._sig = None
+
+    def _state(self, p):
+        st = self.opt.state[p]
+        if len(st) == 0:  # same lazy initialisation as torch.optim.AdamW (fused): fp32 device step counter
+            st["step"] = torch.zeros((), dtype=torch.float32, device=p.device)
+            st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        return st
+
+    def _fill(self):
+        np = self.np
+        rows, chunks = [], []
+        for group in self.opt.param_groups:
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self._state(p)
+                assert p.grad.is_contiguous()
+                idx = len(rows)
+                rows.append((p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
+                             st["step"].data_ptr(), p.numel(), float(group["lr"]), float(group["weight_decay"]),
+                             self.seg[p], 0))
+                for c in range((p.numel() + self.chunk - 1) // self.chunk):
+                    chunks.append((idx, c))
+        g0 = self.opt.param_groups[0]
+        self.betas, self.eps = g0["betas"], float(g0["eps"])
+        tab_h, ck_h, tab_d, ck_d, _ = self.bufs
+        self.n_tensors, self.n_chunks = len(rows), len(chunks)
+        tab_h.numpy()[: self.n_tensors * 64] = np.array(rows, dtype=self._DT).view(np.uint8)
+        ck_h.numpy()[: self.n_chunks] = np.array(chunks, dtype=np.int32)
+        tab_d.copy_(tab_h, non_blocking=True)
+        ck_d.copy_(ck_h, non_blocking=True)
+
+    def step(self, loss):
+        """Returns (gradient norm after the clips, stepped flag) as device scalars."""
+        from . import kernels as kn
+
+        capturing = torch.cuda.is_current_stream_capturing()
+        sig = tuple((p.grad.data_ptr(), g["lr"]) for g in self.opt.param_groups for p in g["params"]
+                    if p.grad is not None)
+        if sig != self._sig or self.bufs is None:
+            if not capturing:  # eager: gradients are fresh tensors every step -> refill, ping-ponging two buffer sets
+                if len(self._eager) < 2:  # so the previous step's asynchronous table upload is never overwritten
+                    self._eager.append(self._alloc())
+                self._flip ^= 1
+                self.bufs = self._eager[min(self._flip, len(self._eager) - 1)]
+            self._fill()
+            self._sig = sig
+        tab_d, ck_d, scratch = self.bufs[2], self.bufs[3], self.bufs[4]
+        kn.clip_adamw_step(tab_d, self.n_tensors, ck_d, self.n_chunks, loss.detach().float().reshape(1),
+                           scratch[0:3], scratch[4:6], self.max_norm, 0.3, 2.0, self.betas[0], self.betas[1], self.eps)
+        return scratch[4].clone(), scratch[5] > 0.5
+
+
 class SmartContractTrainer:
     """Step-level mirror of the reference trainer (constructor keywords of train.py:481-494 that matter for
     the step).  `train_step(batch)` is the body of the reference's batch loop.
@@ -138,7 +246,8 @@ class SmartContractTrainer:
 
     def __init__(self, model, learning_rate=1e-6, weight_decay=0.1, max_grad_norm=1.0, use_augmentation=False,
                  use_gan=False, line_vuln_weight=2.0, contract_vuln_weight=3.0, warmup_epochs=5,
-                 compute_vuln_heads=True, process_group=None, bucket_mb=32, use_cuda_graph=False):
+                 compute_vuln_heads=True, process_group=None, bucket_mb=32, use_cuda_graph=False,
+                 fused_optimizer=True):
         self.model = model
         self.use_augmentation = use_augmentation
         self.use_gan = use_gan
@@ -175,6 +284,8 @@ class SmartContractTrainer:
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.bucket_bytes = bucket_mb << 20
         self.use_cuda_graph = use_cuda_graph and on_gpu
+        self._fused_tail = FusedClipAdamW(self.optimizer, list(model.named_parameters()), use_gan, max_grad_norm) \
+            if (fused_optimizer and on_gpu) else None
         self._graphs = {}
         self.last = {}
 
@@ -237,7 +348,20 @@ class SmartContractTrainer:
         self.optimizer.zero_grad(set_to_none=True)
         losses["total_loss"].backward()
         self._allreduce_grads()
-        params = [p for p in model.parameters() if p.grad is not None]
+        if self._fused_tail is not None:
+            total_norm, ok = self._fused_tail.step(losses["total_loss"])
+        else:
+            total_norm, ok = self._torch_tail(losses["total_loss"])
+        if self.compute_vuln_heads:  # train.py:1174-1184
+            self.focal.copy_(torch.where(self._pending_has_line, self._focal_has, self._focal_none))
+        losses["grad_norm"] = total_norm
+        losses["stepped"] = ok
+        # detached: nothing returned keeps the autograd graph (and its AccumulateGrad nodes) alive
+        return {k: (v.detach() if torch.is_tensor(v) else v) for k, v in losses.items()}
+
+    def _torch_tail(self, loss):
+        """The same tail with PyTorch's foreach / fused-AdamW kernels (A/B reference for FusedClipAdamW)."""
+        params = [p for p in self.model.parameters() if p.grad is not None]
         torch.nn.utils.clip_grad_norm_(params, self.max_grad_norm, foreach=True)
         if self.use_gan:
             dp = [p for p in self.disc_params if p.grad is not None]
@@ -248,19 +372,14 @@ class SmartContractTrainer:
             torch.nn.utils.clip_grad_norm_(vp, self.max_grad_norm * 2.0, foreach=True)
         norms = torch._foreach_norm([p.grad for p in params])
         total_norm = torch.linalg.vector_norm(torch.stack(norms))
-        ok = torch.isfinite(losses["total_loss"]) & torch.isfinite(total_norm) & (total_norm <= 1000)
+        ok = torch.isfinite(loss) & torch.isfinite(total_norm) & (total_norm <= 1000)
         # skip rule of train.py:1301-1309 without a host decision: the fused AdamW skips when found_inf == 1
         self._found_inf.copy_((~ok).to(self._found_inf.dtype).reshape(()))
         if not self._found_inf.is_cuda and not bool(ok):
             self.optimizer.zero_grad(set_to_none=True)
         else:
             self.optimizer.step()
-        if self.compute_vuln_heads:  # train.py:1174-1184
-            self.focal.copy_(torch.where(self._pending_has_line, self._focal_has, self._focal_none))
-        losses["grad_norm"] = total_norm
-        losses["stepped"] = ok
-        # detached: nothing returned keeps the autograd graph (and its AccumulateGrad nodes) alive
-        return {k: (v.detach() if torch.is_tensor(v) else v) for k, v in losses.items()}
+        return total_norm, ok
 
     def train_step(self, batch, syntax_penalty=0.0, n_lines=None):
         """One optimisation step; returns a dict of DEVICE scalars (`stepped` included) — nothing in here waits
@@ -287,12 +406,16 @@ class SmartContractTrainer:
         if ent == "warm":
             static = {k: v.to(dev, copy=True) for k, v in tens.items()}
             graph = torch.cuda.CUDAGraph()
+            if self._fused_tail is not None:
+                self._fused_tail.prepare_for_capture()
             torch.cuda.synchronize()
             n0 = _lib.Stats.launches
             with torch.cuda.graph(graph):
                 res = self._step_body(static, syntax_penalty, n_lines)
             ent = self._graphs[key] = (graph, static, res, _lib.Stats.launches - n0)
             _lib.Stats.launches = n0
+            if self._fused_tail is not None:
+                self._fused_tail.bufs, self._fused_tail._sig = None, None  # eager steps must not touch the graph's tables
         graph, static, res, n_launch = ent
         for k, v in tens.items():  # pinned host tensors land directly in the graph's input buffers
             if static[k].data_ptr() != v.data_ptr():

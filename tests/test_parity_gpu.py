@@ -297,3 +297,85 @@ def test_long_context_4096_against_oracle(cuda_dev):
     assert rel_l2(out["encoder_output"], ref["encoder_output"]) < 2e-2
     out["gen_ce_loss"].backward()
     assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+
+
+@pytest.mark.parametrize("scale", [1.0, 300.0, float("nan")], ids=["clip", "heavy_clip", "nan_skip"])
+def test_fused_clip_adamw_matches_torch_and_oracle(cuda_dev, scale):
+    """csrc/optim.cu against (a) the PyTorch tail (3 x clip_grad_norm_ + fused AdamW with found_inf) and (b) the
+    oracle's restatement of train.py:1277-1311, on a toy module whose parameter names hit all three clip scopes and
+    all four learning-rate groups."""
+    import copy
+
+    from oracle import sct_oracle as O
+    from sct_gan_b200.trainer import FusedClipAdamW, param_group_of
+
+    class Toy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.embedding = torch.nn.Embedding(50, 30)               # base group, odd numel
+            self.disc_head = torch.nn.Linear(64, 64)                  # 'disc_' scope
+            self.contract_vulnerability_head = torch.nn.Linear(40, 8)  # vuln scope, contract lr group
+            self.line_feature_extractor = torch.nn.Linear(128, 520)   # vuln scope, line lr group, > 1 chunk? no
+            self.big = torch.nn.Parameter(torch.zeros(3, 40000))       # several 32768-element chunks
+            self.dead = torch.nn.Parameter(torch.zeros(7))             # never gets a gradient
+
+    torch.manual_seed(0)
+    base = Toy().cuda()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    with torch.no_grad():
+        for p in base.parameters():
+            p.copy_(torch.randn(p.shape, device="cuda", generator=g))
+    grads = {n: (torch.randn(p.shape, device="cuda", generator=g) * 0.05 * (1.0 if scale != scale else scale))
+             for n, p in base.named_parameters() if n != "dead"}
+    if scale != scale:
+        grads["big"][0, 0] = float("nan")
+
+    def make_opt(m):
+        groups = [[], [], [], []]
+        for n, p in m.named_parameters():
+            groups[param_group_of(n, True)].append(p)
+        pg = [{"params": gr, "lr": 1e-3 * mult} for gr, mult in zip(groups, (1.0, 2.0, 3.0, 0.5)) if gr]
+        return torch.optim.AdamW(pg, weight_decay=0.1, betas=(0.9, 0.98), eps=1e-9, fused=True)
+
+    # (a) PyTorch tail
+    ma = copy.deepcopy(base)
+    oa = make_opt(ma)
+    found = torch.zeros((), device="cuda")
+    oa.found_inf = found
+    mb = copy.deepcopy(base)
+    ob = make_opt(mb)
+    tail = FusedClipAdamW(ob, list(mb.named_parameters()), True, 1.0)
+    params_o = {n: p.detach().cpu().clone() for n, p in base.named_parameters()}
+    state_o = {}
+    loss = torch.tensor(1.0, device="cuda")
+    for it in range(3):
+        for n, p in ma.named_parameters():
+            p.grad = grads[n].clone() if n in grads else None
+        pa = [p for p in ma.parameters() if p.grad is not None]
+        torch.nn.utils.clip_grad_norm_(pa, 1.0, foreach=True)
+        torch.nn.utils.clip_grad_norm_([p for n, p in ma.named_parameters() if "disc_" in n], 0.3, foreach=True)
+        torch.nn.utils.clip_grad_norm_([p for n, p in ma.named_parameters()
+                                        if "vulnerability_head" in n or "line_feature_extractor" in n], 2.0, foreach=True)
+        tn_a = torch.linalg.vector_norm(torch.stack(torch._foreach_norm([p.grad for p in pa])))
+        ok_a = torch.isfinite(tn_a) & (tn_a <= 1000)
+        found.copy_((~ok_a).float())
+        oa.step()
+        for n, p in mb.named_parameters():
+            p.grad = grads[n].clone() if n in grads else None
+        tn_b, ok_b = tail.step(loss)
+        assert bool(ok_a) == bool(ok_b)
+        if bool(ok_a):
+            assert abs(tn_a.item() - tn_b.item()) < 1e-4 * tn_a.item()
+        go = {n: (grads[n].detach().cpu().clone() if n in grads else None) for n in params_o}
+        stepped_o, tn_o = O.clip_and_adamw(params_o, go, state_o, lr=1e-3, wd=0.1)
+        assert stepped_o == bool(ok_b)
+        if stepped_o:
+            assert abs(tn_o - tn_b.item()) < 1e-4 * tn_o
+    for (n, a), b in zip(ma.named_parameters(), mb.parameters()):
+        assert torch.allclose(a, b, rtol=2e-5, atol=2e-6), n
+        assert torch.allclose(params_o[n].cuda(), b, rtol=2e-5, atol=2e-6), n
+    expect_steps = 0.0 if scale != scale else 3.0  # (after the clips the norm is <= 1: only NaN/Inf can skip)
+    for p in mb.parameters():
+        if p.grad is not None:
+            assert ob.state[p]["step"].item() == expect_steps
+    assert torch.equal(mb.dead, base.dead) and len(ob.state[mb.dead]) == 0
