@@ -45,18 +45,36 @@ __host__ inline DropCfg make_drop(float p, uint64_t seed, uint64_t offset) {
   return c;
 }
 
-// dropout multipliers for 4 consecutive elements starting at even index idx (idx % 4 == 0)
+// dropout multipliers for 4 consecutive elements starting at index idx (idx % 4 == 0): one strong hash of
+// (seed, offset, idx / 4) gives the first two 16-bit uniforms, a xorshift-multiply step of it the other two
 __device__ __forceinline__ void drop4(const DropCfg& dc, uint64_t idx, float (&m)[4]) {
   if (dc.thresh16 == 0) {
     m[0] = m[1] = m[2] = m[3] = 1.f;
     return;
   }
-  const uint32_t h0 = rng_pair(dc.seed, dc.offset, idx >> 1);
-  const uint32_t h1 = rng_pair(dc.seed, dc.offset, (idx >> 1) + 1);
+  const uint32_t h0 = rng_pair(dc.seed, dc.offset, idx >> 2);
+  uint32_t h1 = (h0 ^ (h0 >> 15)) * 0x2C1B3C6Du;
+  h1 ^= h1 >> 13;
   m[0] = ((h0 & 0xFFFFu) >= dc.thresh16) ? dc.inv_keep : 0.f;
   m[1] = ((h0 >> 16) >= dc.thresh16) ? dc.inv_keep : 0.f;
-  m[2] = ((h1 & 0xFFFFu) >= dc.thresh16) ? dc.inv_keep : 0.f;
-  m[3] = ((h1 >> 16) >= dc.thresh16) ? dc.inv_keep : 0.f;
+  m[2] = ((h1 >> 16) >= dc.thresh16) ? dc.inv_keep : 0.f;
+  m[3] = ((h1 & 0xFFFFu) >= dc.thresh16) ? dc.inv_keep : 0.f;
+}
+// 8 consecutive elements (idx % 8 == 0): one strong hash + three cheap steps
+__device__ __forceinline__ void drop8(const DropCfg& dc, uint64_t idx, float (&m)[8]) {
+  if (dc.thresh16 == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = 1.f;
+    return;
+  }
+  uint32_t h = rng_pair(dc.seed, dc.offset ^ 0x9E3779B97F4A7C15ull, idx >> 3);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m[2 * i] = ((h & 0xFFFFu) >= dc.thresh16) ? dc.inv_keep : 0.f;
+    m[2 * i + 1] = ((h >> 16) >= dc.thresh16) ? dc.inv_keep : 0.f;
+    h = (h ^ (h >> 15)) * 0x2C1B3C6Du;
+    h ^= h >> 13;
+  }
 }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -459,10 +477,8 @@ gelu_dropout_fwd_kernel(const __nv_bfloat16* __restrict__ z, __nv_bfloat16* __re
     const uint4 u = *reinterpret_cast<const uint4*>(z + i * 8);
     const uint32_t in[4] = {u.x, u.y, u.z, u.w};
     uint32_t out[4];
-    float m0[4], m1[4];
-    drop4(dc, (uint64_t)i * 8, m0);
-    drop4(dc, (uint64_t)i * 8 + 4, m1);
-    const float mm[8] = {m0[0], m0[1], m0[2], m0[3], m1[0], m1[1], m1[2], m1[3]};
+    float mm[8];
+    drop8(dc, (uint64_t)i * 8, mm);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float2 f = unpack_bf16(in[k]);
@@ -483,10 +499,8 @@ gelu_dropout_bwd_kernel(const __nv_bfloat16* __restrict__ g_h, const __nv_bfloat
     const uint32_t zi[4] = {uz.x, uz.y, uz.z, uz.w};
     const uint32_t gi[4] = {ug.x, ug.y, ug.z, ug.w};
     uint32_t out[4];
-    float m0[4], m1[4];
-    drop4(dc, (uint64_t)i * 8, m0);
-    drop4(dc, (uint64_t)i * 8 + 4, m1);
-    const float mm[8] = {m0[0], m0[1], m0[2], m0[3], m1[0], m1[1], m1[2], m1[3]};
+    float mm[8];
+    drop8(dc, (uint64_t)i * 8, mm);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float2 f = unpack_bf16(zi[k]);
