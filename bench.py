@@ -324,11 +324,22 @@ def main():
         kernels[k] = {"launches": n, "ms": round(t, 3), "share_of_step": round(t / step_ms_instr, 4),
                       "achieved": round(rate, 1), "unit": unit,
                       "frac": round(rate / (hbm_peak if unit == "GB/s" else tf_peak), 4)}
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01f_gemm_traffic.json")
+    if os.path.exists(tpath):  # DRAM bytes per launch of this kernel family from the committed ncu pass of the same step
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
     roofline = {"bound": "tensor", "kernel": "gemm_kernel (sct_gemm_bf16_nt/nn/tn: tcgen05 + TMEM + TMA)",
                 "achieved": round(achieved, 1), "peak": tf_peak, "unit": "TFLOP/s",
-                "frac": round(achieved / tf_peak, 4), "traffic": None, "peak_source": f"{peak_src} (sustained bf16)",
+                "frac": round(achieved / tf_peak, 4), "traffic": traffic,
+                "traffic_note": "ncu dram__bytes_read+write per launch, averaged over the 255 GEMM launches of one step "
+                                "(profiles/r01f_gemm_traffic.json); algorithmic A+B+D bytes average ~160 MB per launch",
+                "flops_per_launch": round(g_work / max(g_n, 1), 0),
+                "peak_source": f"{peak_src} (sustained bf16)",
                 "launches_per_step": g_n, "ms_per_step_in_kernel": round(g_ms, 3),
-                "share_of_step": round(g_ms / step_ms_instr, 4), "by_call": kernels}
+                "share_of_step": round(g_ms / step_ms_instr, 4), "share_of_timed_step": round(g_ms / ms_per_step, 4),
+                "note": "timed with CUDA events around every launch in one extra eager (non-graph) step after the timed region",
+                "by_call": kernels}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
