@@ -438,46 +438,97 @@ class SmartContractTransformer(nn.Module):
         """The sampling loop of model.py:862-930 (BOS = 1) with a KV cache: the reference re-embeds and re-decodes the
         whole prefix for every new token (O(T^2) decoder passes); here each step runs the decoder on ONE position,
         attending to cached self-attention K/V ([B, T_max, 2d] per layer) and to cross-attention K/V of the encoder
-        memory projected once.  Same arithmetic per position, so greedy tokens match the reference."""
+        memory projected once.  Same arithmetic per position, so greedy tokens match the reference.
+
+        The step has no host-visible state: the position is a device scalar (token / positional-encoding row / cache
+        slot are selected with it, keys past it are masked by a [B, T_max] byte mask that the attention kernel turns
+        into a tile count on the device), so ONE captured CUDA graph serves every step of every call with the same
+        (B, S, T_max) signature."""
         if not use_kv_cache:
             return self._generate_recompute(mem_b, B, S, src_kpm, apply_syntax_constraints, greedy, max_new_tokens)
-        dev, d, H = mem_b.device, self.d_model, self.nhead
+        dev, d = mem_b.device, self.d_model
         max_len = min(self.max_length, 1024)
         steps = max_len - 1 if max_new_tokens is None else min(max_len - 1, max_new_tokens)
-        layers = self.decoder.layers
-        ol = self.output_layer
-        pe = self.pos_encoder.pe.view(-1, d)
         t_max = (steps + 127) // 128 * 128
-        self_kv = [torch.zeros((B, t_max, 2 * d), dtype=BF16, device=dev) for _ in layers]
-        mem_kv = [self._lin_rows(mem_b, l.multihead_attn.in_proj_weight, l.multihead_attn.in_proj_bias, d, 3 * d)
-                  for l in layers]  # [B*S, 2d] each, projected once
-        tgt = torch.ones((B, steps + 1), dtype=torch.long, device=dev)
-        n_out = 1
+        key = (B, S, t_max, bool(apply_syntax_constraints), bool(greedy), dev.index)
+        cache = self.__dict__.setdefault("_decode_cache", {})
+        ent = cache.get(key)
+        layers = self.decoder.layers
+        if ent is None:
+            st = {
+                "pos": torch.zeros(1, dtype=torch.long, device=dev),
+                "tgt": torch.ones((B, t_max + 1), dtype=torch.long, device=dev),
+                "kpm_self": torch.ones((B, t_max), dtype=torch.uint8, device=dev),
+                "self_kv": [torch.zeros((B, t_max, 2 * d), dtype=BF16, device=dev) for _ in layers],
+                "mem_kv": [torch.empty((B * S, 2 * d), dtype=BF16, device=dev) for _ in layers],
+                "src_kpm": torch.empty((B, S), dtype=torch.bool, device=dev),
+                "nxt": torch.zeros((B, 1), dtype=torch.long, device=dev),
+            }
+            ent = cache[key] = {"st": st, "graph": None, "calls": 0}
+        st = ent["st"]
+        # per-call state: BOS, nothing cached yet, this call's encoder memory and padding mask
+        st["pos"].zero_()
+        st["tgt"].fill_(1)
+        st["kpm_self"].fill_(1)
+        st["src_kpm"].copy_(src_kpm)
+        self._shadow.begin_step(refresh=False)
+        for li, l in enumerate(layers):
+            ca = l.multihead_attn
+            st["mem_kv"][li].copy_(self._lin_rows(mem_b, ca.in_proj_weight, ca.in_proj_bias, d, 3 * d))
+        for l in layers:  # make every bf16 weight shadow the step reads valid before (re)playing the graph
+            for w in (l.self_attn.in_proj_weight, l.self_attn.out_proj.weight, l.multihead_attn.in_proj_weight,
+                      l.multihead_attn.out_proj.weight, l.linear1.weight, l.linear2.weight):
+                self._w(w)
+        self._w(self.output_layer.weight)
+        n_out = steps + 1
         for i in range(steps):
-            ids = tgt[:, i:i + 1].contiguous()
-            x, _ = ops.embed_ln_pe(ids, self.embedding.weight, self.embedding_norm.weight, self.embedding_norm.bias,
-                                   pe[i:], 1, math.sqrt(d), 0.0, True, False)
-            _, y = ops.residual_ln(x, None, layers[0].norm1.weight, layers[0].norm1.bias, mode="ln", want_x=False)
-            for li, layer in enumerate(layers):
-                sa = layer.self_attn
-                qkv = ops.linear(y, sa.in_proj_weight, sa.in_proj_bias, self._w(sa.in_proj_weight))
-                self_kv[li][:, i, :] = qkv[:, d:]
-                a = ops.cached_attention(qkv[:, :d], self_kv[li], B, H, i + 1)
-                x, y = ops.residual_ln(x, self._lin(a, sa.out_proj), layer.norm2.weight, layer.norm2.bias, 1.0, 0.0, "ln")
-                ca = layer.multihead_attn
-                q = self._lin_rows(y, ca.in_proj_weight, ca.in_proj_bias, 0, d)
-                c = ops.cross_attention(q, mem_kv[li], B, H, 1, S, src_kpm, 0.0)
-                x, y = ops.residual_ln(x, self._lin(c, ca.out_proj), layer.norm3.weight, layer.norm3.bias, 1.0, 0.0, "ln")
-                f = self._ffn(y, layer)
-                nxt_norm = layers[li + 1].norm1 if li + 1 < len(layers) else self.output_norm
-                x, y = ops.residual_ln(x, f, nxt_norm.weight, nxt_norm.bias, 1.0, 0.0, "ln")
-            logits = ops.linear(y, ol.weight, ol.bias, self._w(ol.weight))
-            nxt = self._sample(logits, tgt[:, :i + 1], apply_syntax_constraints, greedy)
-            tgt[:, i + 1] = nxt.view(-1)
-            n_out = i + 2
-            if max_new_tokens is None and self._stop(nxt, i):
+            if ent["graph"] is None and ent["calls"] >= 1 and i == 0:
+                # second call with this signature: capture the step once (the first call was the eager warm-up)
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g):
+                    self._decode_step(st, B, S, apply_syntax_constraints, greedy)
+                ent["graph"] = g
+            if ent["graph"] is not None:
+                ent["graph"].replay()
+            else:
+                self._decode_step(st, B, S, apply_syntax_constraints, greedy)
+            if max_new_tokens is None and self._stop(st["nxt"], i):
+                n_out = i + 2
                 break
-        return tgt[:, :n_out].contiguous()
+        ent["calls"] += 1
+        return st["tgt"][:, :n_out].clone()
+
+    def _decode_step(self, st, B, S, apply_syntax_constraints, greedy):
+        """One position through the decoder against the caches; everything indexed by the device scalar st['pos']."""
+        d, H = self.d_model, self.nhead
+        layers = self.decoder.layers
+        pos = st["pos"]
+        ids = st["tgt"].index_select(1, pos)                               # [B, 1] current input token
+        pe_row = self.pos_encoder.pe.view(-1, d).index_select(0, pos)      # [1, d]
+        st["kpm_self"].index_fill_(1, pos, 0)                              # the new position becomes visible
+        x, _ = ops.embed_ln_pe(ids, self.embedding.weight, self.embedding_norm.weight, self.embedding_norm.bias,
+                               pe_row, 1, math.sqrt(d), 0.0, True, False)
+        _, y = ops.residual_ln(x, None, layers[0].norm1.weight, layers[0].norm1.bias, mode="ln", want_x=False)
+        for li, layer in enumerate(layers):
+            sa = layer.self_attn
+            qkv = ops.linear(y, sa.in_proj_weight, sa.in_proj_bias, self._w(sa.in_proj_weight))
+            st["self_kv"][li].index_copy_(1, pos, qkv[:, d:].unsqueeze(1))
+            a = ops.cached_attention(qkv[:, :d], st["self_kv"][li], B, H, st["self_kv"][li].shape[1], st["kpm_self"])
+            x, y = ops.residual_ln(x, self._lin(a, sa.out_proj), layer.norm2.weight, layer.norm2.bias, 1.0, 0.0, "ln")
+            ca = layer.multihead_attn
+            q = self._lin_rows(y, ca.in_proj_weight, ca.in_proj_bias, 0, d)
+            c = ops.cross_attention(q, st["mem_kv"][li], B, H, 1, S, st["src_kpm"], 0.0)
+            x, y = ops.residual_ln(x, self._lin(c, ca.out_proj), layer.norm3.weight, layer.norm3.bias, 1.0, 0.0, "ln")
+            f = self._ffn(y, layer)
+            nxt_norm = layers[li + 1].norm1 if li + 1 < len(layers) else self.output_norm
+            x, y = ops.residual_ln(x, f, nxt_norm.weight, nxt_norm.bias, 1.0, 0.0, "ln")
+        ol = self.output_layer
+        logits = ops.linear(y, ol.weight, ol.bias, self._w(ol.weight))
+        nxt = self._sample(logits, ids, apply_syntax_constraints, greedy)
+        st["nxt"].copy_(nxt)
+        st["tgt"].index_copy_(1, pos + 1, nxt)
+        pos.add_(1)
 
     @torch.no_grad()
     def _generate_recompute(self, mem_b, B, S, src_kpm, apply_syntax_constraints, greedy, max_new_tokens):

@@ -60,36 +60,39 @@ class DropoutRng:
 
 
 class ShadowCache:
-    """bf16 copies of fp32 parameters for the tensor-core GEMMs (private, non-persistent)."""
+    """bf16 copies of fp32 parameters for the tensor-core GEMMs (private, non-persistent).
+
+    Fused optimisers (torch's and csrc/optim.cu) update parameters without bumping Tensor._version, so a
+    training forward re-casts every weight it touches once per pass (~1.2 GB of traffic for the full model) and
+    marks the copy as not reusable; inference re-casts such a copy on first use and then keeps it until the
+    parameter's version or storage changes (load_state_dict, .to()).  Buffers are reused, so their addresses are
+    stable across casts (captured CUDA graphs keep reading the right memory)."""
 
     def __init__(self):
-        self._store = {}
-        # Fused optimisers update parameters without bumping Tensor._version, so a training forward re-casts
-        # every weight it touches once (always_refresh; ~1.2 GB of traffic for the full model).  Inference keeps
-        # the cached shadow until the parameter's version or storage changes (load_state_dict, .to()).
-        self.always_refresh = False
+        self._store = {}  # id(param) -> [version, bf16 buffer, data_ptr, reusable_in_eval]
+        self.training = False
         self._fresh = set()
 
     def begin_step(self, refresh: bool):
-        self.always_refresh = refresh
+        self.training = refresh
         self._fresh.clear()
 
     def get(self, p: torch.Tensor) -> torch.Tensor:
         key = id(p)
         ent = self._store.get(key)
-        if ent is not None and ent[1].device == p.device and ent[2] == p.data_ptr():
-            if self.always_refresh:
+        same = ent is not None and ent[1].device == p.device and ent[2] == p.data_ptr() and ent[1].shape == p.shape
+        if same:
+            if self.training:
                 if key in self._fresh:
                     return ent[1]
-            elif ent[0] == p._version:
+            elif ent[3] and ent[0] == p._version:
                 return ent[1]
         src = p.detach()
         src2 = src if src.dim() == 2 else src.view(1, -1)
         assert src2.is_contiguous()
-        buf = ent[1] if (ent is not None and ent[1].device == p.device and ent[1].shape == src.shape) else \
-            torch.empty(src.shape, dtype=BF16, device=p.device)
+        buf = ent[1] if same else torch.empty(src.shape, dtype=BF16, device=p.device)
         kn.cast_scale(src2, buf.view(src2.shape), 0, 1.0)
-        self._store[key] = (p._version, buf, p.data_ptr())
+        self._store[key] = [p._version, buf, p.data_ptr(), not self.training]
         self._fresh.add(key)
         return buf
 

@@ -261,7 +261,10 @@ def test_kv_cache_decode_matches_recompute_long(cuda_dev):
     kw = dict(input_ids=b["input_ids"], attention_mask=b["attention_mask"], ast_input_ids=b["ast_input_ids"],
               ast_attention_mask=b["ast_attention_mask"], target_ids=None, greedy=True, max_new_tokens=150,
               compute_vuln_heads=False)
-    a = m(**kw, use_kv_cache=True)["generated_sequence"]
+    a = m(**kw, use_kv_cache=True)["generated_sequence"]   # eager decode steps
+    a2 = m(**kw, use_kv_cache=True)["generated_sequence"]  # same signature again: steps replayed from one CUDA graph
+    a3 = m(**kw, use_kv_cache=True)["generated_sequence"]
+    assert torch.equal(a, a2) and torch.equal(a, a3)
     r = m(**kw, use_kv_cache=False)["generated_sequence"]
     assert a.shape == r.shape == (3, 151)
     agree = (a == r).float().mean().item()

@@ -34,7 +34,8 @@ def main():
     pm = torch.ones(B, 128, dtype=torch.long, device="cuda")
     kw = dict(input_ids=ids, attention_mask=am, ast_input_ids=ast, ast_attention_mask=pm, target_ids=None,
               greedy=True, compute_vuln_heads=False, use_kv_cache=not a.recompute)
-    m(**kw, max_new_tokens=8)
+    m(**kw, max_new_tokens=a.new)  # eager warm-up of this signature
+    m(**kw, max_new_tokens=a.new)  # second call captures the decode step into a CUDA graph
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     out = m(**kw, max_new_tokens=a.new)["generated_sequence"]
