@@ -179,3 +179,62 @@ def test_line_heads_vectorised_match_oracle_loops():
         ref_c = O.contract_heads(sd, cfg, memory, torch.float32)
         assert (mine_c - ref_c).abs().max().item() < 1e-4
         assert (m._line_heads(memory, None) - O.line_heads(sd, cfg, memory, None, torch.float32)).abs().max().item() < 1e-4
+
+
+def test_cabi_argument_errors_are_reported_without_a_gpu():
+    """Error behaviour of the boundary: bad arguments return non-zero and leave a message in sct_last_error()
+    (checked before any CUDA call, so this runs on a CPU box); the Python layer turns them into RuntimeError."""
+    import ctypes as C
+
+    from sct_gan_b200 import _lib
+
+    lib = _lib.load()
+    rc = lib.sct_embed_ln_pe_fwd(None, None, None, None, None, None, None, None, 8, 4, 10, 768, 1.0, 0.0, 0, 0, None)
+    assert rc != 0 and "null pointer" in _lib.last_error()
+    buf = (C.c_float * 8)()
+    p = C.cast(buf, C.c_void_p)
+    rc = lib.sct_gemm_bf16_nt(p, 8, p, 8, p, 8, None, 1.0, 0, 128, 64, 128, None)
+    assert rc != 0 and "empty GEMM" in _lib.last_error()
+    rc = lib.sct_attn_fwd(p, 768, p, p, 768, p, 768, None, None, 1, 8, 16, 16, 64, 0, 0.125, 0.0, 0, 0, None)
+    assert rc != 0 and "head_dim" in _lib.last_error()
+    rc = lib.sct_add_dropout_ln_fwd(p, None, 1.0, None, None, p, None, None, None, 4, 100, 0.0, 0, 0, None)
+    assert rc != 0 and "unsupported row width" in _lib.last_error()
+    rc = lib.sct_ce_rows(p, p, p, p, 4, 10, 9, 1.0, 0, None)
+    assert rc != 0 and "pitch" in _lib.last_error()
+    with pytest.raises(RuntimeError, match="sct_colsum_bf16 failed"):
+        _lib.call("sct_colsum_bf16", p, 7, p, 4, 8, 1.0, None)
+
+
+def test_eval_after_training_recasts_weight_shadows():
+    """ShadowCache rules (host logic): copies made during a training pass are never reused by an eval pass (fused
+    optimisers update weights without bumping Tensor._version); eval copies are reused until the version moves."""
+    from sct_gan_b200 import ops
+
+    calls = []
+    real = ops.kn.cast_scale
+    ops.kn.cast_scale = lambda src, dst, col_off=0, scale=1.0: calls.append(1) or dst.copy_(src)
+    try:
+        w = torch.nn.Parameter(torch.randn(4, 8))
+        sc = ops.ShadowCache()
+        sc.begin_step(refresh=True)
+        a = sc.get(w)
+        sc.get(w)
+        assert len(calls) == 1  # once per training pass
+        sc.begin_step(refresh=True)
+        sc.get(w)
+        assert len(calls) == 2  # and again in the next one
+        with torch.no_grad():
+            w.data.add_(1.0)  # what a fused optimiser does: no version bump
+        sc.begin_step(refresh=False)
+        b = sc.get(w)
+        assert len(calls) == 3 and b.data_ptr() == a.data_ptr()  # eval after training: re-cast, same buffer
+        assert torch.equal(b.float(), w.detach().to(torch.bfloat16).float())
+        sc.begin_step(refresh=False)
+        sc.get(w)
+        assert len(calls) == 3  # eval copy reused
+        with torch.no_grad():
+            w.mul_(2.0)  # versioned in-place update (load_state_dict, manual edits)
+        sc.get(w)
+        assert len(calls) == 4
+    finally:
+        ops.kn.cast_scale = real
