@@ -88,7 +88,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -158,7 +158,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     sB, sS, sP = 1, CFG["S"], CFG["P"]
-    sec, toks, threads = cpu_reference_step_time(sB, sS, sP, max(1, min(args.steps, 2)), min(args.warmup, 1))
+    sec, toks, threads = cpu_reference_step_time(sB, sS, sP, max(1, min(args.steps, 40)), max(0, min(args.warmup, 5)))
     v = toks / sec
     sample = f"{sB} contract(s) of the workload (S=P=T={sS}) per step, fp32, {threads} host threads, dropout off"
     print(json.dumps({
@@ -343,10 +343,10 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sec, toks, threads = cpu_reference_step_time(1, S, P, 1, 1)
+        sec, toks, threads = cpu_reference_step_time(1, S, P, 4, 1)
         cpu = {"value": toks / sec, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"1 contract of the workload (S=P=T={S}) per step, full step incl. backward/clips/AdamW, fp32, "
-                         f"1 warm-up + 1 timed step = {sec:.1f} s/step"}
+                         f"1 warm-up + 4 timed steps, {sec:.1f} s/step"}
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
