@@ -341,6 +341,14 @@ def main():
                 "note": "timed with CUDA events around every launch in one extra eager (non-graph) step after the timed region",
                 "by_call": kernels}
 
+    in_sync = None
+    if world > 1:  # data-parallel sanity: after the same number of steps every replica must hold identical weights
+        probe = torch.stack([model.output_layer.weight.detach().double().sum(),
+                             model.encoder.layers[0].linear1.weight.detach().double().sum(),
+                             model.embedding.weight.detach().double().sum()])
+        gathered = [torch.empty_like(probe) for _ in range(world)]
+        dist.all_gather(gathered, probe)
+        in_sync = all(torch.equal(g, gathered[0]) for g in gathered)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sec, toks, threads = cpu_reference_step_time(1, S, P, 4, 1)
@@ -358,7 +366,7 @@ def main():
                        "l2": "no explicit flush: each step streams several GB of activations/weights (>> 126 MB L2)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu,
-            "host_enqueue_ms_per_step": round(cpu_ms_per_step, 2),
+            "host_enqueue_ms_per_step": round(cpu_ms_per_step, 2), "dp_replicas_in_sync": in_sync,
         }))
     if world > 1:
         # Tearing the NCCL communicator down while captured graphs still reference its collectives hangs

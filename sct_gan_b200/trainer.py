@@ -91,8 +91,39 @@ def param_group_of(name: str, use_gan: bool) -> int:
     return 0
 
 
+def _is_nccl(group):
+    try:
+        return dist.get_backend(group) == "nccl"
+    except Exception:
+        return False
+
+
+def _launch_bucket(bucket, world, group):
+    """Mean all-reduce of the gradients of `bucket`, in place and asynchronously.  NCCL: one grouped launch
+    (coalescing manager, ReduceOp.AVG: no flatten / copy-back / scaling passes).  Other back-ends (gloo in the CPU
+    tests): flat SUM + scale."""
+    if _is_nccl(group):
+        with dist._coalescing_manager(group=group, device=bucket[0].grad.device, async_ops=True) as cm:
+            for p in bucket:
+                dist.all_reduce(p.grad, op=dist.ReduceOp.AVG, group=group)
+        return (cm, None, None)
+    flat = torch.cat([p.grad.reshape(-1) for p in bucket])
+    return (dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True), flat, bucket)
+
+
+def _finish_bucket(work, world):
+    w, flat, ps = work
+    w.wait()
+    if flat is not None:
+        off = 0
+        for p in ps:
+            n = p.grad.numel()
+            p.grad.copy_(flat[off:off + n].view_as(p.grad)).mul_(1.0 / world)
+            off += n
+
+
 def allreduce_mean_grads(params, world, group=None, bucket_bytes=32 << 20):
-    """Data-parallel gradient exchange: mean-reduce `.grad` across ranks in flat fp32 buckets, launched
+    """Data-parallel gradient exchange after backward: mean-reduce `.grad` across ranks in buckets, launched
     asynchronously in reverse registration order (the order backward produced them: vocab projection first,
     embeddings last) and joined before the clips.  Parameters without a gradient (the dead
     disc_grammar_embedding, empty_line_embedding when every line has tokens) are skipped; they are the same
@@ -100,28 +131,45 @@ def allreduce_mean_grads(params, world, group=None, bucket_bytes=32 << 20):
     losses => the result equals the single-process gradient of the concatenated batch."""
     live = [p for p in params if p.grad is not None]
     works, bucket, size = [], [], 0
-
-    def flush():
-        nonlocal bucket, size
-        if bucket:
-            flat = torch.cat([p.grad.reshape(-1) for p in bucket])
-            works.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True), flat, bucket))
-            bucket, size = [], 0
-
     for p in reversed(live):
         bucket.append(p)
         size += p.grad.numel() * p.grad.element_size()
         if size >= bucket_bytes:
-            flush()
-    flush()
-    inv = 1.0 / world
-    for work, flat, ps in works:
-        work.wait()
-        off = 0
-        for p in ps:
-            n = p.grad.numel()
-            p.grad.copy_(flat[off:off + n].view_as(p.grad)).mul_(inv)
-            off += n
+            works.append(_launch_bucket(bucket, world, group))
+            bucket, size = [], 0
+    if bucket:
+        works.append(_launch_bucket(bucket, world, group))
+    for w in works:
+        _finish_bucket(w, world)
+
+
+class OverlappedGradReducer:
+    """The same exchange, overlapped with backward: a post-accumulate-grad hook on every parameter collects
+    gradients as autograd finishes them and launches a bucket's all-reduce as soon as it is full, on NCCL's own
+    stream, while backward keeps producing the next bucket.  `finish()` joins before the clips.  Works inside a
+    CUDA-graph capture (the collectives become graph nodes on a forked stream)."""
+
+    def __init__(self, params, world, group=None, bucket_bytes=32 << 20):
+        self.world, self.group, self.bucket_bytes = world, group, bucket_bytes
+        self.bucket, self.size, self.works = [], 0, []
+        self.handles = [p.register_post_accumulate_grad_hook(self._hook) for p in params if p.requires_grad]
+
+    def _hook(self, p):
+        if p.grad is None:
+            return
+        self.bucket.append(p)
+        self.size += p.grad.numel() * p.grad.element_size()
+        if self.size >= self.bucket_bytes:
+            self.works.append(_launch_bucket(self.bucket, self.world, self.group))
+            self.bucket, self.size = [], 0
+
+    def finish(self):
+        if self.bucket:
+            self.works.append(_launch_bucket(self.bucket, self.world, self.group))
+            self.bucket, self.size = [], 0
+        for w in self.works:
+            _finish_bucket(w, self.world)
+        self.works = []
 
 
 class FusedClipAdamW:
@@ -283,6 +331,8 @@ class SmartContractTrainer:
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.bucket_bytes = bucket_mb << 20
+        self._reducer = OverlappedGradReducer(list(model.parameters()), self.world, process_group, self.bucket_bytes) \
+            if self.world > 1 else None
         self.use_cuda_graph = use_cuda_graph and on_gpu
         self._fused_tail = FusedClipAdamW(self.optimizer, list(model.named_parameters()), use_gan, max_grad_norm) \
             if (fused_optimizer and on_gpu) else None
@@ -335,7 +385,7 @@ class SmartContractTrainer:
 
     def _allreduce_grads(self):
         if self.world > 1:
-            allreduce_mean_grads(list(self.model.parameters()), self.world, self.pg, self.bucket_bytes)
+            self._reducer.finish()  # buckets were launched from the gradient hooks while backward was running
 
     def _step_body(self, batch, syntax_penalty, n_lines):
         model = self.model

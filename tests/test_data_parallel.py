@@ -29,19 +29,24 @@ class Toy(nn.Module):
         return self.b(torch.tanh(self.a(x)))
 
 
-def _worker(rank, world, port, bucket_bytes, ret):
+def _worker(rank, world, port, bucket_bytes, overlapped, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from sct_gan_b200.trainer import allreduce_mean_grads
+    from sct_gan_b200.trainer import OverlappedGradReducer, allreduce_mean_grads
 
     torch.manual_seed(1)
     x = torch.randn(8, 16)
     y = torch.randn(8, 4)
     m = Toy()
     shard = slice(rank * 4, rank * 4 + 4)
-    ((m(x[shard]) - y[shard]) ** 2).mean().backward()
-    allreduce_mean_grads(list(m.parameters()), world, None, bucket_bytes)
+    if overlapped:  # buckets launched from post-accumulate-grad hooks during backward, joined afterwards
+        red = OverlappedGradReducer(list(m.parameters()), world, None, bucket_bytes)
+        ((m(x[shard]) - y[shard]) ** 2).mean().backward()
+        red.finish()
+    else:
+        ((m(x[shard]) - y[shard]) ** 2).mean().backward()
+        allreduce_mean_grads(list(m.parameters()), world, None, bucket_bytes)
     # confidence exchange used for the 0.3 / 0.8 GAN branches (trainer.compute_losses)
     c = torch.tensor([0.2 + 0.4 * rank])
     dist.all_reduce(c)
@@ -55,10 +60,10 @@ def _worker(rank, world, port, bucket_bytes, ret):
 
 def test_bucketed_allreduce_equals_single_process():
     world = 2
-    for bucket_bytes in (64, 1 << 20):  # many tiny buckets / one bucket
+    for bucket_bytes, overlapped in ((64, False), (1 << 20, False), (64, True), (1 << 20, True)):
         mgr = mp.Manager()
         ret = mgr.dict()
-        mp.spawn(_worker, args=(world, _free_port(), bucket_bytes, ret), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), bucket_bytes, overlapped, ret), nprocs=world, join=True)
         torch.manual_seed(1)
         x = torch.randn(8, 16)
         y = torch.randn(8, 4)
