@@ -47,7 +47,10 @@ class DropoutRng:
         if ep is None or ep.device != device:
             ep = torch.zeros(2, dtype=torch.int64, device=device)  # [0] = epoch (16-byte allocation)
             owner._drop_epoch = ep
-            owner._drop_seed = (torch.initial_seed() * 1000003 + 0x5C7B200) & 0x7FFFFFFFFFFFFFFF
+            rank = 0
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                rank = torch.distributed.get_rank()  # replicas see different samples: give them different masks too
+            owner._drop_seed = (torch.initial_seed() * 1000003 + rank * 7919 + 0x5C7B200) & 0x7FFFFFFFFFFFFFFF
         cls.seed = owner._drop_seed
         _lib.call("sct_set_dropout_epoch_ptr", ep.data_ptr())
         ep[:1].add_(1)
