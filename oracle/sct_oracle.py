@@ -505,3 +505,37 @@ def synth_state_dict(shapes: dict, seed: int = 0) -> dict:
     if "path_embedding.weight" in shapes:
         sd["path_embedding.weight"] = sd["ast_embedding.weight"]
     return sd
+
+
+# ------------------------------------------------------------------------------------------------
+# syntax penalty (train.py:334-431), loops kept
+# ------------------------------------------------------------------------------------------------
+def syntax_penalty_loops(target_ids, keyword_followers: dict, stmt_ids, semicolon, lpar, rpar, lbrace, rbrace):
+    """keyword_followers: {keyword id: [follower ids]} (train.py:284-304).  Returns a Python float."""
+    n = target_ids.numel()
+    if target_ids.dim() == 1:
+        t = target_ids.view(n // 1024, 1024) if (n % 1024 == 0 and n > 0) else target_ids.view(1, n)
+    else:
+        t = target_ids
+    total, count = 0.0, 0
+    B, L = t.shape
+    rows = t.tolist()
+    for b in range(B):
+        row = rows[b]
+        for i in range(L - 1):
+            cur, nxt = row[i], row[i + 1]
+            if cur in keyword_followers:
+                exp = keyword_followers[cur]
+                if exp and nxt not in exp:
+                    total += 2.0
+                    count += 1
+            if cur in stmt_ids and nxt != semicolon:
+                total += 1.5
+                count += 1
+            if cur == lpar and rpar not in row[i + 1:min(i + 20, L)]:
+                total += 1.0
+                count += 1
+            if cur == lbrace and rbrace not in row[i + 1:min(i + 50, L)]:
+                total += 1.0
+                count += 1
+    return total / count if count > 0 else 0.0

@@ -7,6 +7,7 @@ its hot path runs in hand-written sm_100a CUDA behind the C ABI of include/sct_b
 built in-tree by `python -m sct_gan_b200.build`).  There is no CPU or PyTorch-eager fallback for that path.
 """
 from .model import PositionalEncoding, SmartContractTransformer  # noqa: F401
+from .syntax import SoliditySyntaxRules  # noqa: F401
 from .trainer import SmartContractTrainer  # noqa: F401
 
-__all__ = ["SmartContractTransformer", "PositionalEncoding", "SmartContractTrainer"]
+__all__ = ["SmartContractTransformer", "PositionalEncoding", "SmartContractTrainer", "SoliditySyntaxRules"]

@@ -295,7 +295,7 @@ class SmartContractTrainer:
     def __init__(self, model, learning_rate=1e-6, weight_decay=0.1, max_grad_norm=1.0, use_augmentation=False,
                  use_gan=False, line_vuln_weight=2.0, contract_vuln_weight=3.0, warmup_epochs=5,
                  compute_vuln_heads=True, process_group=None, bucket_mb=32, use_cuda_graph=False,
-                 fused_optimizer=True):
+                 fused_optimizer=True, syntax_rules=None):
         self.model = model
         self.use_augmentation = use_augmentation
         self.use_gan = use_gan
@@ -307,6 +307,9 @@ class SmartContractTrainer:
         self.stability_factor = 1.0
         self.line_loss_scale = 1.0
         self.compute_vuln_heads = compute_vuln_heads
+        # optional sct_gan_b200.syntax.SoliditySyntaxRules: the constant syntax penalty of SoliditySyntaxLoss
+        # (train.py:327-330, weight 0.5 as the trainer constructs it at :510) computed on the device every step
+        self.syntax_rules = syntax_rules
         dev = next(model.parameters()).device
         # SpatialAwareFocalLoss (alpha, gamma, spatial_weight): constructor values (train.py:568-573), switched
         # after every batch on whether it held any vulnerable line (train.py:1174-1184) — kept on the device
@@ -394,7 +397,10 @@ class SmartContractTrainer:
                     ast_input_ids=batch["ast_input_ids"], ast_attention_mask=batch["ast_attention_mask"],
                     target_ids=target_ids, token_to_line=batch.get("token_to_line"), fused_loss=True,
                     return_logits=False, compute_vuln_heads=self.compute_vuln_heads, n_lines=n_lines)
+        if self.syntax_rules is not None:
+            syntax_penalty = self.syntax_rules.penalty(out["target_ids"])
         losses = self.compute_losses(out, batch, syntax_penalty, n_lines)
+        losses["syntax_penalty"] = syntax_penalty if torch.is_tensor(syntax_penalty) else None
         self.optimizer.zero_grad(set_to_none=True)
         losses["total_loss"].backward()
         self._allreduce_grads()

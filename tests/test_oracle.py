@@ -238,3 +238,40 @@ def test_eval_after_training_recasts_weight_shadows():
         assert len(calls) == 4
     finally:
         ops.kn.cast_scale = real
+
+
+def test_vectorised_syntax_penalty_matches_reference_loops():
+    """sct_gan_b200.syntax (vectorised device scan) against the oracle's restatement of the double loop of
+    train.py:334-431, with a fake tokenizer (token -> small id) on id streams dense in the special tokens."""
+    from oracle import sct_oracle as O
+    from sct_gan_b200.syntax import KEYWORD_FOLLOWERS, SoliditySyntaxRules
+
+    class FakeTok:
+        unk_token_id = 3
+
+        def __init__(self):
+            words = sorted({w for k, v in KEYWORD_FOLLOWERS.items() for w in [k] + v} | {";", "(", ")", "{", "}"})
+            words = [w for w in words if w not in ("interface", "'")]  # two unknown tokens -> unk id
+            self.map = {w: 10 + i for i, w in enumerate(words)}
+
+        def convert_tokens_to_ids(self, tok):
+            return self.map.get(tok, self.unk_token_id)
+
+    tok = FakeTok()
+    V = 64
+    rules = SoliditySyntaxRules(tok, V)
+    kf = {}
+    for kw, fl in KEYWORD_FOLLOWERS.items():
+        kid = tok.convert_tokens_to_ids(kw)
+        if kid != tok.unk_token_id:
+            kf[kid] = [i for i in (tok.convert_tokens_to_ids(f) for f in fl) if i != tok.unk_token_id]
+    stmt = [tok.convert_tokens_to_ids(w) for w in ("return", "break", "continue")]
+    args = (kf, stmt, tok.map[";"], tok.map["("], tok.map[")"], tok.map["{"], tok.map["}"])
+    g = torch.Generator().manual_seed(0)
+    for shape in ((2 * 1023,), (3 * 1024,), (2, 300), (1,), (57,)):
+        t = torch.randint(0, V, shape, generator=g)
+        want = O.syntax_penalty_loops(t, *args)
+        got = rules.penalty(t).item()
+        assert abs(got - want) < 1e-6, (shape, got, want)
+    quiet = torch.full((200,), 5, dtype=torch.long)  # nothing fires -> 0
+    assert rules.penalty(quiet).item() == 0.0 and O.syntax_penalty_loops(quiet, *args) == 0.0
