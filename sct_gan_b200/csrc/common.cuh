@@ -223,6 +223,54 @@ __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t cta_mask) {
       "h"(cta_mask)
       : "memory");
 }
+// ---- cta_group::2 (a pair of CTAs on the two SMs of a TPC drives ONE 256-row MMA) ---------------------------
+// Address of the same smem offset in CTA `rank` of the cluster (shared::cluster window).
+__device__ __forceinline__ uint32_t cluster_map(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// Arrive on an mbarrier that may live in a peer CTA (`bar` is a shared::cluster address from cluster_map).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// TMA load issued by either CTA of the pair into its OWN shared memory; the bytes are counted on `bar`, a
+// shared::cluster address (the leader CTA's `full` barrier), which is what the MMA-issuing thread waits on.
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// Executed by the same warp of BOTH CTAs of the pair.
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// One arrival on the barrier at this smem offset in every CTA of `cta_mask` once the pair's MMAs issued so far retire.
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(cta_mask)
+      : "memory");
+}
+// D (rows 0-127 in this CTA's TMEM, rows 128-255 in the peer's) (+)= A (each CTA's own 128 rows) * B (each CTA
+// holds N/2 of the rows); descriptors are CTA-relative and apply to both CTAs.  Leader CTA only.
+__device__ __forceinline__ void tc_mma_bf16_lh_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                    uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

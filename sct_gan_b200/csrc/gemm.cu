@@ -21,11 +21,12 @@
 // warps 2-5 = epilogue (TMEM -> registers -> swizzled smem -> TMA store / TMA reduce-add).
 // Two TMEM accumulator stages let the epilogue of tile i overlap the mainloop of tile i+1.
 //
-// CLUSTER = 2: two CTAs of a thread-block cluster work on vertically adjacent output tiles (same N block,
-// M blocks 2i and 2i+1).  Each loads its own A tile and HALF of the shared B tile, multicast by TMA into
-// both CTAs' shared memory, which halves the L2 -> SM traffic of the B operand (a 128x256 tile is otherwise
-// L2-bound near 12 TB/s).  A pipeline stage is released cluster-wide: each CTA's tcgen05.commit arrives on
-// the `empty` barrier of both CTAs (count 2), so nobody multicasts into a buffer a peer is still reading.
+// CLUSTER = 2 (cta_group::2): the two CTAs of a cluster (the two SMs of a TPC) compute ONE 256 x BN tile with
+// 256-row UMMAs issued by the leader CTA's MMA thread.  Each CTA loads its own 128 rows of A and only HALF of the
+// B tile (BN / 2 rows): the tensor cores of both SMs read both halves, so a pipeline stage is 32 KB instead of
+// 48 KB per SM (6 stages instead of 4, a third less L2 -> SM traffic, half the MMA issue work per SM).  Every
+// TMA load of the pair is counted on the LEADER's `full` barrier; tcgen05.commit multicasts the stage release
+// (`empty`) and the accumulator hand-off (`tfull`) to both CTAs; both epilogues arrive on the leader's `tempty`.
 #include <stdlib.h>
 
 #include "../../include/sct_b200.h"
@@ -48,10 +49,10 @@ struct GemmParams {
   float alpha;        // output scale applied before bias
 };
 
-template <int BN, bool OUT_F32>
+template <int BN, bool OUT_F32, int CLUSTER>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = BN / CLUSTER * BK * 2;  // this CTA's share of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // Epilogue staging: two [128 rows x 128 B] blocks (64 bf16 / 32 fp32 columns each), ping-ponged chunk by chunk.
   // A full-tile staging buffer (64 KB at BN = 256) would leave only 3 pipeline stages, and the mainloop is
@@ -89,8 +90,9 @@ template <int BN, bool A_MN, bool B_MN, bool OUT_F32, int CLUSTER>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
-  using C = Cfg<BN, OUT_F32>;
+  using C = Cfg<BN, OUT_F32, CLUSTER>;
   constexpr int STAGES = C::STAGES;
+  constexpr bool PAIR = CLUSTER == 2;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -121,18 +123,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmD);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, CLUSTER);  // one arrival per CTA of the cluster
+      mbar_init(bar_empty + 8 * s, 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_tempty + 8 * s, 4);  // one arrival per epilogue warp
+      mbar_init(bar_tempty + 8 * s, 4 * CLUSTER);  // one arrival per epilogue warp (of both CTAs of a pair)
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr_addr, C::TMEM_COLS);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(tmem_ptr_addr, C::TMEM_COLS);
+    else tmem_alloc(tmem_ptr_addr, C::TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
-  if (CLUSTER > 1) cluster_sync_all();  // peers' barriers are initialised before any remote arrive / multicast
+  if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
@@ -146,38 +151,44 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (CLUSTER > 1) tc.m_blk = tc.m_blk * CLUSTER + crank;
         for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          const uint32_t full = bar_full + 8 * s;
-          mbar_expect_tx(full, C::STAGE_BYTES);
           const uint32_t sA = smem_base + s * C::STAGE_BYTES;
           const uint32_t sB = sA + C::A_BYTES;
-          if (!A_MN) {
-            tma_load_2d(&tmA, full, sA, kb * BK, tc.m_blk * BM);
-          } else {
-#pragma unroll
-            for (int c = 0; c < BM / 64; ++c)
-              tma_load_2d(&tmA, full, sA + c * (BK * 128), tc.m_blk * BM + c * 64, kb * BK);
-          }
-          if (CLUSTER == 1) {
-            if (!B_MN) {
-              tma_load_2d(&tmB, full, sB, kb * BK, tc.n_blk * BN);
+          constexpr int BNL = BN / CLUSTER;           // B rows this CTA loads
+          const int n_base = tc.n_blk * BN + crank * BNL;
+          if (!PAIR) {
+            const uint32_t full = bar_full + 8 * s;
+            mbar_expect_tx(full, C::STAGE_BYTES);
+            if (!A_MN) {
+              tma_load_2d(&tmA, full, sA, kb * BK, tc.m_blk * BM);
             } else {
 #pragma unroll
-              for (int c = 0; c < BN / 64; ++c)
-                tma_load_2d(&tmB, full, sB + c * (BK * 128), tc.n_blk * BN + c * 64, kb * BK);
+              for (int c = 0; c < BM / 64; ++c)
+                tma_load_2d(&tmA, full, sA + c * (BK * 128), tc.m_blk * BM + c * 64, kb * BK);
+            }
+            if (!B_MN) {
+              tma_load_2d(&tmB, full, sB, kb * BK, n_base);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BNL / 64; ++c)
+                tma_load_2d(&tmB, full, sB + c * (BK * 128), n_base + c * 64, kb * BK);
             }
           } else {
-            // this CTA fetches its half of the B tile and multicasts it to both CTAs of the cluster
-            constexpr uint16_t kMask = (1u << CLUSTER) - 1;
-            if (!B_MN) {
-              constexpr int HR = BN / CLUSTER;  // rows of the [BN x 64] K-major tile per CTA
-              tma_load_2d_mc(&tmB, full, sB + crank * (HR * 128), kb * BK, tc.n_blk * BN + crank * HR, kMask);
+            // both CTAs' bytes are counted on the leader's barrier (its MMA thread consumes both halves)
+            const uint32_t full = cluster_map(bar_full + 8 * s, 0);
+            if (crank == 0) mbar_expect_tx(bar_full + 8 * s, 2 * C::STAGE_BYTES);
+            if (!A_MN) {
+              tma_load_2d_pair(&tmA, full, sA, kb * BK, tc.m_blk * BM);
             } else {
-              constexpr int HC = BN / 64 / CLUSTER;  // 64-wide MN blocks per CTA
 #pragma unroll
-              for (int c = 0; c < HC; ++c) {
-                const int cb = crank * HC + c;
-                tma_load_2d_mc(&tmB, full, sB + cb * (BK * 128), tc.n_blk * BN + cb * 64, kb * BK, kMask);
-              }
+              for (int c = 0; c < BM / 64; ++c)
+                tma_load_2d_pair(&tmA, full, sA + c * (BK * 128), tc.m_blk * BM + c * 64, kb * BK);
+            }
+            if (!B_MN) {
+              tma_load_2d_pair(&tmB, full, sB, kb * BK, n_base);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BNL / 64; ++c)
+                tma_load_2d_pair(&tmB, full, sB + c * (BK * 128), n_base + c * 64, kb * BK);
             }
           }
           if (++s == STAGES) {
@@ -189,8 +200,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * CLUSTER, BN, A_MN, B_MN);
+      constexpr uint16_t kPairMask = 3;
       // K-major: 8-row groups are 1024 B apart (SBO); LBO unused for swizzled K-major.
       // MN-major: 8-k-row groups are 1024 B apart (SBO); 64-wide MN blocks are BK*128 B apart (LBO).
       constexpr uint32_t A_LBO = A_MN ? BK * 128 : 16, B_LBO = B_MN ? BK * 128 : 16;
@@ -212,18 +224,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint32_t sB = sA + C::A_BYTES;
           const uint32_t a_lo = umma_desc_lo(sA, A_LBO), b_lo = umma_desc_lo(sB, B_LBO);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            tc_mma_bf16_lh(d_tmem, umma_lo_add(a_lo, k * A_KSTEP), kDescHi, umma_lo_add(b_lo, k * B_KSTEP), kDescHi,
-                           idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
-          // frees the smem stage once these MMAs retire — in every CTA of the cluster (B halves are shared)
-          if (CLUSTER == 1) tc_commit(bar_empty + 8 * s);
-          else tc_commit_mc(bar_empty + 8 * s, (uint16_t)((1u << CLUSTER) - 1));
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint32_t acc = (kb > tc.kb0 || k > 0) ? 1u : 0u;
+            if (PAIR)
+              tc_mma_bf16_lh_pair(d_tmem, umma_lo_add(a_lo, k * A_KSTEP), kDescHi, umma_lo_add(b_lo, k * B_KSTEP),
+                                  kDescHi, idesc, acc);
+            else
+              tc_mma_bf16_lh(d_tmem, umma_lo_add(a_lo, k * A_KSTEP), kDescHi, umma_lo_add(b_lo, k * B_KSTEP), kDescHi,
+                             idesc, acc);
+          }
+          // frees the smem stage once these MMAs retire (in both CTAs of a pair)
+          if (PAIR) tc_commit_pair(bar_empty + 8 * s, kPairMask);
+          else tc_commit(bar_empty + 8 * s);
           if (++s == STAGES) {
             s = 0;
             ph ^= 1;
           }
         }
-        tc_commit(bar_tfull + 8 * as);  // accumulator ready for the epilogue
+        // accumulator ready for the epilogue (of both CTAs of a pair)
+        if (PAIR) tc_commit_pair(bar_tfull + 8 * as, kPairMask);
+        else tc_commit(bar_tfull + 8 * as);
         if (++as == 2) {
           as = 0;
           aph ^= 1;
@@ -297,7 +317,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (cb == NCHUNK - 1) {  // TMEM stage drained: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(cluster_map(bar_tempty + 8 * as, 0));
+            else mbar_arrive(bar_tempty + 8 * as);
+          }
         }
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
@@ -321,8 +344,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
-  if (CLUSTER > 1) cluster_sync_all();  // no CTA leaves while a peer may still signal / multicast into it
-  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+  if (PAIR) cluster_sync_all();  // no CTA leaves while its peer may still signal it or read its B half
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
 }
 
 // -----------------------------------------------------------------------------------------------
@@ -332,7 +358,7 @@ template <int BN, bool A_MN, bool B_MN, bool OUT_F32, int CLUSTER>
 int launch_impl(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd,
                 const float* bias, float alpha, int64_t M, int64_t N, int64_t K, int k_splits_req,
                 cudaStream_t stream) {
-  using C = Cfg<BN, OUT_F32>;
+  using C = Cfg<BN, OUT_F32, CLUSTER>;
   auto kern = gemm_kernel<BN, A_MN, B_MN, OUT_F32, CLUSTER>;
   static bool attr_set = false;  // benign race: idempotent call
   if (!attr_set) {
@@ -364,7 +390,7 @@ int launch_impl(const void* A, int64_t lda, const void* B, int64_t ldb, void* D,
   p.m_tiles = (int)((M + BM * CLUSTER - 1) / (BM * CLUSTER));  // CLUSTER = 2: pairs of vertically adjacent tiles
   p.n_tiles = (int)((N + BN - 1) / BN);
   p.kb_total = (int)((K + BK - 1) / BK);
-  const int sms = num_sms();
+  const int sms = num_sms() / CLUSTER;  // concurrent work items (CTAs, or CTA pairs)
   int ks = 1;
   if (OUT_F32) {
     // split-K so that a small [N_out x K_in] weight gradient still fills the machine: the smallest split count
@@ -402,7 +428,7 @@ int launch_impl(const void* A, int64_t lda, const void* B, int64_t ldb, void* D,
     const int grid = total < sms ? total : sms;
     kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, tmD, p);
   } else {
-    const int clusters = total < sms / CLUSTER ? total : sms / CLUSTER;
+    const int clusters = total < sms ? total : sms;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(clusters * CLUSTER));
     cfg.blockDim = dim3(kThreads);
@@ -421,19 +447,21 @@ int launch_impl(const void* A, int64_t lda, const void* B, int64_t ldb, void* D,
   return 0;
 }
 
-// Measured on B200 (tools/gemm_bench.py, M = 32768): the multicast pairs halve the B-operand L2 traffic but do
-// not change throughput (1071 vs 1056 TFLOP/s at N = 2304, 843 vs 901 at N = K = 768): the 128x256 tile is not
-// L2-bound.  Off by default; SCT_GEMM_CLUSTER=1 enables it (kept: correct, tested, the base for cta_group::2).
+// CTA pairs (cta_group::2) for the 256-wide tile whenever there are at least two row tiles; SCT_GEMM_PAIR=0 forces
+// the single-CTA kernel (A/B timing).
 template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
 int launch(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd, const float* bias,
            float alpha, int64_t M, int64_t N, int64_t K, int k_splits_req, cudaStream_t stream) {
   static int use_cluster = -1;
   if (use_cluster < 0) {
-    const char* e = getenv("SCT_GEMM_CLUSTER");
-    use_cluster = (e != nullptr && e[0] == '1') ? 1 : 0;
+    const char* e = getenv("SCT_GEMM_PAIR");
+    use_cluster = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
-  if (use_cluster && M >= 4 * BM)
-    return launch_impl<BN, A_MN, B_MN, OUT_F32, 2>(A, lda, B, ldb, D, ldd, bias, alpha, M, N, K, k_splits_req, stream);
+  if constexpr (BN == 256) {
+    if (use_cluster && M > BM)
+      return launch_impl<BN, A_MN, B_MN, OUT_F32, 2>(A, lda, B, ldb, D, ldd, bias, alpha, M, N, K, k_splits_req,
+                                                     stream);
+  }
   return launch_impl<BN, A_MN, B_MN, OUT_F32, 1>(A, lda, B, ldb, D, ldd, bias, alpha, M, N, K, k_splits_req, stream);
 }
 

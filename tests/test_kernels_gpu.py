@@ -29,7 +29,7 @@ def _no_timeouts():
 @pytest.mark.parametrize("M,N,K,bn", [
     (128, 128, 64, 128), (256, 256, 128, 128), (4096, 768, 768, 128), (4096, 2304, 768, 256),
     (4096, 2048, 768, 256), (4096, 768, 2048, 128), (1000, 520, 776, 128), (2048, 50265, 768, 256),
-    (333, 384, 768, 128), (4096, 768, 384, 128),
+    (333, 384, 768, 128), (4096, 768, 384, 128), (1000, 520, 776, 256), (384, 512, 128, 256), (129, 768, 768, 256),
 ])
 def test_gemm_nt(cuda_dev, M, N, K, bn):
     from sct_gan_b200 import kernels as kn
@@ -50,7 +50,7 @@ def test_gemm_nt(cuda_dev, M, N, K, bn):
 
 @pytest.mark.parametrize("M,N,K,bn", [
     (128, 128, 64, 128), (4096, 768, 2304, 128), (4096, 768, 768, 128), (4096, 2048, 768, 256),
-    (1000, 776, 520, 128), (2048, 768, 50272, 128),
+    (1000, 776, 520, 128), (2048, 768, 50272, 128), (1000, 776, 520, 256), (4096, 768, 2304, 256),
 ])
 def test_gemm_nn(cuda_dev, M, N, K, bn):
     from sct_gan_b200 import kernels as kn
