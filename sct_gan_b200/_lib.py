@@ -36,6 +36,7 @@ SIGNATURES = {
     "sct_gemm_bf16_nt": [_p, _i64, _p, _i64, _p, _i64, _p, _f, _i64, _i64, _i64, _i32, _p],
     "sct_gemm_bf16_nn": [_p, _i64, _p, _i64, _p, _i64, _p, _f, _i64, _i64, _i64, _i32, _p],
     "sct_gemm_bf16_tn": [_p, _i64, _p, _i64, _p, _i64, _f, _i64, _i64, _i64, _i32, _p],
+    "sct_gemm_bf16_tn_colsum": [_p, _i64, _p, _i64, _p, _i64, _p, _f, _i64, _i64, _i64, _i32, _p],
     "sct_attn_fwd": [_p, _i64, _p, _p, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _f, _f,
                      _u64, _u64, _p],
     "sct_attn_fwd_strided": [_p, _i64, _p, _p, _i64, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _f,
@@ -107,9 +108,14 @@ class Stats:
         cls._work = work
 
 
+# entry points that run the same kernel are accounted under one name
+STAT_NAME = {"sct_gemm_bf16_tn_colsum": "sct_gemm_bf16_tn"}
+
+
 def call(name: str, *args) -> None:
     fn = getattr(load(), name)
     ev = Stats.events
+    name = STAT_NAME.get(name, name)
     if ev is not None and name in Stats.timed:
         import torch
 

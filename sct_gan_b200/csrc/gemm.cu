@@ -17,8 +17,10 @@
 // [rows x 128 B] with the TMA/UMMA 128-byte swizzle; a K-major tile is one block [128|BN rows x 64 k],
 // an MN-major tile is BM/64 (BN/64) blocks of [64 k-rows x 64 mn].
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2-5 = epilogue (TMEM -> registers -> swizzled smem -> TMA store / TMA reduce-add).
+// Roles (256 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2-5 = epilogue (TMEM -> registers -> swizzled smem -> TMA store / TMA reduce-add), warps 6-7 = optional
+// column sums of the A operand (wgrad only: the bias gradient db = colsum(dY) read from the dY tiles that are in
+// shared memory anyway, instead of a separate pass over dY in HBM).
 // Two TMEM accumulator stages let the epilogue of tile i overlap the mainloop of tile i+1.
 //
 // CLUSTER = 2 (cta_group::2): the two CTAs of a cluster (the two SMs of a TPC) compute ONE 256 x BN tile with
@@ -37,7 +39,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 192;
+constexpr int kThreads = 256;
 constexpr int kSmemLimit = 232448;  // 227 KB
 
 struct GemmParams {
@@ -47,6 +49,7 @@ struct GemmParams {
   int n_fast;         // 1: consecutive tiles walk N first (A tile reused from L2), 0: walk M first
   const float* bias;  // nullable, fp32 [N]
   float alpha;        // output scale applied before bias
+  float* colsum;      // nullable (MN-major A only), fp32 [M]: += alpha * sum_k A[k, m]
 };
 
 template <int BN, bool OUT_F32, int CLUSTER>
@@ -58,7 +61,7 @@ struct Cfg {
   // A full-tile staging buffer (64 KB at BN = 256) would leave only 3 pipeline stages, and the mainloop is
   // bound by the bytes it can keep in flight (measured: the MMA thread waited on `full` 44 % of the time).
   static constexpr int C_BYTES = 2 * BM * 128;
-  static constexpr int AUX_BYTES = 1024;  // barriers + tmem ptr + bias tile
+  static constexpr int AUX_BYTES = 1024;  // barriers + tmem ptr
   static constexpr int STAGES_RAW = (kSmemLimit - 1024 - C_BYTES - AUX_BYTES - BN * 4) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + C_BYTES + AUX_BYTES + BN * 4;
@@ -105,6 +108,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t bar_tfull = sAux + 16 * STAGES;
   const uint32_t bar_tempty = bar_tfull + 16;
   const uint32_t tmem_ptr_addr = bar_tempty + 16;
+  const uint32_t bar_done = sAux + 512;  // [STAGES] colsum mode: the MMAs reading this stage have retired
   volatile uint32_t* tmem_ptr_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_addr - smem_base));
   float* bias_s = reinterpret_cast<float*>(smem_gen + (sAux + C::AUX_BYTES - smem_base));
@@ -124,6 +128,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_done + 8 * s, 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
@@ -217,6 +222,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         mbar_wait(bar_tempty + 8 * as, aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
+        int sel = (A_MN && p.colsum != nullptr) ? tc.kb0 % p.n_tiles : -1;  // == n_blk: stage goes to the colsum warps
         for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
@@ -233,9 +239,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tc_mma_bf16_lh(d_tmem, umma_lo_add(a_lo, k * A_KSTEP), kDescHi, umma_lo_add(b_lo, k * B_KSTEP), kDescHi,
                              idesc, acc);
           }
-          // frees the smem stage once these MMAs retire (in both CTAs of a pair)
-          if (PAIR) tc_commit_pair(bar_empty + 8 * s, kPairMask);
-          else tc_commit(bar_empty + 8 * s);
+          // frees the smem stage once these MMAs retire (in both CTAs of a pair); in column-sum mode every
+          // n_tiles-th stage goes to the colsum warps first, which release it after reading the A tile
+          const uint32_t rel = (sel == tc.n_blk) ? bar_done : bar_empty;
+          if (sel >= 0 && ++sel == p.n_tiles) sel = 0;
+          if (PAIR) tc_commit_pair(rel + 8 * s, kPairMask);
+          else tc_commit(rel + 8 * s);
           if (++s == STAGES) {
             s = 0;
             ph ^= 1;
@@ -247,6 +256,65 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (++as == 2) {
           as = 0;
           aph ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 6) {
+    // ===================== column sums of A (warps 6, 7; wgrad only) =====================
+    // The n_tiles items that share a row block see the same A tiles: item n_blk sums the k-blocks with
+    // kb % n_tiles == n_blk, so the extra shared-memory reads are spread over all items.
+    if (A_MN && p.colsum != nullptr) {
+      const int cw = warp - 6;  // 64-column block of the [64 k x 128 m] A tile this warp sums
+      // lane reads the 16-byte chunk (lane & 7) of k-rows (lane >> 3) + 4 i; chunks are XOR-swizzled by (row & 7)
+      const uint32_t rg = lane >> 3, ch = lane & 7;
+      const uint32_t off_even = rg * 128 + ((ch ^ rg) << 4);        // rows with (row & 7) == rg
+      const uint32_t off_odd = rg * 128 + ((ch ^ (rg + 4)) << 4);   // rows with (row & 7) == rg + 4
+      int s = 0;
+      uint32_t done_ph = 0;  // phase bit per stage of the `done` barriers (only some stages use them)
+      for (int t = item0; t < total_tiles; t += item_stride) {
+        TileCoord tc = decode_tile(p, t);
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        int sel = tc.kb0 % p.n_tiles;
+        for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+          if (sel == tc.n_blk) {
+            mbar_wait(bar_done + 8 * s, (done_ph >> s) & 1u);
+            done_ph ^= 1u << s;
+            const uint32_t blk = smem_base + s * C::STAGE_BYTES + cw * (BK * 128);
+#pragma unroll
+            for (int i = 0; i < BK / 4; ++i) {
+              uint32_t u0, u1, u2, u3;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3)
+                           : "r"(blk + i * 512 + ((i & 1) ? off_odd : off_even)));
+              acc[0] += __uint_as_float(u0 << 16);
+              acc[1] += __uint_as_float(u0 & 0xffff0000u);
+              acc[2] += __uint_as_float(u1 << 16);
+              acc[3] += __uint_as_float(u1 & 0xffff0000u);
+              acc[4] += __uint_as_float(u2 << 16);
+              acc[5] += __uint_as_float(u2 & 0xffff0000u);
+              acc[6] += __uint_as_float(u3 << 16);
+              acc[7] += __uint_as_float(u3 & 0xffff0000u);
+            }
+            named_bar_sync(2, 64);  // both colsum warps are done with the stage
+            if (warp == 6 && lane == 0) mbar_arrive(bar_empty + 8 * s);
+          }
+          if (++sel == p.n_tiles) sel = 0;
+          if (++s == STAGES) s = 0;
+        }
+        // fold the four row groups, then lanes 0..7 hold 8 columns each
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+          acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+        }
+        if (lane < 8) {
+          const int m_blk = CLUSTER > 1 ? tc.m_blk * CLUSTER + crank : tc.m_blk;
+          const int m = m_blk * BM + cw * 64 + 8 * lane;
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (m + e < p.M) atomicAdd(p.colsum + m + e, acc[e] * p.alpha);
         }
       }
     }
@@ -356,7 +424,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // -----------------------------------------------------------------------------------------------
 template <int BN, bool A_MN, bool B_MN, bool OUT_F32, int CLUSTER>
 int launch_impl(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd,
-                const float* bias, float alpha, int64_t M, int64_t N, int64_t K, int k_splits_req,
+                const float* bias, float* colsum, float alpha, int64_t M, int64_t N, int64_t K, int k_splits_req,
                 cudaStream_t stream) {
   using C = Cfg<BN, OUT_F32, CLUSTER>;
   auto kern = gemm_kernel<BN, A_MN, B_MN, OUT_F32, CLUSTER>;
@@ -422,6 +490,7 @@ int launch_impl(const void* A, int64_t lda, const void* B, int64_t ldb, void* D,
   p.k_splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.n_fast = (p.n_tiles <= p.m_tiles) ? 1 : 0;
   p.bias = bias;
+  p.colsum = colsum;
   p.alpha = alpha;
   const int total = p.m_tiles * p.n_tiles * p.k_splits;
   if (CLUSTER == 1) {
@@ -451,7 +520,7 @@ int launch_impl(const void* A, int64_t lda, const void* B, int64_t ldb, void* D,
 // the single-CTA kernel (A/B timing).
 template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
 int launch(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd, const float* bias,
-           float alpha, int64_t M, int64_t N, int64_t K, int k_splits_req, cudaStream_t stream) {
+           float* colsum, float alpha, int64_t M, int64_t N, int64_t K, int k_splits_req, cudaStream_t stream) {
   static int use_cluster = -1;
   if (use_cluster < 0) {
     const char* e = getenv("SCT_GEMM_PAIR");
@@ -459,10 +528,11 @@ int launch(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int6
   }
   if constexpr (BN == 256) {
     if (use_cluster && M > BM)
-      return launch_impl<BN, A_MN, B_MN, OUT_F32, 2>(A, lda, B, ldb, D, ldd, bias, alpha, M, N, K, k_splits_req,
-                                                     stream);
+      return launch_impl<BN, A_MN, B_MN, OUT_F32, 2>(A, lda, B, ldb, D, ldd, bias, colsum, alpha, M, N, K,
+                                                     k_splits_req, stream);
   }
-  return launch_impl<BN, A_MN, B_MN, OUT_F32, 1>(A, lda, B, ldb, D, ldd, bias, alpha, M, N, K, k_splits_req, stream);
+  return launch_impl<BN, A_MN, B_MN, OUT_F32, 1>(A, lda, B, ldb, D, ldd, bias, colsum, alpha, M, N, K, k_splits_req,
+                                                 stream);
 }
 
 int check_common(const void* A, const void* B, const void* D, int64_t M, int64_t N, int64_t K) {
@@ -496,8 +566,8 @@ int32_t sct_gemm_bf16_nt(const void* A, int64_t lda, const void* W, int64_t ldw,
                          void* stream) {
   if (int rc = sct::check_common(A, W, D, M, N, K)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (bn == 256) return sct::launch<256, false, false, false>(A, lda, W, ldw, D, ldd, bias, alpha, M, N, K, 1, st);
-  return sct::launch<128, false, false, false>(A, lda, W, ldw, D, ldd, bias, alpha, M, N, K, 1, st);
+  if (bn == 256) return sct::launch<256, false, false, false>(A, lda, W, ldw, D, ldd, bias, nullptr, alpha, M, N, K, 1, st);
+  return sct::launch<128, false, false, false>(A, lda, W, ldw, D, ldd, bias, nullptr, alpha, M, N, K, 1, st);
 }
 
 int32_t sct_gemm_bf16_nn(const void* A, int64_t lda, const void* W, int64_t ldw, void* D, int64_t ldd,
@@ -505,12 +575,18 @@ int32_t sct_gemm_bf16_nn(const void* A, int64_t lda, const void* W, int64_t ldw,
                          void* stream) {
   if (int rc = sct::check_common(A, W, D, M, N, K)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (bn == 256) return sct::launch<256, false, true, false>(A, lda, W, ldw, D, ldd, bias, alpha, M, N, K, 1, st);
-  return sct::launch<128, false, true, false>(A, lda, W, ldw, D, ldd, bias, alpha, M, N, K, 1, st);
+  if (bn == 256) return sct::launch<256, false, true, false>(A, lda, W, ldw, D, ldd, bias, nullptr, alpha, M, N, K, 1, st);
+  return sct::launch<128, false, true, false>(A, lda, W, ldw, D, ldd, bias, nullptr, alpha, M, N, K, 1, st);
 }
 
 int32_t sct_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int64_t ldb, float* D, int64_t ldd,
                          float alpha, int64_t M, int64_t N, int64_t K, int32_t k_splits, void* stream) {
+  return sct_gemm_bf16_tn_colsum(A, lda, B, ldb, D, ldd, nullptr, alpha, M, N, K, k_splits, stream);
+}
+
+int32_t sct_gemm_bf16_tn_colsum(const void* A, int64_t lda, const void* B, int64_t ldb, float* D, int64_t ldd,
+                                float* colsum, float alpha, int64_t M, int64_t N, int64_t K, int32_t k_splits,
+                                void* stream) {
   if (int rc = sct::check_common(A, B, D, M, N, K)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static int tn_bn = -1;  // SCT_GEMM_TN_BN=128 forces the narrow tile (A/B timing)
@@ -519,8 +595,8 @@ int32_t sct_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int64_t ldb,
     tn_bn = e ? atoi(e) : 256;
   }
   if (tn_bn == 256 && N >= 512)
-    return sct::launch<256, true, true, true>(A, lda, B, ldb, D, ldd, nullptr, alpha, M, N, K, k_splits, st);
-  return sct::launch<128, true, true, true>(A, lda, B, ldb, D, ldd, nullptr, alpha, M, N, K, k_splits, st);
+    return sct::launch<256, true, true, true>(A, lda, B, ldb, D, ldd, nullptr, colsum, alpha, M, N, K, k_splits, st);
+  return sct::launch<128, true, true, true>(A, lda, B, ldb, D, ldd, nullptr, colsum, alpha, M, N, K, k_splits, st);
 }
 
 }  // extern "C"

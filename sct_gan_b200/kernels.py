@@ -219,8 +219,8 @@ def gemm_nn(a, w, alpha=1.0, out=None, bn=None):
     return out
 
 
-def gemm_tn(a, b, out, alpha=1.0, k_splits=0):
-    """out[M,N] (fp32) += alpha * a[K,M]^T @ b[K,N]"""
+def gemm_tn(a, b, out, alpha=1.0, k_splits=0, colsum=None):
+    """out[M,N] (fp32) += alpha * a[K,M]^T @ b[K,N]; colsum[M] (fp32, optional) += alpha * a.sum(0)"""
     a, lda = _rows2d(a, BF16, "a")
     b, ldb = _rows2d(b, BF16, "b")
     K, M = a.shape
@@ -229,8 +229,13 @@ def gemm_tn(a, b, out, alpha=1.0, k_splits=0):
     out, ldd = _rows2d(out, F32, "out")
     assert out.shape == (M, N)
     _lib.Stats.annotate(2.0 * M * N * K)
-    _lib.call("sct_gemm_bf16_tn", _ptr(a), lda, _ptr(b), ldb, _ptr(out), ldd, float(alpha), M, N, K,
-              k_splits, _stream())
+    if colsum is None:
+        _lib.call("sct_gemm_bf16_tn", _ptr(a), lda, _ptr(b), ldb, _ptr(out), ldd, float(alpha), M, N, K,
+                  k_splits, _stream())
+    else:
+        assert colsum.dtype == F32 and colsum.is_contiguous() and colsum.numel() >= M
+        _lib.call("sct_gemm_bf16_tn_colsum", _ptr(a), lda, _ptr(b), ldb, _ptr(out), ldd, _sptr(colsum), float(alpha),
+                  M, N, K, k_splits, _stream())
     return out
 
 

@@ -293,12 +293,15 @@ class Linear(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = kn.gemm_nn(dy, w_bf16)
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
+        if want_db:
+            db = torch.zeros(ld, dtype=F32, device=dy.device)
         if ctx.needs_input_grad[1]:
             dw = torch.zeros(ctx.w_shape, dtype=F32, device=dy.device)
-            kn.gemm_tn(dy, x, dw)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = torch.zeros(ld, dtype=F32, device=dy.device)
+            kn.gemm_tn(dy, x, dw, colsum=db)  # bias gradient summed from the dY tiles of the wgrad GEMM
+        elif want_db:
             kn.colsum_bf16(full, db)
+        if want_db:
             db = db[:N]
         return dx, dw, db, None
 
@@ -416,16 +419,7 @@ class VocabCE(torch.autograd.Function):
             row_lse[r0:r1] = rs
             if need_grad:
                 kn.gemm_nn(logits, w_bf16, out=dh[r0:r1])
-                kn.gemm_tn(logits, h[r0:r1], dw)
-                if db is not None:
-                    # colsum needs an 8-aligned width: the pad columns of the scratch are zero
-                    full = scratch[:n]
-                    if ld != V:
-                        dbp = torch.zeros(ld, dtype=F32, device=dev)
-                        kn.colsum_bf16(full, dbp)
-                        db += dbp[:V]
-                    else:
-                        kn.colsum_bf16(full, db)
+                kn.gemm_tn(logits, h[r0:r1], dw, colsum=db)  # + bias gradient from the same tiles
         loss = row_loss.sum() * inv
         if need_grad:
             ctx.save_for_backward(dh, dw, db if db is not None else torch.empty(0))

@@ -82,6 +82,15 @@ def test_gemm_tn(cuda_dev, M, N, K, ks):
     ref = base + 0.5 * (a.float().t() @ b.float())
     # fp32 output: only accumulation-order differences
     assert rel_l2(out, ref) < 1e-4
+    # same call with the fused bias gradient: colsum[m] += alpha * sum_k a[k, m], D unchanged by it
+    out2 = base.clone()
+    cs0 = torch.randn(M, device="cuda", generator=g)
+    cs = cs0.clone()
+    kn.gemm_tn(a, b, out2, alpha=0.5, k_splits=ks, colsum=cs)
+    _no_timeouts()
+    assert rel_l2(out2, ref) < 1e-4
+    cs_ref = cs0 + 0.5 * a.float().sum(0)
+    assert (cs - cs_ref).abs().max().item() < 1e-3 * max(1.0, cs_ref.abs().max().item())
 
 
 # -------------------------------------------------------------------------------------- attention
