@@ -43,6 +43,9 @@ SIGNATURES = {
                              _f, _u64, _u64, _p],
     "sct_attn_bwd": [_p, _i64, _p, _p, _i64, _p, _p, _i64, _p, _p, _p, _i64, _p, _p, _i64, _p, _i64, _i64,
                      _i64, _i64, _i64, _i32, _f, _f, _u64, _u64, _p],
+    "sct_attn_bwd_ws": [_p, _i64, _p, _p, _i64, _p, _p, _i64, _p, _p, _p, _i64, _p, _p, _i64, _p, _i64, _i64,
+                        _i64, _i64, _i64, _i32, _f, _f, _u64, _u64, _p, _i64, _p],
+    "sct_attn_bwd_workspace_bytes": [_i64, _i64, _i64, _i64],
     "sct_ce_rows": [_p, _p, _p, _p, _i64, _i64, _i64, _f, _i32, _p],
     "sct_small_linear_fwd": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p],
     "sct_small_linear_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p],
@@ -53,6 +56,7 @@ SIGNATURES = {
 }
 NOARG = {"sct_opt_chunk_elems": _i32, "sct_version": _i32, "sct_device_check": _i32, "sct_debug_timeouts": _i32, "sct_last_error": C.c_char_p}
 
+RESTYPE = {"sct_attn_bwd_workspace_bytes": _i64}  # everything else returns an int32 status
 _lib = None
 
 
@@ -73,7 +77,7 @@ def load() -> C.CDLL:
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = args
-        fn.restype = _i32
+        fn.restype = RESTYPE.get(name, _i32)
     for name, res in NOARG.items():
         fn = getattr(lib, name)
         fn.argtypes = []
@@ -87,7 +91,7 @@ def last_error() -> str:
 
 
 # kernels launched per C-ABI call (sct_attn_bwd = D-vector + dK/dV + dQ, sct_seq_mean_fwd = memset + reduce, ...)
-KERNELS_PER_CALL = {"sct_clip_adamw_step": 4, "sct_attn_bwd": 3, "sct_small_linear_bwd": 2, "sct_seq_mean_fwd": 2,
+KERNELS_PER_CALL = {"sct_clip_adamw_step": 4, "sct_attn_bwd": 3, "sct_attn_bwd_ws": 3, "sct_small_linear_bwd": 2, "sct_seq_mean_fwd": 2,
                     "sct_set_dropout_epoch_ptr": 0}
 
 
@@ -109,7 +113,7 @@ class Stats:
 
 
 # entry points that run the same kernel are accounted under one name
-STAT_NAME = {"sct_gemm_bf16_tn_colsum": "sct_gemm_bf16_tn"}
+STAT_NAME = {"sct_gemm_bf16_tn_colsum": "sct_gemm_bf16_tn", "sct_attn_bwd_ws": "sct_attn_bwd"}
 
 
 def call(name: str, *args) -> None:

@@ -49,6 +49,7 @@ struct AttnParams {
   uint32_t tmask[16];    // bit i of the 16-bit drop threshold, spread to a full word
   uint32_t thresh16;     // 0 = dropout off
   float inv_keep;
+  int write_ds;          // dK/dV kernel: also store the dS^T tiles to the workspace (for the streaming dQ kernel)
 };
 
 // ---- attention-probability dropout -------------------------------------------------------------
@@ -635,7 +636,7 @@ constexpr int BWD3_KV_SMEM = 1024 + 2 * QKV_BYTES + 4 * QKV_BYTES + 4 * HALF_BYT
 __global__ void __launch_bounds__(BWD3_THREADS, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
-                      const AttnParams p) {
+                      const __grid_constant__ CUtensorMap tmDS, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -733,17 +734,23 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           tc_fence_after();
           const uint32_t qh = sQ + st * QKV_BYTES + hh * 4096, doh = sdO + st * QKV_BYTES + hh * 4096;
           const uint32_t acc = (it > 0 || hh > 0) ? 1u : 0u;
+          if (p.write_ds) {  // dS^T_h [128 keys x 64 queries] -> workspace [b*H + h][key][query] for the dQ kernel
+            tma_store_3d(&tmDS, sDST + hh * HALF_BYTES, (i_begin + it) * TILE + hh * 64, kv0, b * p.H + h);
+            tma_commit_group();
+          }
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             tc_mma_bf16_lh(tmem + 256, lo_k128h(sPT + hh * HALF_BYTES, k), kHi128, lo_mn64(doh, k), kHi64, idesc_g, (acc || k > 0) ? 1u : 0u);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             tc_mma_bf16_lh(tmem + 352, lo_k128h(sDST + hh * HALF_BYTES, k), kHi128, lo_mn64(qh, k), kHi64, idesc_g, (acc || k > 0) ? 1u : 0u);
+          if (p.write_ds) tma_wait_group_read0();  // the store has read dS^T_h before the buffer is handed back
           tc_commit(bar_gd + 8 * hh);
           if (it + 1 < n_it) issue_s(hh, st ^ 1);
         }
         tc_commit(bar_qe + 8 * st);
       }
+      if (p.write_ds) tma_wait_group0();  // workspace writes complete before the grid ends
     }
   } else {
     const int hh = warp >> 2, quad = warp & 3;  // warpgroup hh owns query columns [64 hh, 64 hh + 64) of every tile
@@ -842,6 +849,133 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
+
+// ---- dQ from stored dS^T: one CTA per (q-tile, head, batch), two co-resident per SM ----
+// The dK/dV kernel already computed every dS^T tile (exp, dropout mask, dP - D) and left it in the workspace
+// [B*H][Lk][Lq] (bf16), so dQ = scale * sum_j dS_j K_j is a plain TMA -> tcgen05 stream (no second softmax /
+// dropout recomputation, which is what bounds the recomputing dQ kernel).  A pipeline stage holds 64 keys:
+// dS^T [64 keys x 128 queries] as two swizzle-128 blocks (the MN-major A operand: M = queries contiguous) and
+// K [64 keys x 96] as three swizzle-64 blocks (MN-major B operand).
+constexpr int DQ2_STAGES = 3;
+constexpr int DQ2_A_BYTES = 2 * 64 * 128;   // two [64 keys x 64 queries] blocks
+constexpr int DQ2_B_BYTES = 3 * 64 * 64;    // three [64 keys x 32 d] blocks
+constexpr int DQ2_STAGE_BYTES = DQ2_A_BYTES + DQ2_B_BYTES;
+constexpr int DQ2_SMEM = 1024 + DQ2_STAGES * DQ2_STAGE_BYTES + 256;
+constexpr int DQ2_THREADS = 192;
+
+__global__ void __launch_bounds__(DQ2_THREADS, 2)
+attn_bwd_dq_ds_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant__ CUtensorMap tmK64,
+                      const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t aux = base + DQ2_STAGES * DQ2_STAGE_BYTES;
+  const uint32_t bar_full = aux, bar_empty = aux + 32, bar_done = aux + 64, tmem_ptr_addr = aux + 72;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen + (tmem_ptr_addr - base));
+  int* ext_slot = reinterpret_cast<int*>(gen + (aux + 80 - base));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nq_tiles = gridDim.x;
+  const int qt = nq_tiles - 1 - blockIdx.x;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qt * TILE;
+
+  if (tid == 0) {
+    for (int i = 0; i < DQ2_STAGES; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    mbar_init(bar_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_addr, 128);
+  int nkv = (kv_extent(p, b, ext_slot) + TILE - 1) / TILE;
+  if (p.causal) nkv = min(nkv, qt + 1);
+  const int n_st = 2 * nkv;  // 64-key stages
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < n_st; ++i) {
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        const uint32_t full = bar_full + 8 * s;
+        const uint32_t sA = base + s * DQ2_STAGE_BYTES, sB = sA + DQ2_A_BYTES;
+        mbar_expect_tx(full, DQ2_STAGE_BYTES);
+        tma_load_3d(&tmDS, full, sA, q0, i * 64, b * p.H + h);
+        tma_load_3d(&tmDS, full, sA + 64 * 128, q0 + 64, i * 64, b * p.H + h);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tma_load_3d(&tmK64, full, sB + c * 4096, h * DH + 32 * c, i * 64, b);
+        if (++s == DQ2_STAGES) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_st > 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, DH, true, true);
+      constexpr uint32_t kHiB = umma_desc_hi(512, UMMA_SW64);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < n_st; ++i) {
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t sA = base + s * DQ2_STAGE_BYTES, sB = sA + DQ2_A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // 16 keys per step: 2048 B of A rows, 1024 B of B rows
+          tc_mma_bf16_lh(tmem, umma_desc_lo(sA + k * 2048, 64 * 128), kHi128, umma_desc_lo(sB + k * 1024, 4096), kHiB,
+                         idesc, (i > 0 || k > 0) ? 1u : 0u);
+        tc_commit(bar_empty + 8 * s);
+        if (++s == DQ2_STAGES) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+      tc_commit(bar_done);
+    }
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const int q = q0 + r;
+    const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+    if (n_st > 0) {
+      mbar_wait(bar_done, 0);
+      tc_fence_after();
+    }
+    __nv_bfloat16* dst = p.dq + ((long long)b * p.Lq + q) * p.ldq_out + h * DH;
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+      uint32_t rr[32];
+      if (n_st > 0) {
+        tmem_ld32(tmem + lane_sel + c * 32, rr);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rr[i] = 0u;
+      }
+      if (q < p.Lq) {
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(rr[8 * qd]) * p.scale, __uint_as_float(rr[8 * qd + 1]) * p.scale);
+          u.y = pack_bf16(__uint_as_float(rr[8 * qd + 2]) * p.scale, __uint_as_float(rr[8 * qd + 3]) * p.scale);
+          u.z = pack_bf16(__uint_as_float(rr[8 * qd + 4]) * p.scale, __uint_as_float(rr[8 * qd + 5]) * p.scale);
+          u.w = pack_bf16(__uint_as_float(rr[8 * qd + 6]) * p.scale, __uint_as_float(rr[8 * qd + 7]) * p.scale);
+          *reinterpret_cast<uint4*>(dst + c * 32 + qd * 8) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 128);
+}
+
 // -----------------------------------------------------------------------------------------------
 int make_qkv_map(CUtensorMap* m, const void* ptr, int64_t ld, int64_t B, int64_t L, int64_t H,
                  int64_t batch_stride = 0) {
@@ -876,6 +1010,7 @@ int fill_params(AttnParams& p, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int
   for (int i = 0; i < 16; ++i) p.tmask[i] = ((p.thresh16 >> i) & 1u) ? 0xFFFFFFFFu : 0u;
   // the scale uses the realised keep probability (thresh16 / 65536 is p_drop to within 2^-17)
   p.inv_keep = p_drop > 0.f ? (float)(65536.0 / (65536.0 - (double)p.thresh16)) : 1.0f;
+  p.write_ds = 0;
   p.lse2 = nullptr; p.dvec = nullptr; p.o = nullptr; p.dq = p.dk = p.dv = nullptr;
   p.ldo = p.ldq_out = p.ldkv_out = 0;
   return 0;
@@ -943,7 +1078,26 @@ int32_t sct_attn_bwd(const void* q, int64_t ldq, const void* k, const void* v, i
                      void* dq, int64_t lddq, void* dk, void* dv, int64_t lddkv, const uint8_t* kpm,
                      int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t head_dim, int32_t causal,
                      float scale, float p_drop, uint64_t seed, uint64_t offset, void* stream) {
+  return sct_attn_bwd_ws(q, ldq, k, v, ldkv, o, d_o, ldo, lse2, dvec, dq, lddq, dk, dv, lddkv, kpm, B, H, Lq, Lk,
+                         head_dim, causal, scale, p_drop, seed, offset, nullptr, 0, stream);
+}
+
+int64_t sct_attn_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Lq, int64_t Lk) {
+  const int64_t pitch = (Lq + 63) / 64 * 64;
+  return B * H * Lk * pitch * 2;
+}
+
+int32_t sct_attn_bwd_ws(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                        const void* o, const void* d_o, int64_t ldo, const float* lse2, float* dvec,
+                        void* dq, int64_t lddq, void* dk, void* dv, int64_t lddkv, const uint8_t* kpm,
+                        int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t head_dim, int32_t causal,
+                        float scale, float p_drop, uint64_t seed, uint64_t offset, void* workspace,
+                        int64_t workspace_bytes, void* stream) {
   SCT_CHECK(q && k && v && o && d_o && lse2 && dvec && dq && dk && dv, "null pointer");
+  const bool use_ws = workspace != nullptr;
+  SCT_CHECK(!use_ws || workspace_bytes >= sct_attn_bwd_workspace_bytes(B, H, Lq, Lk),
+            "attention backward workspace too small (%lld < %lld bytes)", (long long)workspace_bytes,
+            (long long)sct_attn_bwd_workspace_bytes(B, H, Lq, Lk));
   SCT_CHECK(head_dim == DH, "head_dim %lld unsupported (kernel is specialised for 96)", (long long)head_dim);
   SCT_CHECK(H * DH == 768 || H * DH <= ldo, "unexpected head layout");
   SCT_CHECK(lddq % 8 == 0 && lddkv % 8 == 0 && ldo % 8 == 0, "gradient pitches must be multiples of 8");
@@ -961,25 +1115,44 @@ int32_t sct_attn_bwd(const void* q, int64_t ldq, const void* k, const void* v, i
                                                          dvec, rows, (int)Lq, (int)H, (int)ldo);
     SCT_LAUNCH_CHECK();
   }
-  CUtensorMap tq, tk, tv, tdo;
+  CUtensorMap tq, tk, tv, tdo, tds_st, tds_ld, tk64;
   if (int rc = make_qkv_map(&tq, q, ldq, B, Lq, H)) return rc;
   if (int rc = make_qkv_map(&tk, k, ldkv, B, Lk, H)) return rc;
   if (int rc = make_qkv_map(&tv, v, ldkv, B, Lk, H)) return rc;
   if (int rc = make_qkv_map(&tdo, d_o, ldo, B, Lq, H)) return rc;
+  tds_st = tq;  // placeholder when the workspace is not used (never dereferenced)
+  if (use_ws) {
+    // workspace = dS^T [B*H][Lk][pitch >= Lq] bf16; stored as [128 keys x 64 queries] blocks, re-read 64 keys at a time
+    const uint64_t pitch = (uint64_t)((Lq + 63) / 64 * 64);
+    if (int rc = make_tmap_3d(&tds_st, workspace, 2, (uint64_t)Lq, (uint64_t)Lk, (uint64_t)(B * H), pitch * 2,
+                              (uint64_t)Lk * pitch * 2, 64, TILE, SWZ_128))
+      return rc;
+    if (int rc = make_tmap_3d(&tds_ld, workspace, 2, (uint64_t)Lq, (uint64_t)Lk, (uint64_t)(B * H), pitch * 2,
+                              (uint64_t)Lk * pitch * 2, 64, 64, SWZ_128))
+      return rc;
+    if (int rc = make_tmap_3d(&tk64, k, 2, (uint64_t)(H * DH), (uint64_t)Lk, (uint64_t)B, (uint64_t)ldkv * 2,
+                              (uint64_t)Lk * ldkv * 2, 32, 64, SWZ_64))
+      return rc;
+    p.write_ds = 1;
+  }
   static bool attr = false;
   if (!attr) {
     SCT_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD3_KV_SMEM));
     SCT_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD3_Q_SMEM));
+    SCT_CUDA(cudaFuncSetAttribute(attn_bwd_dq_ds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ2_SMEM));
     attr = true;
   }
   {
     dim3 grid((unsigned)((Lk + TILE - 1) / TILE), (unsigned)H, (unsigned)B);
-    attn_bwd_dkdv_kernel<<<grid, BWD3_THREADS, BWD3_KV_SMEM, st>>>(tq, tk, tv, tdo, p);
+    attn_bwd_dkdv_kernel<<<grid, BWD3_THREADS, BWD3_KV_SMEM, st>>>(tq, tk, tv, tdo, tds_st, p);
     SCT_LAUNCH_CHECK();
   }
   {
     dim3 grid((unsigned)((Lq + TILE - 1) / TILE), (unsigned)H, (unsigned)B);
-    attn_bwd_dq_kernel<<<grid, BWD3_THREADS, BWD3_Q_SMEM, st>>>(tq, tk, tv, tdo, p);
+    if (use_ws)
+      attn_bwd_dq_ds_kernel<<<grid, DQ2_THREADS, DQ2_SMEM, st>>>(tds_ld, tk64, p);
+    else
+      attn_bwd_dq_kernel<<<grid, BWD3_THREADS, BWD3_Q_SMEM, st>>>(tq, tk, tv, tdo, p);
     SCT_LAUNCH_CHECK();
   }
   return 0;

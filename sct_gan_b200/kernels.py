@@ -6,6 +6,8 @@ The autograd layer (ops.py) and the tests call these.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -277,11 +279,31 @@ def attn_bwd(q, k, v, o, d_o, lse2, B, H, Lq, Lk, dq, dk, dv, kpm=None, causal=F
     if scale is None:
         scale = head_dim ** -0.5
     dvec = torch.empty((B, H, Lq), dtype=F32, device=q.device)
+    ws, ws_bytes = _attn_workspace(B, H, Lq, Lk, q.device)
     _lib.Stats.annotate(10.0 * B * H * Lq * Lk * head_dim * (0.5 if causal else 1.0))
-    _lib.call("sct_attn_bwd", _ptr(q), ldq, _ptr(k), _ptr(v), ldk, _ptr(o), _ptr(d_o), o.stride(0),
+    _lib.call("sct_attn_bwd_ws", _ptr(q), ldq, _ptr(k), _ptr(v), ldk, _ptr(o), _ptr(d_o), o.stride(0),
               _ptr(lse2), _ptr(dvec), _ptr(dq), lddq, _ptr(dk), _ptr(dv), lddk,
               kpm.data_ptr() if kpm is not None else None, B, H, Lq, Lk, head_dim, int(causal),
-              float(scale), float(p_drop), seed, offset, _stream())
+              float(scale), float(p_drop), seed, offset, ws.data_ptr() if ws is not None else None, ws_bytes,
+              _stream())
+
+
+# dS^T workspace of the attention backward: one grow-only buffer per device (the calls of a step run back to back on
+# one stream).  Outgrown buffers are kept alive because captured CUDA graphs may still point at them.
+_ATTN_WS = {}
+_ATTN_WS_LIMIT = int(os.environ.get("SCT_ATTN_BWD_WS_MB", "16384")) << 20  # 0 disables (recomputing dQ kernel)
+
+
+def _attn_workspace(B, H, Lq, Lk, device):
+    need = int(_lib.load().sct_attn_bwd_workspace_bytes(B, H, Lq, Lk))
+    if need > _ATTN_WS_LIMIT:
+        return None, 0
+    ent = _ATTN_WS.setdefault(device, [])
+    if not ent or ent[-1].numel() < need:
+        assert not torch.cuda.is_current_stream_capturing(), \
+            "attention workspace must be sized by an eager step before CUDA-graph capture"
+        ent.append(torch.empty(need, dtype=torch.uint8, device=device))
+    return ent[-1], ent[-1].numel()
 
 
 # --------------------------------------------------------------------------------------------- K4b

@@ -111,8 +111,12 @@ def _attn_ref(q, k, v, kpm, causal, scale):
     (3, 512, 128, False, True), (2, 200, 77, False, True), (1, 1024, 1024, True, False),
     (2, 384, 384, True, False), (2, 130, 130, True, False),
 ])
-def test_attention_fwd_bwd(cuda_dev, B, Lq, Lk, causal, masked):
+@pytest.mark.parametrize("workspace", [True, False])  # streaming dQ from stored dS^T vs the recomputing dQ kernel
+def test_attention_fwd_bwd(cuda_dev, B, Lq, Lk, causal, masked, workspace, monkeypatch):
     from sct_gan_b200 import kernels as kn
+
+    if not workspace:
+        monkeypatch.setattr(kn, "_ATTN_WS_LIMIT", 0)
 
     H, dh = 8, 96
     d = H * dh
