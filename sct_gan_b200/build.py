@@ -27,6 +27,9 @@ NVCC_FLAGS = [
 ]
 
 
+NVCC_FLAGS += os.environ.get("SCT_NVCC_EXTRA", "").split()  # e.g. -DSCT_ATTN_TRACE for instrumented builds
+
+
 def _nvcc() -> str:
     cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(cand):

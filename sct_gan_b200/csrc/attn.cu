@@ -137,7 +137,14 @@ __device__ __forceinline__ uint32_t lo_mn64(uint32_t tile, int k) { return umma_
 __device__ __forceinline__ uint32_t lo_k128(uint32_t tile, int k) {
   return umma_desc_lo(tile + (k >> 2) * (TILE * 128) + (k & 3) * 32, 16);
 }
-// MN-major descriptor of the same [128(k) x 128(mn)] tile (used for dQ-style products if ever needed).
+// The MMA-issuing thread is a serial chain of dependent integer instructions between tcgen05.mma's (measured: ~18
+// SASS instructions and ~90 clk per MMA when every descriptor is rebuilt with shift / mask / or, against 54 clk for the
+// bare instruction, tools/micro/mma_issue.cu), so the loops below build each tile's low word ONCE and step through
+// it with immediate adds (byte offset >> 4; operand tiles never cross the 14-bit address field).
+__device__ __forceinline__ uint32_t base_k64(uint32_t tile) { return umma_desc_lo(tile, 16); }
+__device__ __forceinline__ uint32_t base_mn64(uint32_t tile) { return umma_desc_lo(tile, BLK); }
+__device__ __forceinline__ uint32_t step_k64(uint32_t base, int k) { return base + (((k >> 1) * BLK + (k & 1) * 32) >> 4); }
+__device__ __forceinline__ uint32_t step_mn64(uint32_t base, int k) { return base + ((k * 1024) >> 4); }
 
 // write 32 consecutive bf16 (columns c0..c0+31, c0 % 32 == 0) of row r into a swizzle-128 [128x128] tile
 __device__ __forceinline__ void store_row32_sw128(uint32_t tile, int r, int c0, const float (&v)[32]) {
@@ -145,6 +152,20 @@ __device__ __forceinline__ void store_row32_sw128(uint32_t tile, int r, int c0, 
   const int chunk0 = (c0 & 63) >> 3;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
+    const uint32_t dst = rowbase + ((((chunk0 + q) ^ (r & 7)) & 7) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
+                 "r"(pack_bf16(v[8 * q], v[8 * q + 1])), "r"(pack_bf16(v[8 * q + 2], v[8 * q + 3])),
+                 "r"(pack_bf16(v[8 * q + 4], v[8 * q + 5])), "r"(pack_bf16(v[8 * q + 6], v[8 * q + 7]))
+                 : "memory");
+  }
+}
+
+// write 16 consecutive bf16 (columns c0..c0+15, c0 % 16 == 0) of row r into a [128 x 64] swizzle-128 block
+__device__ __forceinline__ void store_row16_sw128(uint32_t blk, int r, int c0, const float (&v)[16]) {
+  const uint32_t rowbase = blk + r * 128;
+  const int chunk0 = c0 >> 3;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
     const uint32_t dst = rowbase + ((((chunk0 + q) ^ (r & 7)) & 7) << 4);
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
                  "r"(pack_bf16(v[8 * q], v[8 * q + 1])), "r"(pack_bf16(v[8 * q + 2], v[8 * q + 3])),
@@ -448,7 +469,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   int* ext_slot = reinterpret_cast<int*>(gen + (aux + 272 - base));
   const uint32_t bar0 = aux + 512;
   const uint32_t bar_q = bar0, bar_kvf = bar0 + 8, bar_kve = bar0 + 24, bar_mkf = bar0 + 40, bar_sf = bar0 + 56,
-                 bar_pf = bar0 + 72, bar_dsd = bar0 + 88;
+                 bar_pf = bar0 + 72, bar_dsd = bar0 + 88, bar_fin = bar0 + 104;
   const uint32_t tmem_ptr_addr = bar0 + 112;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen + (tmem_ptr_addr - base));
 
@@ -460,6 +481,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (tid == 0) {
     mbar_init(bar_q, 1);
+    mbar_init(bar_fin, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_kvf + 8 * i, 1);
       mbar_init(bar_kve + 8 * i, 1);
@@ -543,6 +565,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         tc_commit(bar_kve + 8 * st);
       }
+      tc_commit(bar_fin);  // every dQ MMA has retired (a parity wait on the other half's barrier could pass early)
     }
   } else {
     const int hh = warp >> 2, quad = warp & 3;  // warpgroup hh owns key columns [64 hh, 64 hh + 64) of every tile
@@ -594,7 +617,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     // epilogue: dQ * scale -> bf16; warpgroup 0 stores columns [0,64), warpgroup 1 columns [64,96)
     if (nkv > 0) {
-      mbar_wait(bar_dsd + 8, (nkv - 1) & 1);  // the last gradient GEMM (half 1 of the last key tile)
+      mbar_wait(bar_fin, 0);  // the last gradient GEMM
       tc_fence_after();
     }
     {
@@ -651,7 +674,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   int* ext_slot = reinterpret_cast<int*>(gen + (aux + 2048 - base));
   const uint32_t bar0 = aux + 2560;
   const uint32_t bar_kv = bar0, bar_qf = bar0 + 8, bar_qe = bar0 + 24, bar_stf = bar0 + 40, bar_sf = bar0 + 56,
-                 bar_pf = bar0 + 72, bar_gd = bar0 + 88;
+                 bar_pf = bar0 + 72, bar_gd = bar0 + 88, bar_fin = bar0 + 104;
   const uint32_t tmem_ptr_addr = bar0 + 112;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen + (tmem_ptr_addr - base));
 
@@ -663,6 +686,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   if (tid == 0) {
     mbar_init(bar_kv, 1);
+    mbar_init(bar_fin, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_qf + 8 * i, 1);
       mbar_init(bar_qe + 8 * i, 1);
@@ -679,7 +703,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_gen;
-  // TMEM columns: S^T_h at 64h, dP^T_h at 128 + 64h, dV at 256, dK at 352
+  // TMEM columns: S^T_h at 64h, dP^T_h at 128 + 64h, dV at 256, dK at 352, P^T_h (packed bf16) at 448 + 32h
   if (warp == 9) {
     if (lane == 0 && n_it > 0) {
       mbar_expect_tx(bar_kv, 2 * QKV_BYTES);
@@ -709,14 +733,26 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (lane == 0 && n_it > 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);
       constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, false, true);
+      const uint32_t bK = base_k64(sK), bV = base_k64(sV);
+      const uint32_t bQk = base_k64(sQ), bdOk = base_k64(sdO);     // K-major views (S^T, dP^T: B operand)
+      const uint32_t bQm = base_mn64(sQ), bdOm = base_mn64(sdO);   // MN-major views (dK, dV: B operand)
       auto issue_s = [&](int hh, int st) {
-        const uint32_t qh = sQ + st * QKV_BYTES + hh * 4096, doh = sdO + st * QKV_BYTES + hh * 4096;
+        const uint32_t off = (uint32_t)(st * QKV_BYTES + hh * 4096) >> 4;
+        const uint32_t qh = bQk + off, doh = bdOk + off;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) tc_mma_bf16_lh(tmem + 64 * hh, lo_k64(sK, k), kHi64, lo_k64(qh, k), kHi64, idesc_s, k > 0);
+        for (int k = 0; k < 6; ++k) tc_mma_bf16_lh(tmem + 64 * hh, step_k64(bK, k), kHi64, step_k64(qh, k), kHi64, idesc_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) tc_mma_bf16_lh(tmem + 128 + 64 * hh, lo_k64(sV, k), kHi64, lo_k64(doh, k), kHi64, idesc_s, k > 0);
+        for (int k = 0; k < 6; ++k) tc_mma_bf16_lh(tmem + 128 + 64 * hh, step_k64(bV, k), kHi64, step_k64(doh, k), kHi64, idesc_s, k > 0);
         tc_commit(bar_sf + 8 * hh);
       };
+#ifdef SCT_ATTN_TRACE
+      long long tr_t0 = clock64(), tr_qf = 0, tr_pf = 0, tr_g = 0, tr_sw = 0, tr_s = 0, tr_x;
+#define TR_BEGIN() tr_x = clock64()
+#define TR_END(acc) acc += clock64() - tr_x
+#else
+#define TR_BEGIN()
+#define TR_END(acc)
+#endif
       mbar_wait(bar_kv, 0);
       mbar_wait(bar_qf, 0);
       tc_fence_after();
@@ -724,49 +760,85 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       issue_s(1, 0);
       for (int it = 0; it < n_it; ++it) {
         const int st = it & 1;
-        if (it + 1 < n_it) {
-          mbar_wait(bar_qf + 8 * (st ^ 1), ((it + 1) >> 1) & 1);
-          tc_fence_after();
-        }
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
+          TR_BEGIN();
           mbar_wait(bar_pf + 8 * hh, it & 1);
+          TR_END(tr_pf);
           tc_fence_after();
-          const uint32_t qh = sQ + st * QKV_BYTES + hh * 4096, doh = sdO + st * QKV_BYTES + hh * 4096;
+          TR_BEGIN();
+          const uint32_t off = (uint32_t)(st * QKV_BYTES + hh * 4096) >> 4;
+          const uint32_t qh = bQm + off, doh = bdOm + off;
           const uint32_t acc = (it > 0 || hh > 0) ? 1u : 0u;
           if (p.write_ds) {  // dS^T_h [128 keys x 64 queries] -> workspace [b*H + h][key][query] for the dQ kernel
             tma_store_3d(&tmDS, sDST + hh * HALF_BYTES, (i_begin + it) * TILE + hh * 64, kv0, b * p.H + h);
             tma_commit_group();
           }
+          // dV += P^T_h dO_h and dK += dS^T_h Q_h with the A operands read from TMEM (packed bf16: P^T_h in 32 columns
+          // at 448 + 32 hh, dS^T_h over the first 32 columns of the consumed dP^T_h buffer): no shared-memory reads
+          // for A (tools/micro/mma_issue.cu: 48 instead of >= 56 clk per MMA, and less contention with the ALU warps)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            tc_mma_bf16_lh(tmem + 256, lo_k128h(sPT + hh * HALF_BYTES, k), kHi128, lo_mn64(doh, k), kHi64, idesc_g, (acc || k > 0) ? 1u : 0u);
+            tc_mma_bf16_ts(tmem + 256, tmem + 448 + 32 * hh + 8 * k, step_mn64(doh, k), kHi64, idesc_g, (acc || k > 0) ? 1u : 0u);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            tc_mma_bf16_lh(tmem + 352, lo_k128h(sDST + hh * HALF_BYTES, k), kHi128, lo_mn64(qh, k), kHi64, idesc_g, (acc || k > 0) ? 1u : 0u);
-          if (p.write_ds) tma_wait_group_read0();  // the store has read dS^T_h before the buffer is handed back
+            tc_mma_bf16_ts(tmem + 352, tmem + 128 + 64 * hh + 8 * k, step_mn64(qh, k), kHi64, idesc_g, (acc || k > 0) ? 1u : 0u);
+          TR_END(tr_g);
+          // every MMA that reads Q / dO stage `st` has been issued: hand the stage back to the TMA warp now, so the
+          // tiles of iteration it + 2 have a whole iteration to land
+          if (hh == 1) tc_commit(bar_qe + 8 * st);
+          if (it + 1 < n_it) {
+            if (hh == 0) {
+              TR_BEGIN();
+              mbar_wait(bar_qf + 8 * (st ^ 1), ((it + 1) >> 1) & 1);
+              TR_END(tr_qf);
+              tc_fence_after();
+            }
+            TR_BEGIN();
+            issue_s(hh, st ^ 1);
+            TR_END(tr_s);
+          }
+          // P^T_h / dS^T_h go back to warpgroup hh once the gradient MMAs have retired and the workspace store has
+          // read dS^T_h; the warpgroup waits for S^T_h (just issued) first, so this later commit costs it nothing
+          TR_BEGIN();
+          if (p.write_ds) tma_wait_group_read0();
+          TR_END(tr_sw);
           tc_commit(bar_gd + 8 * hh);
-          if (it + 1 < n_it) issue_s(hh, st ^ 1);
         }
-        tc_commit(bar_qe + 8 * st);
       }
+      tc_commit(bar_fin);  // every gradient MMA has retired: dV / dK may be drained (both warpgroups wait on this one;
+                           // a parity wait on the other half's `gd` barrier can pass a phase too early)
       if (p.write_ds) tma_wait_group0();  // workspace writes complete before the grid ends
+#ifdef SCT_ATTN_TRACE
+      if (blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0)
+        printf("dkdv MMA thread: total %lld  wait_qf %lld  wait_pf %lld  issue_grad %lld  store_wait %lld  issue_s %lld  (n_it %d)\n",
+               clock64() - tr_t0, tr_qf, tr_pf, tr_g, tr_sw, tr_s, n_it);
+#endif
     }
   } else {
     const int hh = warp >> 2, quad = warp & 3;  // warpgroup hh owns query columns [64 hh, 64 hh + 64) of every tile
     const int r = quad * 32 + lane;  // local key row
     const int kv = kv0 + r;
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t tST = tmem + 64 * hh, tDPT = tmem + 128 + 64 * hh;
-    const uint32_t sPTh = sPT + hh * HALF_BYTES, sDSTh = sDST + hh * HALF_BYTES;
+    const uint32_t tST = tmem + 64 * hh, tDPT = tmem + 128 + 64 * hh, tPT = tmem + 448 + 32 * hh;
+    const uint32_t sDSTh = sDST + hh * HALF_BYTES;
     bool row_valid = kv < p.Lk;
     if (row_valid && p.kpm) row_valid = p.kpm[(long long)b * p.Lk + kv] == 0;
     const uint32_t bh = (uint32_t)(b * p.H + h);
     const DropKey dkey = drop_key(p);
+#ifdef SCT_ATTN_TRACE
+    long long ta_t0 = clock64(), ta_rng = 0, ta_sf = 0, ta_gd = 0, ta_alu = 0, ta_x;
+#define TA_BEGIN() ta_x = clock64()
+#define TA_END(acc) acc += clock64() - ta_x
+#else
+#define TA_BEGIN()
+#define TA_END(acc)
+#endif
     for (int it = 0; it < n_it; ++it) {
       const int st = it & 1;
       const int qi = i_begin + it;
       const int q0 = qi * TILE + hh * 64;  // first query of this half
+      TA_BEGIN();
       // keep bits of (q = q0 + c0 + i, k = this thread's key row): lane L makes the word of query q0 + c0 + L over the
       // warp's 32 keys, then the warp transposes the 32x32 bit tile (index-only work, done before the waits)
       uint32_t kw0 = keep_word(p, dkey, bh, (uint32_t)(q0 + lane), (uint32_t)((kv0 >> 5) + quad));
@@ -775,44 +847,75 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         kw0 = warp_bit_transpose(kw0, lane);
         kw1 = warp_bit_transpose(kw1, lane);
       }
+      TA_END(ta_rng);
+      TA_BEGIN();
       mbar_wait(bar_stf + 8 * st, (it >> 1) & 1);
       mbar_wait(bar_sf + 8 * hh, it & 1);
+      TA_END(ta_sf);
       tc_fence_after();
       const bool diag = p.causal && (qi == jt);
+      TA_BEGIN();
       if (it > 0) mbar_wait(bar_gd + 8 * hh, (it - 1) & 1);  // P^T_h / dS^T_h buffers free again
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c0 = cc * 32;
-        const uint32_t kw = cc == 0 ? kw0 : kw1;
-        uint32_t rs[32], rp[32];
-        tmem_ld32(tST + lane_sel + c0, rs);
-        tmem_ld32(tDPT + lane_sel + c0, rp);
+      TA_END(ta_gd);
+      TA_BEGIN();
+      // four 16-query chunks; the TMEM loads of chunk cc + 1 are in flight while chunk cc is in the ALUs
+      uint32_t rs[2][16], rp[2][16];
+      tmem_ld16(tST + lane_sel, rs[0]);
+      tmem_ld16(tDPT + lane_sel, rp[0]);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c0 = cc * 16;
+        const uint32_t kw = (cc < 2 ? kw0 : kw1) >> ((cc & 1) * 16);
         tmem_ld_wait();
-        float pd[32], ds[32];
+        if (cc + 1 < 4) {
+          tmem_ld16(tST + lane_sel + c0 + 16, rs[(cc + 1) & 1]);
+          tmem_ld16(tDPT + lane_sel + c0 + 16, rp[(cc + 1) & 1]);
+        }
+        const uint32_t (&s_)[16] = rs[cc & 1];
+        const uint32_t (&p_)[16] = rp[cc & 1];
+        float pd[16], ds[16];
         if (row_valid) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
+          for (int i = 0; i < 16; ++i) {
             const int c = hh * 64 + c0 + i;  // query column inside the 128-query tile
-            float pr = exp2f(fmaf(__uint_as_float(rs[i]), p.scale_log2, -lse_s[st * 128 + c]));
+            float pr = exp2f(fmaf(__uint_as_float(s_[i]), p.scale_log2, -lse_s[st * 128 + c]));
             if (diag && r > c) pr = 0.f;
             const float dm = (kw & (1u << i)) ? p.inv_keep : 0.f;
             pd[i] = pr * dm;
-            ds[i] = pr * fmaf(__uint_as_float(rp[i]), dm, -dv_s[st * 128 + c]);
+            ds[i] = pr * fmaf(__uint_as_float(p_[i]), dm, -dv_s[st * 128 + c]);
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) pd[i] = ds[i] = 0.f;
+          for (int i = 0; i < 16; ++i) pd[i] = ds[i] = 0.f;
         }
-        store_row32_sw128(sPTh, r, c0, pd);
-        store_row32_sw128(sDSTh, r, c0, ds);
+        {  // P^T chunk -> TMEM (8 packed columns per 16 queries): the A operand of the dV MMA, no shared-memory trip
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(pd[2 * i], pd[2 * i + 1]);
+          tmem_st8(tPT + lane_sel + cc * 8, pk);
+        }
+        {  // dS^T chunk -> TMEM over dP^T columns this thread has consumed (A operand of the dK MMA) ...
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(ds[2 * i], ds[2 * i + 1]);
+          tmem_st8(tDPT + lane_sel + cc * 8, pk);
+        }
+        if (p.write_ds) store_row16_sw128(sDSTh, r, c0, ds);  // ... and -> shared memory for the workspace store
       }
+      tmem_st_wait();
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_pf + 8 * hh);
+      TA_END(ta_alu);
     }
+#ifdef SCT_ATTN_TRACE
+    if (blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (warp == 0 || warp == 4))
+      printf("dkdv warp %d: loop total %lld  rng %lld  wait_sf %lld  wait_gd %lld  alu %lld\n", warp, clock64() - ta_t0, ta_rng,
+             ta_sf, ta_gd, ta_alu);
+#endif
     if (n_it > 0) {
-      mbar_wait(bar_gd + 8, (n_it - 1) & 1);
+      mbar_wait(bar_fin, 0);
       tc_fence_after();
     }
     {
