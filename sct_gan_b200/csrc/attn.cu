@@ -29,7 +29,6 @@ constexpr int DH = 96;            // head dim
 constexpr int TILE = 128;         // q-tile and kv-tile rows
 constexpr int BLK = TILE * 64;    // bytes of one [128 x 32 bf16] swizzle-64 column block
 constexpr int QKV_BYTES = 3 * BLK;          // one [128 x 96] operand tile
-constexpr int P_BYTES = 2 * TILE * 128;     // one [128 x 128] bf16 tile as 2 swizzle-128 blocks
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct AttnParams {
@@ -133,10 +132,6 @@ __device__ __forceinline__ uint32_t lo_k64(uint32_t tile, int k) {
 // MN-major view of the same tile (rows = contraction index), k16 step k (0..7): N = 96 spans the three column
 // blocks (LBO = BLK), 8-row groups are 512 B apart (SBO), 16 rows per step = 1024 B.
 __device__ __forceinline__ uint32_t lo_mn64(uint32_t tile, int k) { return umma_desc_lo(tile + k * 1024, BLK); }
-// K-major [128 x 128] bf16 swizzle-128 tile (P / dS), k16 step k (0..7)
-__device__ __forceinline__ uint32_t lo_k128(uint32_t tile, int k) {
-  return umma_desc_lo(tile + (k >> 2) * (TILE * 128) + (k & 3) * 32, 16);
-}
 // The MMA-issuing thread is a serial chain of dependent integer instructions between tcgen05.mma's (measured: ~18
 // SASS instructions and ~90 clk per MMA when every descriptor is rebuilt with shift / mask / or, against 54 clk for the
 // bare instruction, tools/micro/mma_issue.cu), so the loops below build each tile's low word ONCE and step through
@@ -188,7 +183,7 @@ __device__ __forceinline__ void load_tile(const CUtensorMap* m, uint32_t bar, ui
 // probabilities then stay below 2^8, harmless in fp32/bf16), so the O accumulator in TMEM is almost
 // never rescaled after the first tile.  Key tiles past the last unmasked key are skipped.
 // =================================================================================================
-constexpr int FWD_SMEM = 1024 + 3 * QKV_BYTES + P_BYTES + 4096;
+constexpr int FWD_SMEM = 1024 + 3 * QKV_BYTES + 4096;
 
 __global__ void __launch_bounds__(256, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -196,8 +191,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sQ = base, sK = sQ + QKV_BYTES, sV = sK + QKV_BYTES, sP = sV + QKV_BYTES;
-  const uint32_t aux = sP + P_BYTES;
+  const uint32_t sQ = base, sK = sQ + QKV_BYTES, sV = sK + QKV_BYTES;
+  const uint32_t aux = sV + QKV_BYTES;
   float* bias_s = reinterpret_cast<float*>(gen + (aux - base));  // [128]
   float* mx_s = bias_s + 128;                                     // [2][128]
   float* l_s = mx_s + 256;                                        // [2][128]
@@ -233,6 +228,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
   constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, false, true);
+  const uint32_t bQ = base_k64(sQ), bK = base_k64(sK), bVm = base_mn64(sV);  // descriptor low words, built once
 
   if (tid == 0 && nkv > 0) {
     mbar_expect_tx(bar_q, QKV_BYTES);
@@ -245,7 +241,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(bar_k, 0);
     tc_fence_after();
 #pragma unroll
-    for (int k = 0; k < 6; ++k) tc_mma_bf16_lh(tS, lo_k64(sQ, k), kHi64, lo_k64(sK, k), kHi64, idesc_s, k > 0);
+    for (int k = 0; k < 6; ++k) tc_mma_bf16_lh(tS, step_k64(bQ, k), kHi64, step_k64(bK, k), kHi64, idesc_s, k > 0);
     tc_commit(bar_mma);
   }
 
@@ -319,7 +315,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         rs += e;
         pv[i] = (kw & (1u << i)) ? e : 0.f;
       }
-      store_row32_sw128(sP, r, c_base + kb * 32, pv);
+      // P (bf16, dropped) goes straight back to TMEM as the A operand of the P V product: packed two keys per
+      // column over S columns [0, 64), which every thread has read by now (the max exchange above is a block-wide
+      // barrier after the S loads) — no shared-memory round trip for P
+#pragma unroll
+      for (int g8 = 0; g8 < 2; ++g8) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(pv[16 * g8 + 2 * i], pv[16 * g8 + 2 * i + 1]);
+        tmem_st8(tS + lane_sel + hf * 32 + kb * 16 + g8 * 8, pk);
+      }
     }
     l_run = l_run * alpha + rs;
     m_run = m_next;
@@ -334,9 +339,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int i = 0; i < 32; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) * alpha);
         tmem_st32(tO + lane_sel + c * 32, rr);
       }
-      tmem_st_wait();
     }
-    fence_proxy_async_smem();
+    tmem_st_wait();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
@@ -345,12 +349,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < 8; ++k)
-        tc_mma_bf16_lh(tO, lo_k128(sP, k), kHi128, lo_mn64(sV, k), kHi64, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-      if (j + 1 < nkv) {
+        tc_mma_bf16_ts(tO, tS + 8 * k, step_mn64(bVm, k), kHi64, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+      if (j + 1 < nkv) {  // the next S overwrites P: issued after (and executed in order behind) the P V MMAs
         mbar_wait(bar_k, (j + 1) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 6; ++k) tc_mma_bf16_lh(tS, lo_k64(sQ, k), kHi64, lo_k64(sK, k), kHi64, idesc_s, k > 0);
+        for (int k = 0; k < 6; ++k) tc_mma_bf16_lh(tS, step_k64(bQ, k), kHi64, step_k64(bK, k), kHi64, idesc_s, k > 0);
       }
       tc_commit(bar_mma);
     }
