@@ -660,7 +660,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 //   -> dV += P^T_h dO_h, dK += dS^T_h Q_h
 constexpr int BWD3_KV_SMEM = 1024 + 2 * QKV_BYTES + 4 * QKV_BYTES + 4 * HALF_BYTES + 4096;
 
-__global__ void __launch_bounds__(BWD3_THREADS, 1)
+// Warps: 0-7 arithmetic (two warpgroups, one per 64-query half), 8 = S^T / dP^T MMA issuer, 9 = TMA producer,
+// 10 = dV / dK MMA issuer.  TWO issuing threads on different schedulers: a single thread needs >= 54 clk per
+// tcgen05.mma (tools/micro/mma_issue.cu) and ~70-90 clk when it shares its scheduler with busy arithmetic warps, which
+// made the one issuer of 40 small MMAs per query tile the critical path (measured with clock64 traces).
+constexpr int BWD_KV_THREADS = 352;
+__global__ void __launch_bounds__(BWD_KV_THREADS, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                       const __grid_constant__ CUtensorMap tmDS, const AttnParams p) {
@@ -693,7 +698,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_init(bar_fin, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_qf + 8 * i, 1);
-      mbar_init(bar_qe + 8 * i, 1);
+      mbar_init(bar_qe + 8 * i, 2);  // both MMA issuers release a Q / dO stage
       mbar_init(bar_stf + 8 * i, 1);
       mbar_init(bar_sf + 8 * i, 1);
       mbar_init(bar_pf + 8 * i, 4);
@@ -734,12 +739,12 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (lane == 0) mbar_arrive(bar_stf + 8 * st);
     }
   } else if (warp == 8) {
+    // ---- S^T_h = K Q_h^T and dP^T_h = V dO_h^T of the NEXT query tile, as soon as warpgroup h has consumed the
+    //      current ones
     if (lane == 0 && n_it > 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);
-      constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, false, true);
       const uint32_t bK = base_k64(sK), bV = base_k64(sV);
-      const uint32_t bQk = base_k64(sQ), bdOk = base_k64(sdO);     // K-major views (S^T, dP^T: B operand)
-      const uint32_t bQm = base_mn64(sQ), bdOm = base_mn64(sdO);   // MN-major views (dK, dV: B operand)
+      const uint32_t bQk = base_k64(sQ), bdOk = base_k64(sdO);
       auto issue_s = [&](int hh, int st) {
         const uint32_t off = (uint32_t)(st * QKV_BYTES + hh * 4096) >> 4;
         const uint32_t qh = bQk + off, doh = bdOk + off;
@@ -749,28 +754,38 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int k = 0; k < 6; ++k) tc_mma_bf16_lh(tmem + 128 + 64 * hh, step_k64(bV, k), kHi64, step_k64(doh, k), kHi64, idesc_s, k > 0);
         tc_commit(bar_sf + 8 * hh);
       };
-#ifdef SCT_ATTN_TRACE
-      long long tr_t0 = clock64(), tr_qf = 0, tr_pf = 0, tr_g = 0, tr_sw = 0, tr_s = 0, tr_x;
-#define TR_BEGIN() tr_x = clock64()
-#define TR_END(acc) acc += clock64() - tr_x
-#else
-#define TR_BEGIN()
-#define TR_END(acc)
-#endif
       mbar_wait(bar_kv, 0);
       mbar_wait(bar_qf, 0);
       tc_fence_after();
       issue_s(0, 0);
       issue_s(1, 0);
-      for (int it = 0; it < n_it; ++it) {
-        const int st = it & 1;
+      tc_commit(bar_qe);  // this issuer's last MMAs on stage 0
+      for (int it = 0; it + 1 < n_it; ++it) {
+        const int sn = (it + 1) & 1;
+        mbar_wait(bar_qf + 8 * sn, ((it + 1) >> 1) & 1);
+        tc_fence_after();
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          TR_BEGIN();
-          mbar_wait(bar_pf + 8 * hh, it & 1);
-          TR_END(tr_pf);
+          mbar_wait(bar_pf + 8 * hh, it & 1);  // S^T_h / dP^T_h of tile `it` are in registers
           tc_fence_after();
-          TR_BEGIN();
+          issue_s(hh, sn);
+        }
+        tc_commit(bar_qe + 8 * sn);
+      }
+    }
+  } else if (warp == 10) {
+    // ---- dV += P^T_h dO_h (A = P^T_h packed bf16 in TMEM) and dK += dS^T_h Q_h (A = dS^T_h in shared memory, which
+    //      is also what the workspace store reads)
+    if (lane == 0 && n_it > 0) {
+      constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, false, true);
+      const uint32_t bQm = base_mn64(sQ), bdOm = base_mn64(sdO);  // MN-major views (B operands)
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it & 1;
+        mbar_wait(bar_qf + 8 * st, (it >> 1) & 1);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          mbar_wait(bar_pf + 8 * hh, it & 1);
+          tc_fence_after();
           const uint32_t off = (uint32_t)(st * QKV_BYTES + hh * 4096) >> 4;
           const uint32_t qh = bQm + off, doh = bdOm + off;
           const uint32_t acc = (it > 0 || hh > 0) ? 1u : 0u;
@@ -778,46 +793,22 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             tma_store_3d(&tmDS, sDST + hh * HALF_BYTES, (i_begin + it) * TILE + hh * 64, kv0, b * p.H + h);
             tma_commit_group();
           }
-          // dV += P^T_h dO_h and dK += dS^T_h Q_h with the A operands read from TMEM (packed bf16: P^T_h in 32 columns
-          // at 448 + 32 hh, dS^T_h over the first 32 columns of the consumed dP^T_h buffer): no shared-memory reads
-          // for A (tools/micro/mma_issue.cu: 48 instead of >= 56 clk per MMA, and less contention with the ALU warps)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             tc_mma_bf16_ts(tmem + 256, tmem + 448 + 32 * hh + 8 * k, step_mn64(doh, k), kHi64, idesc_g, (acc || k > 0) ? 1u : 0u);
+          const uint32_t bDS = umma_desc_lo(sDST + hh * HALF_BYTES, 16);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            tc_mma_bf16_ts(tmem + 352, tmem + 128 + 64 * hh + 8 * k, step_mn64(qh, k), kHi64, idesc_g, (acc || k > 0) ? 1u : 0u);
-          TR_END(tr_g);
-          // every MMA that reads Q / dO stage `st` has been issued: hand the stage back to the TMA warp now, so the
-          // tiles of iteration it + 2 have a whole iteration to land
-          if (hh == 1) tc_commit(bar_qe + 8 * st);
-          if (it + 1 < n_it) {
-            if (hh == 0) {
-              TR_BEGIN();
-              mbar_wait(bar_qf + 8 * (st ^ 1), ((it + 1) >> 1) & 1);
-              TR_END(tr_qf);
-              tc_fence_after();
-            }
-            TR_BEGIN();
-            issue_s(hh, st ^ 1);
-            TR_END(tr_s);
-          }
-          // P^T_h / dS^T_h go back to warpgroup hh once the gradient MMAs have retired and the workspace store has
-          // read dS^T_h; the warpgroup waits for S^T_h (just issued) first, so this later commit costs it nothing
-          TR_BEGIN();
+            tc_mma_bf16_lh(tmem + 352, bDS + 2 * k, kHi128, step_mn64(qh, k), kHi64, idesc_g, (acc || k > 0) ? 1u : 0u);
+          if (hh == 1) tc_commit(bar_qe + 8 * st);  // this issuer's last MMAs on Q / dO stage `st`
+          // P^T_h / dS^T_h go back to warpgroup hh once these MMAs have retired and the workspace store has read dS^T_h
           if (p.write_ds) tma_wait_group_read0();
-          TR_END(tr_sw);
           tc_commit(bar_gd + 8 * hh);
         }
       }
       tc_commit(bar_fin);  // every gradient MMA has retired: dV / dK may be drained (both warpgroups wait on this one;
                            // a parity wait on the other half's `gd` barrier can pass a phase too early)
       if (p.write_ds) tma_wait_group0();  // workspace writes complete before the grid ends
-#ifdef SCT_ATTN_TRACE
-      if (blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0)
-        printf("dkdv MMA thread: total %lld  wait_qf %lld  wait_pf %lld  issue_grad %lld  store_wait %lld  issue_s %lld  (n_it %d)\n",
-               clock64() - tr_t0, tr_qf, tr_pf, tr_g, tr_sw, tr_s, n_it);
-#endif
     }
   } else {
     const int hh = warp >> 2, quad = warp & 3;  // warpgroup hh owns query columns [64 hh, 64 hh + 64) of every tile
@@ -830,19 +821,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (row_valid && p.kpm) row_valid = p.kpm[(long long)b * p.Lk + kv] == 0;
     const uint32_t bh = (uint32_t)(b * p.H + h);
     const DropKey dkey = drop_key(p);
-#ifdef SCT_ATTN_TRACE
-    long long ta_t0 = clock64(), ta_rng = 0, ta_sf = 0, ta_gd = 0, ta_alu = 0, ta_x;
-#define TA_BEGIN() ta_x = clock64()
-#define TA_END(acc) acc += clock64() - ta_x
-#else
-#define TA_BEGIN()
-#define TA_END(acc)
-#endif
     for (int it = 0; it < n_it; ++it) {
       const int st = it & 1;
       const int qi = i_begin + it;
       const int q0 = qi * TILE + hh * 64;  // first query of this half
-      TA_BEGIN();
       // keep bits of (q = q0 + c0 + i, k = this thread's key row): lane L makes the word of query q0 + c0 + L over the
       // warp's 32 keys, then the warp transposes the 32x32 bit tile (index-only work, done before the waits)
       uint32_t kw0 = keep_word(p, dkey, bh, (uint32_t)(q0 + lane), (uint32_t)((kv0 >> 5) + quad));
@@ -851,17 +833,11 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         kw0 = warp_bit_transpose(kw0, lane);
         kw1 = warp_bit_transpose(kw1, lane);
       }
-      TA_END(ta_rng);
-      TA_BEGIN();
       mbar_wait(bar_stf + 8 * st, (it >> 1) & 1);
       mbar_wait(bar_sf + 8 * hh, it & 1);
-      TA_END(ta_sf);
       tc_fence_after();
       const bool diag = p.causal && (qi == jt);
-      TA_BEGIN();
       if (it > 0) mbar_wait(bar_gd + 8 * hh, (it - 1) & 1);  // P^T_h / dS^T_h buffers free again
-      TA_END(ta_gd);
-      TA_BEGIN();
       // four 16-query chunks; the TMEM loads of chunk cc + 1 are in flight while chunk cc is in the ALUs
       uint32_t rs[2][16], rp[2][16];
       tmem_ld16(tST + lane_sel, rs[0]);
@@ -898,26 +874,14 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(pd[2 * i], pd[2 * i + 1]);
           tmem_st8(tPT + lane_sel + cc * 8, pk);
         }
-        {  // dS^T chunk -> TMEM over dP^T columns this thread has consumed (A operand of the dK MMA) ...
-          uint32_t pk[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(ds[2 * i], ds[2 * i + 1]);
-          tmem_st8(tDPT + lane_sel + cc * 8, pk);
-        }
-        if (p.write_ds) store_row16_sw128(sDSTh, r, c0, ds);  // ... and -> shared memory for the workspace store
+        store_row16_sw128(sDSTh, r, c0, ds);  // dS^T chunk -> shared memory: A operand of the dK MMA and workspace store
       }
       tmem_st_wait();
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_pf + 8 * hh);
-      TA_END(ta_alu);
     }
-#ifdef SCT_ATTN_TRACE
-    if (blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (warp == 0 || warp == 4))
-      printf("dkdv warp %d: loop total %lld  rng %lld  wait_sf %lld  wait_gd %lld  alu %lld\n", warp, clock64() - ta_t0, ta_rng,
-             ta_sf, ta_gd, ta_alu);
-#endif
     if (n_it > 0) {
       mbar_wait(bar_fin, 0);
       tc_fence_after();
@@ -1251,7 +1215,7 @@ int32_t sct_attn_bwd_ws(const void* q, int64_t ldq, const void* k, const void* v
   }
   {
     dim3 grid((unsigned)((Lk + TILE - 1) / TILE), (unsigned)H, (unsigned)B);
-    attn_bwd_dkdv_kernel<<<grid, BWD3_THREADS, BWD3_KV_SMEM, st>>>(tq, tk, tv, tdo, tds_st, p);
+    attn_bwd_dkdv_kernel<<<grid, BWD_KV_THREADS, BWD3_KV_SMEM, st>>>(tq, tk, tv, tdo, tds_st, p);
     SCT_LAUNCH_CHECK();
   }
   {
