@@ -169,6 +169,28 @@ __device__ __forceinline__ void store_row16_sw128(uint32_t blk, int r, int c0, c
   }
 }
 
+// epilogues: 32 fp32 accumulator columns of row r (scaled) -> bf16 into column block c of a swizzle-64 [128 x 96]
+// tile (the layout the 3-D tensor maps of Q / K / V / O use), from where ONE thread stores the tile with TMA: a
+// thread-per-row st.global touches 32 different 4.6 kB-strided rows per instruction and took ~15 % of the dK/dV
+// kernel's time (ncu source view).
+__device__ __forceinline__ void stage_chunk_sw64(uint32_t tile, int r, int c, const uint32_t (&rr)[32], float sc) {
+  const uint32_t rowbase = tile + c * BLK + r * 64;
+#pragma unroll
+  for (int qd = 0; qd < 4; ++qd) {
+    const uint32_t dst = rowbase + (((qd ^ (r >> 1)) & 3) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
+                 "r"(pack_bf16(__uint_as_float(rr[8 * qd]) * sc, __uint_as_float(rr[8 * qd + 1]) * sc)),
+                 "r"(pack_bf16(__uint_as_float(rr[8 * qd + 2]) * sc, __uint_as_float(rr[8 * qd + 3]) * sc)),
+                 "r"(pack_bf16(__uint_as_float(rr[8 * qd + 4]) * sc, __uint_as_float(rr[8 * qd + 5]) * sc)),
+                 "r"(pack_bf16(__uint_as_float(rr[8 * qd + 6]) * sc, __uint_as_float(rr[8 * qd + 7]) * sc))
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void store_tile(const CUtensorMap* m, uint32_t src, int col0, int row0, int b) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) tma_store_3d(m, src + c * BLK, col0 + 32 * c, row0, b);
+}
+
 __device__ __forceinline__ void load_tile(const CUtensorMap* m, uint32_t bar, uint32_t dst, int col0,
                                           int row0, int b) {
 #pragma unroll
@@ -187,7 +209,7 @@ constexpr int FWD_SMEM = 1024 + 3 * QKV_BYTES + 4096;
 
 __global__ void __launch_bounds__(256, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -370,7 +392,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float l_tot = l_s[r] + l_s[128 + r];
     const float inv_l = l_tot > 0.f ? p.inv_keep / l_tot : 0.f;
     const bool valid = q < p.Lq;
-    __nv_bfloat16* dst = p.o + ((long long)b * p.Lq + q) * p.ldo + h * DH;
+    // O / l -> bf16, staged in the (dead) Q tile and stored by one thread with TMA (rows past Lq are clipped)
 #pragma unroll 1
     for (int c = (hf == 0 ? 0 : 2); c < (hf == 0 ? 2 : 3); ++c) {
       uint32_t rr[32];
@@ -381,17 +403,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int i = 0; i < 32; ++i) rr[i] = 0u;
       }
-      if (valid) {
-#pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {
-          uint4 u;
-          u.x = pack_bf16(__uint_as_float(rr[8 * qd]) * inv_l, __uint_as_float(rr[8 * qd + 1]) * inv_l);
-          u.y = pack_bf16(__uint_as_float(rr[8 * qd + 2]) * inv_l, __uint_as_float(rr[8 * qd + 3]) * inv_l);
-          u.z = pack_bf16(__uint_as_float(rr[8 * qd + 4]) * inv_l, __uint_as_float(rr[8 * qd + 5]) * inv_l);
-          u.w = pack_bf16(__uint_as_float(rr[8 * qd + 6]) * inv_l, __uint_as_float(rr[8 * qd + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(dst + c * 32 + qd * 8) = u;
-        }
-      }
+      stage_chunk_sw64(sQ, r, c, rr, inv_l);
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      store_tile(&tmO, sQ, h * DH, q0, b);
+      tma_commit_group();
+      tma_wait_group_read0();
     }
     if (valid && hf == 0 && p.lse2)
       p.lse2[((long long)b * p.H + h) * p.Lq + q] = l_tot > 0.f ? (m_run + log2f(l_tot)) : INFINITY;
@@ -668,7 +687,8 @@ constexpr int BWD_KV_THREADS = 352;
 __global__ void __launch_bounds__(BWD_KV_THREADS, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
-                      const __grid_constant__ CUtensorMap tmDS, const AttnParams p) {
+                      const __grid_constant__ CUtensorMap tmDS, const __grid_constant__ CUtensorMap tmDK,
+                      const __grid_constant__ CUtensorMap tmDV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -887,10 +907,12 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tc_fence_after();
     }
     {
-      // warpgroup 0 drains dV, warpgroup 1 drains dK (scaled)
+      // warpgroup 0 drains dV (staged in the V tile's shared memory), warpgroup 1 dK * scale (in the K tile's): every
+      // MMA has retired, the operand tiles are dead.  One thread per warpgroup then stores the tile with TMA (rows
+      // past Lk are clipped by the tensor map).
       const uint32_t src = tmem + (hh == 0 ? 256 : 352);
       const float sc = hh == 0 ? 1.0f : p.scale;
-      __nv_bfloat16* dst = (hh == 0 ? p.dv : p.dk) + ((long long)b * p.Lk + kv) * p.ldkv_out + h * DH;
+      const uint32_t stage = hh == 0 ? sV : sK;
 #pragma unroll 1
       for (int c = 0; c < 3; ++c) {
         uint32_t rr[32];
@@ -901,17 +923,14 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
           for (int i = 0; i < 32; ++i) rr[i] = 0u;
         }
-        if (kv < p.Lk) {
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            uint4 u;
-            u.x = pack_bf16(__uint_as_float(rr[8 * qd]) * sc, __uint_as_float(rr[8 * qd + 1]) * sc);
-            u.y = pack_bf16(__uint_as_float(rr[8 * qd + 2]) * sc, __uint_as_float(rr[8 * qd + 3]) * sc);
-            u.z = pack_bf16(__uint_as_float(rr[8 * qd + 4]) * sc, __uint_as_float(rr[8 * qd + 5]) * sc);
-            u.w = pack_bf16(__uint_as_float(rr[8 * qd + 6]) * sc, __uint_as_float(rr[8 * qd + 7]) * sc);
-            *reinterpret_cast<uint4*>(dst + c * 32 + qd * 8) = u;
-          }
-        }
+        stage_chunk_sw64(stage, r, c, rr, sc);
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + hh, 128);
+      if (quad == 0 && lane == 0) {
+        store_tile(hh == 0 ? &tmDV : &tmDK, stage, h * DH, kv0, b);
+        tma_commit_group();
+        tma_wait_group_read0();  // shared memory stays valid until the store has read it
       }
     }
   }
@@ -936,7 +955,7 @@ constexpr int DQ2_THREADS = 192;
 
 __global__ void __launch_bounds__(DQ2_THREADS, 2)
 attn_bwd_dq_ds_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant__ CUtensorMap tmK64,
-                      const AttnParams p) {
+                      const __grid_constant__ CUtensorMap tmDQ, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -1012,13 +1031,12 @@ attn_bwd_dq_ds_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_con
   } else {
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
-    const int q = q0 + r;
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
     if (n_st > 0) {
       mbar_wait(bar_done, 0);
       tc_fence_after();
     }
-    __nv_bfloat16* dst = p.dq + ((long long)b * p.Lq + q) * p.ldq_out + h * DH;
+    // dQ * scale -> bf16, staged in the (dead) first pipeline stage and stored by one thread with TMA
 #pragma unroll 1
     for (int c = 0; c < 3; ++c) {
       uint32_t rr[32];
@@ -1029,17 +1047,14 @@ attn_bwd_dq_ds_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_con
 #pragma unroll
         for (int i = 0; i < 32; ++i) rr[i] = 0u;
       }
-      if (q < p.Lq) {
-#pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {
-          uint4 u;
-          u.x = pack_bf16(__uint_as_float(rr[8 * qd]) * p.scale, __uint_as_float(rr[8 * qd + 1]) * p.scale);
-          u.y = pack_bf16(__uint_as_float(rr[8 * qd + 2]) * p.scale, __uint_as_float(rr[8 * qd + 3]) * p.scale);
-          u.z = pack_bf16(__uint_as_float(rr[8 * qd + 4]) * p.scale, __uint_as_float(rr[8 * qd + 5]) * p.scale);
-          u.w = pack_bf16(__uint_as_float(rr[8 * qd + 6]) * p.scale, __uint_as_float(rr[8 * qd + 7]) * p.scale);
-          *reinterpret_cast<uint4*>(dst + c * 32 + qd * 8) = u;
-        }
-      }
+      stage_chunk_sw64(base, r, c, rr, p.scale);
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (warp == 2 && lane == 0) {
+      store_tile(&tmDQ, base, h * DH, q0, b);
+      tma_commit_group();
+      tma_wait_group_read0();
     }
   }
   tc_fence_before();
@@ -1119,8 +1134,9 @@ int32_t sct_attn_fwd_strided(const void* q, int64_t ldq, const void* k, const vo
   p.o = (__nv_bfloat16*)o;
   p.ldo = (int)ldo;
   p.lse2 = lse2;
-  CUtensorMap tq, tk, tv;
+  CUtensorMap tq, tk, tv, to;
   if (int rc = make_qkv_map(&tq, q, ldq, B, Lq, H)) return rc;
+  if (int rc = make_qkv_map(&to, o, ldo, B, Lq, H)) return rc;
   SCT_CHECK(kv_batch_stride == 0 || (kv_batch_stride >= Lk * ldkv && kv_batch_stride % 8 == 0),
             "kv_batch_stride must be 0 or a multiple of 8 >= Lk * ldkv");
   if (int rc = make_qkv_map(&tk, k, ldkv, B, Lk, H, kv_batch_stride)) return rc;
@@ -1131,7 +1147,7 @@ int32_t sct_attn_fwd_strided(const void* q, int64_t ldq, const void* k, const vo
     attr = true;
   }
   dim3 grid((unsigned)((Lq + TILE - 1) / TILE), (unsigned)H, (unsigned)B);
-  attn_fwd_kernel<<<grid, 256, FWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  attn_fwd_kernel<<<grid, 256, FWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, to, p);
   SCT_LAUNCH_CHECK();
   return 0;
 }
@@ -1215,15 +1231,21 @@ int32_t sct_attn_bwd_ws(const void* q, int64_t ldq, const void* k, const void* v
   }
   {
     dim3 grid((unsigned)((Lk + TILE - 1) / TILE), (unsigned)H, (unsigned)B);
-    attn_bwd_dkdv_kernel<<<grid, BWD_KV_THREADS, BWD3_KV_SMEM, st>>>(tq, tk, tv, tdo, tds_st, p);
+    CUtensorMap tdk, tdv;
+    if (int rc = make_qkv_map(&tdk, dk, lddkv, B, Lk, H)) return rc;
+    if (int rc = make_qkv_map(&tdv, dv, lddkv, B, Lk, H)) return rc;
+    attn_bwd_dkdv_kernel<<<grid, BWD_KV_THREADS, BWD3_KV_SMEM, st>>>(tq, tk, tv, tdo, tds_st, tdk, tdv, p);
     SCT_LAUNCH_CHECK();
   }
   {
     dim3 grid((unsigned)((Lq + TILE - 1) / TILE), (unsigned)H, (unsigned)B);
-    if (use_ws)
-      attn_bwd_dq_ds_kernel<<<grid, DQ2_THREADS, DQ2_SMEM, st>>>(tds_ld, tk64, p);
-    else
+    if (use_ws) {
+      CUtensorMap tdq;
+      if (int rc = make_qkv_map(&tdq, dq, lddq, B, Lq, H)) return rc;
+      attn_bwd_dq_ds_kernel<<<grid, DQ2_THREADS, DQ2_SMEM, st>>>(tds_ld, tk64, tdq, p);
+    } else {
       attn_bwd_dq_kernel<<<grid, BWD3_THREADS, BWD3_Q_SMEM, st>>>(tq, tk, tv, tdo, p);
+    }
     SCT_LAUNCH_CHECK();
   }
   return 0;
