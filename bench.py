@@ -211,7 +211,11 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("SCT_NCCL_DEBUG", "WARN")  # keep NCCL's banner off stdout (one JSON line)
+        # stdout carries ONE JSON line: whatever NCCL logs (its version banner at NCCL_DEBUG=WARN, INFO traces) goes to
+        # stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if "SCT_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["SCT_NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=dev)
     assert _lib.load().sct_device_check() == 0, _lib.last_error()
     W = max(3, args.warmup)

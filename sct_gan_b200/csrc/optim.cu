@@ -1,7 +1,10 @@
 // sct_b200 — fused optimiser tail of the train step: the three clip_grad_norm_ calls, the
 // per-parameter .item() norm loop, the NaN / norm > 1000 skip rule and AdamW with the four learning-rate
 // groups of SCT-GAN/train.py:512-540, 1277-1311, as three multi-tensor launches without any host decision:
-//   1. opt_sqnorm       sum of squares of every gradient, accumulated per clip scope (rest / disc_ / vuln heads)
+//   1. opt_sqnorm       sum of squares of every gradient chunk, then ONE block adds the chunk sums per clip scope
+//                       (rest / disc_ / vuln heads) in a fixed order: no float atomics, so the clip coefficients — and
+//                       with them every updated weight — are bit-identical on every data-parallel replica and from
+//                       run to run (an atomicAdd version let replicas drift apart by ulps per step)
 //   2. opt_clip_adamw   clip coefficients from those three numbers (the scopes nest: the second and third clip see
 //                       gradients already scaled by the first), skip predicate, AdamW on fp32 master weights
 //   3. opt_finish       per-tensor step counters, reported gradient norm and the stepped flag
@@ -53,7 +56,7 @@ __device__ __forceinline__ ClipInfo clip_info(const float* sq, const float* loss
 }
 
 __global__ void __launch_bounds__(kThreads)
-opt_sqnorm_kernel(const OptTensor* __restrict__ tab, const int2* __restrict__ chunks, float* __restrict__ sq) {
+opt_sqnorm_kernel(const OptTensor* __restrict__ tab, const int2* __restrict__ chunks, float* __restrict__ part) {
   __shared__ float red[kThreads / 32];
   const int2 ck = chunks[blockIdx.x];
   const OptTensor t = tab[ck.x];
@@ -75,8 +78,28 @@ opt_sqnorm_kernel(const OptTensor* __restrict__ tab, const int2* __restrict__ ch
     float tot = 0.f;
 #pragma unroll
     for (int w = 0; w < kThreads / 32; ++w) tot += red[w];
-    atomicAdd(sq + t.seg, tot);
+    part[blockIdx.x] = tot;
   }
+}
+
+constexpr int kReduceThreads = 1024;
+__global__ void __launch_bounds__(kReduceThreads)
+opt_sqnorm_reduce_kernel(const OptTensor* __restrict__ tab, const int2* __restrict__ chunks,
+                         const float* __restrict__ part, int n_chunks, float* __restrict__ sq) {
+  __shared__ double red[3][kReduceThreads];
+  double s[3] = {0.0, 0.0, 0.0};
+  for (int i = threadIdx.x; i < n_chunks; i += kReduceThreads) s[tab[chunks[i].x].seg] += (double)part[i];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) red[k][threadIdx.x] = s[k];
+  __syncthreads();
+  for (int off = kReduceThreads / 2; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) red[k][threadIdx.x] += red[k][threadIdx.x + off];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) sq[threadIdx.x] = (float)red[threadIdx.x][0];
 }
 
 __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v, float lr, float wd, float b1, float b2,
@@ -157,8 +180,10 @@ int32_t sct_clip_adamw_step(const void* table, int32_t n_tensors, const void* ch
   cudaStream_t st = (cudaStream_t)stream;
   const OptTensor* tab = static_cast<const OptTensor*>(table);
   const int2* ck = static_cast<const int2*>(chunks);
-  SCT_CUDA(cudaMemsetAsync(sqnorm3, 0, 3 * sizeof(float), st));
-  opt_sqnorm_kernel<<<n_chunks, kThreads, 0, st>>>(tab, ck, sqnorm3);
+  float* part = sqnorm3 + 4;  // [n_chunks] per-chunk sums of squares
+  opt_sqnorm_kernel<<<n_chunks, kThreads, 0, st>>>(tab, ck, part);
+  SCT_LAUNCH_CHECK();
+  opt_sqnorm_reduce_kernel<<<1, kReduceThreads, 0, st>>>(tab, ck, part, n_chunks, sqnorm3);
   SCT_LAUNCH_CHECK();
   opt_clip_adamw_kernel<<<n_chunks, kThreads, 0, st>>>(tab, ck, sqnorm3, loss, max_norm, disc_mult, vuln_mult, beta1,
                                                        beta2, eps);

@@ -216,7 +216,8 @@ class FusedClipAdamW:
         tab_h = torch.zeros(len(self.all_params) * 64, dtype=torch.uint8).pin_memory()
         ck_h = torch.zeros((self.max_chunks, 2), dtype=torch.int32).pin_memory()
         return (tab_h, ck_h, torch.empty_like(tab_h, device=dev), torch.empty_like(ck_h, device=dev),
-                torch.zeros(8, dtype=torch.float32, device=dev))  # scratch: [0:3] squared norms, [4:6] out2
+                # scratch: [0:2] out2 (norm, stepped), [4:7] squared norms per clip scope, [8:8+chunks] chunk sums
+                torch.zeros(8 + self.max_chunks, dtype=torch.float32, device=dev))
 
     def prepare_for_capture(self):
         """A CUDA graph replays the host->device table copy, so every captured graph gets buffers of its own,
@@ -276,8 +277,8 @@ class FusedClipAdamW:
             self._sig = sig
         tab_d, ck_d, scratch = self.bufs[2], self.bufs[3], self.bufs[4]
         kn.clip_adamw_step(tab_d, self.n_tensors, ck_d, self.n_chunks, loss.detach().float().reshape(1),
-                           scratch[0:3], scratch[4:6], self.max_norm, 0.3, 2.0, self.betas[0], self.betas[1], self.eps)
-        return scratch[4].clone(), scratch[5] > 0.5
+                           scratch[4:], scratch[0:2], self.max_norm, 0.3, 2.0, self.betas[0], self.betas[1], self.eps)
+        return scratch[0].clone(), scratch[1] > 0.5
 
 
 class SmartContractTrainer:

@@ -377,6 +377,17 @@ def test_fused_clip_adamw_matches_torch_and_oracle(cuda_dev, scale):
     for (n, a), b in zip(ma.named_parameters(), mb.parameters()):
         assert torch.allclose(a, b, rtol=2e-5, atol=2e-6), n
         assert torch.allclose(params_o[n].cuda(), b, rtol=2e-5, atol=2e-6), n
+    # determinism: a third copy stepped the same way lands on the same bits (the squared norms are reduced in a fixed
+    # order, not with float atomics) — what keeps data-parallel replicas identical (tools/dp_sync_check.py)
+    mc = copy.deepcopy(base)
+    oc = make_opt(mc)
+    tail_c = FusedClipAdamW(oc, list(mc.named_parameters()), True, 1.0)
+    for it in range(3):
+        for n, p in mc.named_parameters():
+            p.grad = grads[n].clone() if n in grads else None
+        tail_c.step(loss)
+    for (n, b), c in zip(mb.named_parameters(), mc.parameters()):
+        assert torch.equal(b, c), n
     expect_steps = 0.0 if scale != scale else 3.0  # (after the clips the norm is <= 1: only NaN/Inf can skip)
     for p in mb.parameters():
         if p.grad is not None:
