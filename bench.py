@@ -329,15 +329,15 @@ def main():
                       "achieved": round(rate, 1), "unit": unit,
                       "frac": round(rate / (hbm_peak if unit == "GB/s" else tf_peak), 4)}
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01f_gemm_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01m_gemm_traffic.json")
     if os.path.exists(tpath):  # DRAM bytes per launch of this kernel family from the committed ncu pass of the same step
         with open(tpath) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
     roofline = {"bound": "tensor", "kernel": "gemm_kernel (sct_gemm_bf16_nt/nn/tn: tcgen05 + TMEM + TMA)",
                 "achieved": round(achieved, 1), "peak": tf_peak, "unit": "TFLOP/s",
                 "frac": round(achieved / tf_peak, 4), "traffic": traffic,
-                "traffic_note": "ncu dram__bytes_read+write per launch, averaged over the 255 GEMM launches of one step "
-                                "(profiles/r01f_gemm_traffic.json); algorithmic A+B+D bytes average ~160 MB per launch",
+                "traffic_note": "ncu dram__bytes_read+write per launch, averaged over the 258 GEMM launches of one step "
+                                "(profiles/r01m_gemm_traffic.json); algorithmic A+B+D bytes average ~160 MB per launch",
                 "flops_per_launch": round(g_work / max(g_n, 1), 0),
                 "peak_source": f"{peak_src} (sustained bf16)",
                 "launches_per_step": g_n, "ms_per_step_in_kernel": round(g_ms, 3),

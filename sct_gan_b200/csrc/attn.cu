@@ -875,14 +875,20 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const uint32_t (&p_)[16] = rp[cc & 1];
         float pd[16], ds[16];
         if (row_valid) {
+          float pr[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            pr[i] = exp2f(fmaf(__uint_as_float(s_[i]), p.scale_log2, -lse_s[st * 128 + hh * 64 + c0 + i]));
+          if (diag) {  // warp-uniform: only the diagonal tile pays for the causal comparison
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (r > hh * 64 + c0 + i) pr[i] = 0.f;
+          }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const int c = hh * 64 + c0 + i;  // query column inside the 128-query tile
-            float pr = exp2f(fmaf(__uint_as_float(s_[i]), p.scale_log2, -lse_s[st * 128 + c]));
-            if (diag && r > c) pr = 0.f;
             const float dm = (kw & (1u << i)) ? p.inv_keep : 0.f;
-            pd[i] = pr * dm;
-            ds[i] = pr * fmaf(__uint_as_float(p_[i]), dm, -dv_s[st * 128 + c]);
+            pd[i] = pr[i] * dm;
+            ds[i] = pr[i] * fmaf(__uint_as_float(p_[i]), dm, -dv_s[st * 128 + hh * 64 + c0 + i]);
           }
         } else {
 #pragma unroll
