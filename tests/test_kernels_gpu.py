@@ -243,11 +243,10 @@ def test_embed_gather_bit_exact(cuda_dev):
     assert torch.equal(rec[:, 0].round().long(), ids)
 
 
-@pytest.mark.parametrize("d", [768, 384, 1536])
-def test_add_dropout_ln(cuda_dev, d):
+@pytest.mark.parametrize("d,n", [(768, 1000), (384, 1000), (1536, 1000), (768, 5003)])  # 5003 rows: staged kernels
+def test_add_dropout_ln(cuda_dev, d, n):
     from sct_gan_b200 import kernels as kn
 
-    n = 1000
     g = torch.Generator(device="cuda").manual_seed(d)
     x = torch.randn(n, d, device="cuda", generator=g).requires_grad_(True)
     br = torch.randn(n, d, device="cuda", generator=g).to(BF16)
@@ -272,10 +271,11 @@ def test_add_dropout_ln(cuda_dev, d):
     assert rel_l2(dbeta, beta.grad) < 1e-3
 
 
-def test_dropout_mask_replay(cuda_dev):
+@pytest.mark.parametrize("n", [2048, 4500])  # plain and bulk-copy-staged kernels generate the same masks
+def test_dropout_mask_replay(cuda_dev, n):
     from sct_gan_b200 import kernels as kn
 
-    n, d = 2048, 768
+    d = 768
     x = torch.zeros(n, d, device="cuda")
     br = torch.ones(n, d, device="cuda", dtype=BF16)
     x_out, _, _, _ = kn.add_dropout_ln_fwd(x, br, 1.0, None, None, want_ln=False, p_drop=0.3, seed=5, offset=9)
