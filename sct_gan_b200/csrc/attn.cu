@@ -973,7 +973,8 @@ attn_bwd_dq_ds_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_con
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nq_tiles = gridDim.x;
   const int qt = nq_tiles - 1 - blockIdx.x;
-  const int h = blockIdx.y, b = blockIdx.z;
+  // the dK/dV kernel wrote the workspace in (b, h) order: start with what it wrote LAST, which is still in L2
+  const int h = gridDim.y - 1 - blockIdx.y, b = gridDim.z - 1 - blockIdx.z;
   const int q0 = qt * TILE;
 
   if (tid == 0) {
