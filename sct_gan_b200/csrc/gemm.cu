@@ -567,6 +567,8 @@ int32_t sct_gemm_bf16_nt(const void* A, int64_t lda, const void* W, int64_t ldw,
   if (int rc = sct::check_common(A, W, D, M, N, K)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (bn == 256) return sct::launch<256, false, false, false>(A, lda, W, ldw, D, ldd, bias, nullptr, alpha, M, N, K, 1, st);
+  // 128x64 tiles: skinny GEMMs of the decode step (M <= 128 rows): N / 64 CTAs stream the weight instead of N / 256
+  if (bn == 64) return sct::launch<64, false, false, false>(A, lda, W, ldw, D, ldd, bias, nullptr, alpha, M, N, K, 1, st);
   return sct::launch<128, false, false, false>(A, lda, W, ldw, D, ldd, bias, nullptr, alpha, M, N, K, 1, st);
 }
 

@@ -181,9 +181,13 @@ def seq_mean_bwd(g, B, S, d, want_f32=False, want_bf16=True):
 
 
 # ---------------------------------------------------------------------------------------------- K2
-def _pick_bn(N):
+def _pick_bn(N, M=None, nt=False):
     # measured on B200 (tools/gemm_bench.py, M = 32768): the 128x256 tile wins from N = 768 up (880 vs 804
-    # TFLOP/s at N = K = 768, 1045 vs 917 at N = 2304); the 128x128 tile only for the narrow N = 384 GEMMs
+    # TFLOP/s at N = K = 768, 1045 vs 917 at N = 2304); the 128x128 tile only for the narrow N = 384 GEMMs.
+    # One row tile (the decode step, M <= 128): the GEMM is a weight stream and N / 256 CTAs (3 for N = 768) leave the
+    # machine empty -> 128x64 tiles (forward GEMM only)
+    if nt and M is not None and M <= 128:
+        return 64
     return 256 if N >= 512 else 128
 
 
@@ -201,7 +205,7 @@ def gemm_nt(a, w, bias=None, alpha=1.0, out=None, bn=None):
         _chk(bias, F32, "bias")
     _lib.Stats.annotate(2.0 * M * N * K)
     _lib.call("sct_gemm_bf16_nt", _ptr(a), lda, _ptr(w), ldw, _ptr(out), ldd, _ptr(bias), float(alpha),
-              M, N, K, bn or _pick_bn(N), _stream())
+              M, N, K, bn or _pick_bn(N, M, nt=True), _stream())
     return out
 
 

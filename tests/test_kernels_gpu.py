@@ -30,6 +30,7 @@ def _no_timeouts():
     (128, 128, 64, 128), (256, 256, 128, 128), (4096, 768, 768, 128), (4096, 2304, 768, 256),
     (4096, 2048, 768, 256), (4096, 768, 2048, 128), (1000, 520, 776, 128), (2048, 50265, 768, 256),
     (333, 384, 768, 128), (4096, 768, 384, 128), (1000, 520, 776, 256), (384, 512, 128, 256), (129, 768, 768, 256),
+    (128, 768, 768, 64), (128, 2304, 768, 64), (100, 50265, 768, 64), (128, 768, 2048, 64), (300, 200, 72, 64),
 ])
 def test_gemm_nt(cuda_dev, M, N, K, bn):
     from sct_gan_b200 import kernels as kn
@@ -163,6 +164,44 @@ def test_attention_fwd_bwd(cuda_dev, B, Lq, Lk, causal, masked, workspace, monke
     assert rel_l2(dv, unheads(vf.grad, Lk)) < 1.5e-2
     assert rel_l2(dk, unheads(kf.grad, Lk)) < 1.5e-2
     assert rel_l2(dq, unheads(qf.grad, Lq)) < 1.5e-2
+
+
+@pytest.mark.parametrize("Lk,masked,t_max", [(1, False, 0), (77, True, 0), (300, True, 512), (1024, False, 1024),
+                                              (513, True, 1024)])
+def test_attention_decode_step(cuda_dev, Lk, masked, t_max):
+    """Lq = 1 (the generation step) runs a SIMT kernel over the K/V cache: against fp32 softmax attention, with a
+    key-padding mask, a cache whose batch stride exceeds Lk rows, and one fully masked row."""
+    from sct_gan_b200 import kernels as kn
+
+    B, H, dh = 5, 8, 96
+    d = H * dh
+    g = torch.Generator(device="cuda").manual_seed(Lk)
+    q = torch.randn(B, d, device="cuda", generator=g).to(BF16)
+    rows = t_max if t_max else Lk
+    cache = torch.randn(B, rows, 2 * d, device="cuda", generator=g).to(BF16)
+    kpm = None
+    if masked:
+        lens = torch.randint(1, Lk + 1, (B,), device="cuda", generator=g)
+        lens[0] = 0  # every key masked: the output row is zero
+        kpm = (torch.arange(Lk, device="cuda")[None, :] >= lens[:, None]).contiguous()
+    flat = cache.view(B * rows, 2 * d)
+    o, lse2 = kn.attn_fwd(q, flat[:, :d], flat[:, d:], B, H, 1, Lk, kpm=kpm, causal=False,
+                          kv_batch_stride=rows * 2 * d if t_max else 0)
+    kf = cache[:, :Lk, :d].float().reshape(B, Lk, H, dh).permute(0, 2, 1, 3)
+    vf = cache[:, :Lk, d:].float().reshape(B, Lk, H, dh).permute(0, 2, 1, 3)
+    qf = q.float().reshape(B, 1, H, dh).permute(0, 2, 1, 3)
+    sc = torch.einsum("bhqd,bhkd->bhqk", qf, kf) * dh ** -0.5
+    if kpm is not None:
+        sc = sc.masked_fill(kpm[:, None, None, :], float("-inf"))
+    ref = torch.nan_to_num(torch.softmax(sc, -1), nan=0.0) @ vf  # [B, H, 1, dh]
+    got = o.float().reshape(B, 1, H, dh).permute(0, 2, 1, 3)
+    assert (got - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+    assert rel_l2(got, ref) < 5e-3
+    if masked:
+        assert torch.all(o[0] == 0) and torch.isinf(lse2[0]).all()
+    ok = slice(1, None) if masked else slice(None)
+    ref_lse = torch.logsumexp(sc, -1)[ok, :, 0] * 1.4426950408889634
+    assert (lse2[ok, :, 0] - ref_lse).abs().max().item() < 1e-2
 
 
 def test_attention_dropout_consistency(cuda_dev):
