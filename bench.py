@@ -161,14 +161,14 @@ def run_reference_arm(args):
     sec, toks, threads = cpu_reference_step_time(sB, sS, sP, max(1, min(args.steps, 40)), max(0, min(args.warmup, 5)))
     v = toks / sec
     sample = f"{sB} contract(s) of the workload (S=P=T={sS}) per step, fp32, {threads} host threads, dropout off"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(), "sample": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def workload_name():
@@ -179,7 +179,29 @@ def workload_name():
 
 
 # ------------------------------------------------------------------------------------------------
+_RESULT_OUT = None
+
+
+def emit(obj):
+    """The result line goes to the process's ORIGINAL stdout, alone (see claim_stdout)."""
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
+def claim_stdout():
+    """stdout must carry ONE JSON line, but native libraries write there too (NCCL prints its version banner on file
+    descriptor 1 whatever NCCL_DEBUG_FILE says): keep a private handle on the real stdout for the result and point
+    fd 1 at stderr for everybody else."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
@@ -243,7 +265,7 @@ def main():
         trainer.train_step(batch, n_lines=n_lines)
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
-        print(json.dumps({"ncu_step": "done", "launches_per_step_through_cabi": _lib.Stats.launches // (W + 1)}))
+        emit({"ncu_step": "done", "launches_per_step_through_cabi": _lib.Stats.launches // (W + 1)})
         return
     if args.torch_profile:
         from torch.profiler import ProfilerActivity, profile
@@ -360,7 +382,7 @@ def main():
                "sample": f"1 contract of the workload (S=P=T={S}) per step, full step incl. backward/clips/AdamW, fp32, "
                          f"1 warm-up + 4 timed steps, {sec:.1f} s/step"}
     if rank == 0:
-        print(json.dumps({
+        emit({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
@@ -371,7 +393,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu,
             "host_enqueue_ms_per_step": round(cpu_ms_per_step, 2), "dp_replicas_in_sync": in_sync,
-        }))
+        })
     if world > 1:
         # Tearing the NCCL communicator down while captured graphs still reference its collectives hangs
         # (seen on 2 GPUs): drain the device, make sure every rank got here, then leave without the destructor.
