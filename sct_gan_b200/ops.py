@@ -434,7 +434,30 @@ class VocabCE(torch.autograd.Function):
         return (dh.float() * g).to(BF16), dw * g, (db * g) if ctx.has_bias else None, None, None, None, None
 
 
-def vocab_ce(h, w_f32, bias, w_bf16, targets, n_valid, chunk_rows=4096):
+def _vocab_chunk_rows(rows, d, V, device):
+    """Rows per chunk of the vocab projection.  The dgrad GEMM of a chunk (dH = dLogits W: K = V, only d / 256 column
+    tiles) has ceil(chunk / 256) * ceil(d / 256) work items for the SMs / 2 CTA pairs: 4096-row chunks fill 48 of 74
+    pairs for a full wave each (8 waves for 32768 rows), 5464-row chunks fill 66 of 74 (6 waves).  Pick the chunk
+    count with the fewest dgrad waves overall, the scratch capped at 1 GiB; ties go to fewer chunks (each one
+    reduce-adds the whole [V, d] weight gradient)."""
+    units = max(1, torch.cuda.get_device_properties(device).multi_processor_count // 2)
+    ld = (V + 7) // 8 * 8
+    n_tiles = (d + 255) // 256
+    best = None
+    for c in range(1, 129):
+        cr = ((rows + c - 1) // c + 7) // 8 * 8
+        if cr * ld * 2 > (1 << 30) and c < 128:
+            continue
+        waves = ((cr + 255) // 256 * n_tiles + units - 1) // units
+        cost = (waves * c, c)
+        if best is None or cost < best[0]:
+            best = (cost, cr)
+    return best[1]
+
+
+def vocab_ce(h, w_f32, bias, w_bf16, targets, n_valid, chunk_rows=None):
+    if chunk_rows is None:
+        chunk_rows = _vocab_chunk_rows(h.shape[0], h.shape[1], w_bf16.shape[0], h.device)
     return VocabCE.apply(h, w_f32, bias, w_bf16, targets, n_valid, chunk_rows)
 
 
