@@ -300,7 +300,22 @@ class SmartContractTransformer(nn.Module):
         pe[:, 1::2] = torch.cos(pos * div)
         return pe
 
-    def _line_heads(self, memory, token_to_line, n_lines=None):
+    def _type_processors(self, spec):
+        """The per-type heads of model.py:741-755 (`vuln_type_processor[t]` = Linear(d/2, d/4) -> GELU -> Dropout(0.1)
+        -> Linear(d/4, 1), one per vulnerability type) evaluated together: the first layers are one linear with the
+        weights concatenated, the second layers a weighted sum per type — ~10 kernels per pass instead of ~25 per
+        type (the [B, lines, .] tensors are tiny: launch count is what they cost)."""
+        procs = self.vuln_type_processor
+        T = len(procs)
+        w1 = torch.cat([p[0].weight for p in procs], dim=0)          # [T * d/4, d/2]
+        b1 = torch.cat([p[0].bias for p in procs], dim=0)            # [T * d/4]
+        w2 = torch.cat([p[3].weight for p in procs], dim=0)          # [T, d/4]
+        b2 = torch.cat([p[3].bias for p in procs], dim=0)            # [T]
+        h = F.dropout(F.gelu(F.linear(spec, w1, b1)), procs[0][2].p, self.training)
+        h = h.view(*spec.shape[:-1], T, -1)
+        return (h * w2.to(h.dtype)).sum(dim=-1) + b2.to(h.dtype)
+
+    def _line_heads(self, memory, token_to_line, n_lines=None, mem_b=None):
         """model.py:480-759 with the two Python loops (batch x lines, lines x types) batched: every line
         goes through the same weights, so [B, L, .] tensors give the same result.  `n_lines` (=
         token_to_line.max() + 1, model.py:484) may be passed by a caller that already knows it on the host;
@@ -311,11 +326,19 @@ class SmartContractTransformer(nn.Module):
             if n_lines is None:
                 n_lines = int(t2l.max().item()) + 1
             idx = torch.where((t2l >= 0) & (t2l < n_lines), t2l, torch.full_like(t2l, n_lines)).long()
-            sums = torch.zeros(B, n_lines + 1, d, device=memory.device, dtype=memory.dtype)
-            sums.scatter_add_(1, idx.unsqueeze(-1).expand(-1, -1, d), memory)
-            cnt = torch.zeros(B, n_lines + 1, device=memory.device, dtype=memory.dtype)
-            cnt.scatter_add_(1, idx, torch.ones_like(idx, dtype=memory.dtype))
-            sums, cnt = sums[:, :n_lines], cnt[:, :n_lines].unsqueeze(-1)
+            if mem_b is not None and memory.is_cuda:
+                # per-line sums as a batched matmul with the 0/1 line-assignment matrix on the bf16 copy of the memory
+                # (tensor cores, fp32 accumulation; the heads below run in bf16 anyway) instead of a 25 M-element atomic
+                # scatter-add and its gather / index_put backward
+                assign = (idx.unsqueeze(1) == torch.arange(n_lines, device=idx.device).view(1, -1, 1))  # [B, lines, S]
+                cnt = assign.sum(dim=2, keepdim=True).to(memory.dtype)
+                sums = torch.bmm(assign.to(mem_b.dtype), mem_b.view(B, S, d)).to(memory.dtype)
+            else:
+                sums = torch.zeros(B, n_lines + 1, d, device=memory.device, dtype=memory.dtype)
+                sums.scatter_add_(1, idx.unsqueeze(-1).expand(-1, -1, d), memory)
+                cnt = torch.zeros(B, n_lines + 1, device=memory.device, dtype=memory.dtype)
+                cnt.scatter_add_(1, idx, torch.ones_like(idx, dtype=memory.dtype))
+                sums, cnt = sums[:, :n_lines], cnt[:, :n_lines].unsqueeze(-1)
             mean = sums / cnt.clamp(min=1.0)
             line_features = torch.where(cnt > 0, mean, self.empty_line_embedding.expand(B, n_lines, d))
             line_features = line_features + self._line_position_encoding(n_lines, memory.device)
@@ -333,7 +356,7 @@ class SmartContractTransformer(nn.Module):
             lf = lf + 0.05 * att2
             main = self.line_vulnerability_head_1(torch.cat([lf, att1], dim=-1))
             spec = self.line_specific_processor(original)
-            typed = torch.cat([proc(spec) for proc in self.vuln_type_processor], dim=-1)
+            typed = self._type_processors(spec)
             logits = (main + 0.1 * typed).float()
         n = logits.shape[1]
         if n < 1024:
@@ -369,7 +392,7 @@ class SmartContractTransformer(nn.Module):
 
         if compute_vuln_heads:
             contract_logits = self._contract_heads(memory, mem_b)
-            line_logits = self._line_heads(memory, token_to_line, n_lines)
+            line_logits = self._line_heads(memory, token_to_line, n_lines, mem_b)
         else:
             contract_logits = line_logits = None
 
