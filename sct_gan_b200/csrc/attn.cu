@@ -45,14 +45,18 @@ struct AttnParams {
   __nv_bfloat16 *dq, *dk, *dv;
   const unsigned long long* epoch;  // device-resident dropout epoch (nullable), folded into the key at run time
   uint32_t key0, key1;   // dropout stream key, mixed from (seed, offset) on the host
-  uint32_t tmask[16];    // bit i of the 16-bit drop threshold, spread to a full word
-  uint32_t thresh16;     // 0 = dropout off
+  uint32_t tmask[16];    // bit i of the kDropBits-bit drop threshold, spread to a full word
+  uint32_t thresh16;     // the threshold (kDropBits bits); 0 = dropout off
   float inv_keep;
   int write_ds;          // dK/dV kernel: also store the dS^T tiles to the workspace (for the streaming dQ kernel)
 };
 
 // ---- attention-probability dropout -------------------------------------------------------------
-// keep(b,h,q,k) <=> u16(b,h,q,k) >= thresh16.  The 16-bit uniforms of 32 consecutive keys of one query
+// kDropBits: resolution of the drop probability (p is rounded to a multiple of 2^-12: 0.3 -> 0.30005; the scale uses the
+// realised keep probability, so the expectation is exact).  Every bit is one round of the bit-sliced generator, i.e.
+// 4 integer instructions per 32 probabilities, in the forward AND in both backward kernels.
+constexpr int kDropBits = 12;
+// keep(b,h,q,k) <=> u(b,h,q,k) >= thresh.  The kDropBits-bit uniforms of 32 consecutive keys of one query
 // row are generated bit-sliced: 16 cheap xorshift-multiply words off one strong hash of (stream key,
 // b*H+h, q, k/32); a 16-step bitwise comparator (one LOP3 per word) then yields the 32 keep bits at
 // once, ~2 integer instructions per element instead of one full hash each.  Forward and the dQ kernel
@@ -83,9 +87,9 @@ __device__ __forceinline__ uint32_t keep_word(const AttnParams& p, const DropKey
   if (p.thresh16 == 0) return 0xFFFFFFFFu;
   uint32_t x = fmix32(((bh * (uint32_t)p.Lq + q) * 0x9E3779B1u) ^ dk.k0);
   x = fmix32(x ^ (kb * 0x85EBCA77u) ^ dk.k1);
-  uint32_t lt = 0u;  // lt bit = 1 <=> u16 < thresh16 (LSB-first ripple comparison)
+  uint32_t lt = 0u;  // lt bit = 1 <=> u < thresh (LSB-first ripple comparison)
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < kDropBits; ++i) {
     x = (x ^ (x >> 15)) * 0x2C1B3C6Du;
     const uint32_t nw = ~x, tm = p.tmask[i];
     lt = (nw & lt) | (tm & (nw | lt));
@@ -1193,11 +1197,13 @@ int fill_params(AttnParams& p, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int
     p.key1 = (uint32_t)(z >> 32);
   }
   p.epoch = dropout_epoch_ptr();
-  double t = (double)p_drop * 65536.0 + 0.5;
-  p.thresh16 = p_drop > 0.f ? (uint32_t)(t > 65535.0 ? 65535.0 : t) : 0u;
+  const double full = (double)(1u << kDropBits);
+  double t = (double)p_drop * full + 0.5;
+  if (t < 1.0) t = 1.0;  // p_drop > 0 drops at least 2^-kDropBits
+  p.thresh16 = p_drop > 0.f ? (uint32_t)(t > full - 1.0 ? full - 1.0 : t) : 0u;
   for (int i = 0; i < 16; ++i) p.tmask[i] = ((p.thresh16 >> i) & 1u) ? 0xFFFFFFFFu : 0u;
-  // the scale uses the realised keep probability (thresh16 / 65536 is p_drop to within 2^-17)
-  p.inv_keep = p_drop > 0.f ? (float)(65536.0 / (65536.0 - (double)p.thresh16)) : 1.0f;
+  // the scale uses the realised keep probability (thresh / 2^kDropBits is p_drop to within 2^-(kDropBits+1))
+  p.inv_keep = p_drop > 0.f ? (float)(full / (full - (double)p.thresh16)) : 1.0f;
   p.write_ds = 0;
   p.lse2 = nullptr; p.dvec = nullptr; p.o = nullptr; p.dq = p.dk = p.dv = nullptr;
   p.ldo = p.ldq_out = p.ldkv_out = 0;
