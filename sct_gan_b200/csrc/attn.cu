@@ -427,10 +427,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // =================================================================================================
 // decode step (Lq = 1, inference): one block per (head, batch) streams that head's K and V rows once — the op is a
 // pure read of the KV cache (2 * Lk * 192 B per block), so it is written as a SIMT stream, not as 128-row tensor-core
-// tiles of which one row would be real.  Eight lanes share a key row (24 bytes = 12 head dims each, so a warp reads
-// four whole 192-byte rows per load instruction: coalesced); each 8-lane group keeps a private online softmax
-// (running max, sum, 12 output accumulators per lane) over keys g, g + 64, ..., and the 64 groups of the block are
-// rescaled to the common maximum and folded through shared memory at the end.
+// tiles of which one row would be real.  Four lanes share a key row (48 bytes = 24 head dims = three 16-byte loads
+// each, so a warp reads eight whole 192-byte rows per load instruction: coalesced); each 4-lane group keeps a private
+// online softmax (running max, sum, 24 output accumulators per lane) over keys g, g + 32, ..., and the groups of the
+// block are rescaled to the common maximum and folded through shared memory at the end.
 // =================================================================================================
 template <int DEC_THREADS>
 __global__ void __launch_bounds__(DEC_THREADS)
@@ -438,63 +438,72 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __n
                    const __nv_bfloat16* __restrict__ v, long long ldkv, long long kv_bs, __nv_bfloat16* __restrict__ o,
                    long long ldo, float* __restrict__ lse2, const uint8_t* __restrict__ kpm, int H, int Lk,
                    float scale_log2) {
-  constexpr int DEC_GROUPS = DEC_THREADS / 8;
+  constexpr int LPK = 4;             // lanes per key row: 48 bytes = 24 head dims = three 16-byte loads each
+  constexpr int DPL = DH / LPK;      // head dims per lane
+  constexpr int DEC_GROUPS = DEC_THREADS / LPK;
   __shared__ float part[DEC_GROUPS][DH];
   __shared__ float ms[DEC_GROUPS], ls[DEC_GROUPS];
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-  const int g = tid >> 3, j = tid & 7;  // key group, 12-dim slice of the head
-  const unsigned gmask = 0xFFu << (tid & 24);
-  float qr[12];
+  const int g = tid / LPK, j = tid % LPK;  // key group, slice of the head
+  const unsigned gmask = 0xFu << (tid & 28);
+  float qr[DPL];
   {
-    const uint2* qp = reinterpret_cast<const uint2*>(q + (long long)b * ldq + h * DH + j * 12);
+    const uint4* qp = reinterpret_cast<const uint4*>(q + (long long)b * ldq + h * DH + j * DPL);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const uint2 u = qp[c];
-      const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y);
-      qr[4 * c] = f0.x * scale_log2;  // scores come out in the log2 domain
-      qr[4 * c + 1] = f0.y * scale_log2;
-      qr[4 * c + 2] = f1.x * scale_log2;
-      qr[4 * c + 3] = f1.y * scale_log2;
+    for (int c = 0; c < DPL / 8; ++c) {
+      const uint4 u = qp[c];
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16(w[i]);
+        qr[8 * c + 2 * i] = f.x * scale_log2;  // scores come out in the log2 domain
+        qr[8 * c + 2 * i + 1] = f.y * scale_log2;
+      }
     }
   }
-  const __nv_bfloat16* kb = k + (long long)b * kv_bs + h * DH + j * 12;
-  const __nv_bfloat16* vb = v + (long long)b * kv_bs + h * DH + j * 12;
+  const __nv_bfloat16* kb = k + (long long)b * kv_bs + h * DH + j * DPL;
+  const __nv_bfloat16* vb = v + (long long)b * kv_bs + h * DH + j * DPL;
   const uint8_t* mrow = kpm ? kpm + (long long)b * Lk : nullptr;
   float m = -INFINITY, l = 0.f;
-  float acc[12];
+  float acc[DPL];
 #pragma unroll
-  for (int i = 0; i < 12; ++i) acc[i] = 0.f;
+  for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
 #pragma unroll 2
   for (int kk = g; kk < Lk; kk += DEC_GROUPS) {
-    if (mrow != nullptr && mrow[kk] != 0) continue;  // uniform inside the 8-lane group
-    const uint2* krow = reinterpret_cast<const uint2*>(kb + (long long)kk * ldkv);
-    const uint2* vrow = reinterpret_cast<const uint2*>(vb + (long long)kk * ldkv);
-    uint2 kr[3], vr[3];
+    if (mrow != nullptr && mrow[kk] != 0) continue;  // uniform inside the group
+    const uint4* krow = reinterpret_cast<const uint4*>(kb + (long long)kk * ldkv);
+    const uint4* vrow = reinterpret_cast<const uint4*>(vb + (long long)kk * ldkv);
+    uint4 kr[DPL / 8], vr[DPL / 8];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) kr[c] = krow[c];
+    for (int c = 0; c < DPL / 8; ++c) kr[c] = krow[c];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) vr[c] = vrow[c];
+    for (int c = 0; c < DPL / 8; ++c) vr[c] = vrow[c];
     float sc = 0.f;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float2 f0 = unpack_bf16(kr[c].x), f1 = unpack_bf16(kr[c].y);
-      sc += f0.x * qr[4 * c] + f0.y * qr[4 * c + 1] + f1.x * qr[4 * c + 2] + f1.y * qr[4 * c + 3];
+    for (int c = 0; c < DPL / 8; ++c) {
+      const uint32_t w[4] = {kr[c].x, kr[c].y, kr[c].z, kr[c].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16(w[i]);
+        sc += f.x * qr[8 * c + 2 * i] + f.y * qr[8 * c + 2 * i + 1];
+      }
     }
-    sc += __shfl_xor_sync(gmask, sc, 1);  // the four groups of a warp run different trip counts: group-wide mask
+    sc += __shfl_xor_sync(gmask, sc, 1);  // the groups of a warp run different trip counts: group-wide mask
     sc += __shfl_xor_sync(gmask, sc, 2);
-    sc += __shfl_xor_sync(gmask, sc, 4);
     const float m_new = fmaxf(m, sc);
     const float alpha = exp2f(m - m_new);  // first key: exp2(-inf) = 0
     const float e = exp2f(sc - m_new);
     l = l * alpha + e;
     m = m_new;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float2 f0 = unpack_bf16(vr[c].x), f1 = unpack_bf16(vr[c].y);
-      acc[4 * c] = acc[4 * c] * alpha + e * f0.x;
-      acc[4 * c + 1] = acc[4 * c + 1] * alpha + e * f0.y;
-      acc[4 * c + 2] = acc[4 * c + 2] * alpha + e * f1.x;
-      acc[4 * c + 3] = acc[4 * c + 3] * alpha + e * f1.y;
+    for (int c = 0; c < DPL / 8; ++c) {
+      const uint32_t w[4] = {vr[c].x, vr[c].y, vr[c].z, vr[c].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16(w[i]);
+        acc[8 * c + 2 * i] = acc[8 * c + 2 * i] * alpha + e * f.x;
+        acc[8 * c + 2 * i + 1] = acc[8 * c + 2 * i + 1] * alpha + e * f.y;
+      }
     }
   }
   if (j == 0) ms[g] = m;
@@ -505,7 +514,7 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __n
   const float rs = (m == -INFINITY) ? 0.f : exp2f(m - mx);  // this group's weight (0 if it saw no key)
   if (j == 0) ls[g] = l * rs;
 #pragma unroll
-  for (int i = 0; i < 12; ++i) part[g][j * 12 + i] = acc[i] * rs;
+  for (int i = 0; i < DPL; ++i) part[g][j * DPL + i] = acc[i] * rs;
   __syncthreads();
   if (tid < DH) {
     float lt = 0.f, st = 0.f;
@@ -1252,24 +1261,20 @@ int32_t sct_attn_fwd_strided(const void* q, int64_t ldq, const void* k, const vo
   if (use_dec && Lq == 1 && p_drop == 0.f) {  // decode step: SIMT stream over the KV cache
     SCT_CHECK(ldq % 8 == 0 && ldkv % 8 == 0, "row pitches must be multiples of 8");
     const long long kv_bs = kv_batch_stride > 0 ? kv_batch_stride : Lk * ldkv;
-    // more key groups per block for longer caches (measured at B = 128, H = 8: 128 threads win up to ~1024 cached rows, 512 threads beyond)
+    // more key groups per block for longer caches (measured at B = 128, H = 8: 128 threads win up to ~1024 cached rows)
     static int dec_threads = 0;
     if (dec_threads == 0) {
       const char* e = getenv("SCT_ATTN_DECODE_THREADS");
       dec_threads = e ? atoi(e) : -1;
     }
-    const int nt = dec_threads > 0 ? dec_threads : (Lk <= 1024 ? 128 : 512);
+    const int nt = dec_threads > 0 ? dec_threads : (Lk <= 1024 ? 128 : 256);
     const dim3 grid((unsigned)H, (unsigned)B);
     if (nt == 128)
       attn_decode_kernel<128><<<grid, 128, 0, (cudaStream_t)stream>>>(
           (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv, kv_bs,
           (__nv_bfloat16*)o, ldo, lse2, kpm, (int)H, (int)Lk, p.scale_log2);
-    else if (nt == 256)
-      attn_decode_kernel<256><<<grid, 256, 0, (cudaStream_t)stream>>>(
-          (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv, kv_bs,
-          (__nv_bfloat16*)o, ldo, lse2, kpm, (int)H, (int)Lk, p.scale_log2);
     else
-      attn_decode_kernel<512><<<grid, 512, 0, (cudaStream_t)stream>>>(
+      attn_decode_kernel<256><<<grid, 256, 0, (cudaStream_t)stream>>>(
           (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv, kv_bs,
           (__nv_bfloat16*)o, ldo, lse2, kpm, (int)H, (int)Lk, p.scale_log2);
     SCT_LAUNCH_CHECK();
