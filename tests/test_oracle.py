@@ -181,6 +181,37 @@ def test_line_heads_vectorised_match_oracle_loops():
         assert (m._line_heads(memory, None) - O.line_heads(sd, cfg, memory, None, torch.float32)).abs().max().item() < 1e-4
 
 
+def test_type_processors_batched_equal_per_module_loop():
+    """model._type_processors (one concatenated linear + weighted sums) == the reference's per-type Sequential loop
+    (model.py:741-755), in eval mode and fp32."""
+    from sct_gan_b200 import SmartContractTransformer
+
+    torch.manual_seed(5)
+    m = SmartContractTransformer(d_model=96, nhead=8, num_encoder_layers=1, num_decoder_layers=1, dim_feedforward=64,
+                                 max_length=32, vocab_size=50).eval()
+    with torch.no_grad():
+        for p in m.vuln_type_processor.parameters():
+            p.normal_(0.0, 0.3)
+        spec = torch.randn(3, 7, 48)
+        loop = torch.cat([proc(spec) for proc in m.vuln_type_processor], dim=-1)
+        assert (m._type_processors(spec) - loop).abs().max().item() < 1e-5
+
+
+def test_vocab_chunk_rows_fills_dgrad_waves(monkeypatch):
+    """ops._vocab_chunk_rows: fewest dgrad waves for the 74 CTA pairs of a B200, scratch capped at 1 GiB."""
+    from sct_gan_b200 import ops
+
+    class Props:
+        multi_processor_count = 148
+
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda dev: Props())
+    assert ops._vocab_chunk_rows(32768, 768, 50265, "cuda") == 5464    # 6 chunks x 66 of 74 pairs
+    assert ops._vocab_chunk_rows(4096, 768, 50265, "cuda") == 4096     # one chunk, one wave
+    assert ops._vocab_chunk_rows(200, 768, 777, "cuda") == 200
+    big = ops._vocab_chunk_rows(1 << 20, 768, 50265, "cuda")
+    assert big * 50272 * 2 <= 1 << 30 and big % 8 == 0
+
+
 def test_cabi_argument_errors_are_reported_without_a_gpu():
     """Error behaviour of the boundary: bad arguments return non-zero and leave a message in sct_last_error()
     (checked before any CUDA call, so this runs on a CPU box); the Python layer turns them into RuntimeError."""
