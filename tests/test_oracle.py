@@ -234,6 +234,12 @@ def test_cabi_argument_errors_are_reported_without_a_gpu():
     assert rc != 0 and "pitch" in _lib.last_error()
     with pytest.raises(RuntimeError, match="sct_colsum_bf16 failed"):
         _lib.call("sct_colsum_bf16", p, 7, p, 4, 8, 1.0, None)
+    # attention backward with a caller-owned workspace: the size contract is checked before anything is launched
+    need = lib.sct_attn_bwd_workspace_bytes(2, 8, 100, 300)
+    assert need == 2 * 8 * 300 * 128 * 2  # [B*H][Lk][Lq rounded up to 64] bf16
+    rc = lib.sct_attn_bwd_ws(p, 768, p, p, 768, p, p, 768, p, p, p, 768, p, p, 768, None, 2, 8, 100, 300, 96, 0, 0.1,
+                             0.0, 0, 0, p, need - 1, None)
+    assert rc != 0 and "workspace too small" in _lib.last_error()
 
 
 def test_eval_after_training_recasts_weight_shadows():
