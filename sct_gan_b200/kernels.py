@@ -269,7 +269,7 @@ def attn_fwd(q, k, v, B, H, Lq, Lk, kpm=None, causal=False, scale=None, p_drop=0
 
 
 def attn_bwd(q, k, v, o, d_o, lse2, B, H, Lq, Lk, dq, dk, dv, kpm=None, causal=False, scale=None,
-             p_drop=0.0, seed=0, offset=0, head_dim=96):
+             p_drop=0.0, seed=0, offset=0, head_dim=96, ws_slot=0):
     """dq [B*Lq, ld], dk/dv [B*Lk, ld] are written (2-D bf16 views, e.g. slices of a packed buffer)."""
     q, ldq = _rows2d(q, BF16, "q")
     k, ldk = _rows2d(k, BF16, "k")
@@ -283,7 +283,7 @@ def attn_bwd(q, k, v, o, d_o, lse2, B, H, Lq, Lk, dq, dk, dv, kpm=None, causal=F
     if scale is None:
         scale = head_dim ** -0.5
     dvec = torch.empty((B, H, Lq), dtype=F32, device=q.device)
-    ws, ws_bytes = _attn_workspace(B, H, Lq, Lk, q.device)
+    ws, ws_bytes = _attn_workspace(B, H, Lq, Lk, q.device, ws_slot)
     _lib.Stats.annotate(10.0 * B * H * Lq * Lk * head_dim * (0.5 if causal else 1.0))
     _lib.call("sct_attn_bwd_ws", _ptr(q), ldq, _ptr(k), _ptr(v), ldk, _ptr(o), _ptr(d_o), o.stride(0),
               _ptr(lse2), _ptr(dvec), _ptr(dq), lddq, _ptr(dk), _ptr(dv), lddk,
@@ -292,17 +292,40 @@ def attn_bwd(q, k, v, o, d_o, lse2, B, H, Lq, Lk, dq, dk, dv, kpm=None, causal=F
               _stream())
 
 
-# dS^T workspace of the attention backward: one grow-only buffer per device (the calls of a step run back to back on
-# one stream).  Outgrown buffers are kept alive because captured CUDA graphs may still point at them.
+# dS^T workspace of the attention backward: one grow-only buffer per (device, slot); the calls of a step run back to
+# back on one stream, work that runs concurrently on a side stream (the vulnerability heads) uses a slot of its own,
+# chosen at forward time (`ws_slot`).  Outgrown buffers are kept alive because captured CUDA graphs may still point at
+# them.
 _ATTN_WS = {}
+_WS_SLOT = 0
+
+
+def current_ws_slot() -> int:
+    return _WS_SLOT
+
+
+class use_ws_slot:
+    """`with use_ws_slot(1): ...` — attention ops recorded inside draw their backward workspace from slot 1."""
+
+    def __init__(self, slot):
+        self.slot = slot
+
+    def __enter__(self):
+        global _WS_SLOT
+        self.prev, _WS_SLOT = _WS_SLOT, self.slot
+
+    def __exit__(self, *exc):
+        global _WS_SLOT
+        _WS_SLOT = self.prev
+
 _ATTN_WS_LIMIT = int(os.environ.get("SCT_ATTN_BWD_WS_MB", "16384")) << 20  # 0 disables (recomputing dQ kernel)
 
 
-def _attn_workspace(B, H, Lq, Lk, device):
+def _attn_workspace(B, H, Lq, Lk, device, slot=0):
     need = int(_lib.load().sct_attn_bwd_workspace_bytes(B, H, Lq, Lk))
     if need > _ATTN_WS_LIMIT:
         return None, 0
-    ent = _ATTN_WS.setdefault(device, [])
+    ent = _ATTN_WS.setdefault((device, slot), [])
     if not ent or ent[-1].numel() < need:
         assert not torch.cuda.is_current_stream_capturing(), \
             "attention workspace must be sized by an eager step before CUDA-graph capture"

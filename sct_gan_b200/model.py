@@ -20,6 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
+from .kernels import use_ws_slot as kn_slot
 from .ops import BF16, F32
 
 
@@ -130,6 +131,9 @@ class SmartContractTransformer(nn.Module):
         for p in self.feature_fusion.parameters():  # model.py:285-286: clamp parameter grads to +-1
             p.register_hook(self.hook_fn)
         self._shadow = ops.ShadowCache()
+        self._heads_stream = None
+        # training: vulnerability heads on a side stream, overlapped with the decoder (SCT_HEADS_SIDE_STREAM=0: A/B timing)
+        self.heads_side_stream = __import__("os").environ.get("SCT_HEADS_SIDE_STREAM", "1") != "0"
         self._step_counter = 0
         self.heads_autocast = True  # bf16 matmuls for the PyTorch vulnerability heads on the GPU
 
@@ -390,7 +394,23 @@ class SmartContractTransformer(nn.Module):
             mem, mem_b = self._ast_fuse(mem, mem_b, ast_b, B, S, P, ast_kpm)
         memory = mem.view(B, S, d)
 
-        if compute_vuln_heads:
+        heads_stream = None
+        if compute_vuln_heads and self.training and self.heads_side_stream and target_ids is not None:
+            # The vulnerability heads are ~450 tiny kernels on [B, .] / [B, lines, .] rows (3 ms of launch latency, a few
+            # SMs): run them on a side stream next to the decoder.  Autograd runs a node's backward on the stream of its
+            # forward, so their backward overlaps with the decoder's as well (inside the step's CUDA graph the two
+            # branches are independent until the encoder needs d(memory)).  Joined before the dict is returned.
+            main = torch.cuda.current_stream()
+            if self._heads_stream is None:
+                self._heads_stream = torch.cuda.Stream(device=memory.device)
+            heads_stream = self._heads_stream
+            heads_stream.wait_stream(main)
+            with torch.cuda.stream(heads_stream), kn_slot(1):
+                contract_logits = self._contract_heads(memory, mem_b)
+                line_logits = self._line_heads(memory, token_to_line, n_lines, mem_b)
+            mem.record_stream(heads_stream)
+            mem_b.record_stream(heads_stream)
+        elif compute_vuln_heads:
             contract_logits = self._contract_heads(memory, mem_b)
             line_logits = self._line_heads(memory, token_to_line, n_lines, mem_b)
         else:
@@ -420,6 +440,11 @@ class SmartContractTransformer(nn.Module):
             with torch.no_grad():
                 logits = ops.linear(h.detach(), ol.weight, ol.bias, self._w(ol.weight))
             out["logits"] = logits.view(B, T, -1)[:, :-1, :].float().reshape(B * (T - 1), -1)
+        if heads_stream is not None:  # join: whoever consumes the logits does so on the caller's stream
+            main = torch.cuda.current_stream()
+            main.wait_stream(heads_stream)
+            contract_logits.record_stream(main)
+            line_logits.record_stream(main)
         out["contract_vulnerability_logits"] = contract_logits
         out["line_vulnerability_logits"] = line_logits
         out["encoder_output"] = memory.mean(dim=1)

@@ -322,6 +322,7 @@ class SelfAttention(torch.autograd.Function):
                               p_drop=p_drop, seed=seed, offset=off, head_dim=d // H)
         ctx.save_for_backward(qkv, o, lse2, kpm if kpm is not None else torch.empty(0))
         ctx.cfg = (B, H, L, causal, p_drop, seed, off, kpm is not None)
+        ctx.ws_slot = kn.current_ws_slot()
         return o
 
     @staticmethod
@@ -332,7 +333,7 @@ class SelfAttention(torch.autograd.Function):
         dqkv = torch.empty_like(qkv)
         kn.attn_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], o, d_o.contiguous(), lse2, B, H, L, L,
                     dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:], kpm=kpm if has_kpm else None, causal=causal,
-                    p_drop=p_drop, seed=seed, offset=off, head_dim=d // H)
+                    p_drop=p_drop, seed=seed, offset=off, head_dim=d // H, ws_slot=ctx.ws_slot)
         return dqkv, None, None, None, None, None, None
 
 
@@ -347,6 +348,7 @@ class CrossAttention(torch.autograd.Function):
                               seed=seed, offset=off, head_dim=d // H)
         ctx.save_for_backward(q, kv, o, lse2, kpm if kpm is not None else torch.empty(0))
         ctx.cfg = (B, H, Lq, Lk, p_drop, seed, off, kpm is not None)
+        ctx.ws_slot = kn.current_ws_slot()
         return o
 
     @staticmethod
@@ -358,7 +360,7 @@ class CrossAttention(torch.autograd.Function):
         dkv = torch.empty_like(kv)
         kn.attn_bwd(q, kv[:, :d], kv[:, d:], o, d_o.contiguous(), lse2, B, H, Lq, Lk, dq, dkv[:, :d], dkv[:, d:],
                     kpm=kpm if has_kpm else None, causal=False, p_drop=p_drop, seed=seed, offset=off,
-                    head_dim=d // H)
+                    head_dim=d // H, ws_slot=ctx.ws_slot)
         return dq, dkv, None, None, None, None, None, None
 
 

@@ -152,24 +152,38 @@ class OverlappedGradReducer:
     def __init__(self, params, world, group=None, bucket_bytes=32 << 20):
         self.world, self.group, self.bucket_bytes = world, group, bucket_bytes
         self.bucket, self.size, self.works = [], 0, []
+        self.streams = {}  # CUDA streams gradients were produced on (the vulnerability heads run on a side stream)
         self.handles = [p.register_post_accumulate_grad_hook(self._hook) for p in params if p.requires_grad]
+
+    def _launch(self):
+        """A bucket may hold gradients from several streams, and the collective only orders itself after the stream
+        it is launched from: make that stream wait for the others first."""
+        if self.bucket[0].grad.is_cuda:
+            cur = torch.cuda.current_stream()
+            for sid, s in self.streams.items():
+                if sid != cur.cuda_stream:
+                    cur.wait_stream(s)
+        self.works.append(_launch_bucket(self.bucket, self.world, self.group))
+        self.bucket, self.size = [], 0
 
     def _hook(self, p):
         if p.grad is None:
             return
+        if p.grad.is_cuda:
+            cur = torch.cuda.current_stream()
+            self.streams.setdefault(cur.cuda_stream, cur)
         self.bucket.append(p)
         self.size += p.grad.numel() * p.grad.element_size()
         if self.size >= self.bucket_bytes:
-            self.works.append(_launch_bucket(self.bucket, self.world, self.group))
-            self.bucket, self.size = [], 0
+            self._launch()
 
     def finish(self):
         if self.bucket:
-            self.works.append(_launch_bucket(self.bucket, self.world, self.group))
-            self.bucket, self.size = [], 0
+            self._launch()
         for w in self.works:
             _finish_bucket(w, self.world)
         self.works = []
+        self.streams = {}  # per step: a captured step runs on other streams than the eager warm-up before it
 
 
 class FusedClipAdamW:
