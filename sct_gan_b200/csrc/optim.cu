@@ -8,7 +8,8 @@
 //   2. opt_clip_adamw   clip coefficients from those three numbers (the scopes nest: the second and third clip see
 //                       gradients already scaled by the first), skip predicate, AdamW on fp32 master weights
 //   3. opt_finish       per-tensor step counters, reported gradient norm and the stepped flag
-// HBM-bound: 4 B/param for pass 1, 28 B/param (read g, p, m, v; write p, m, v) for pass 2.
+// HBM-bound: 4 B/param for pass 1, 28 B/param (read g, p, m, v; write p, m, v) for pass 2, + 2 B/param for the bf16
+// weight shadow the next forward's GEMMs read (written here instead of re-cast from the fp32 weights: -4 B/param).
 #include <math.h>
 
 #include "../../include/sct_b200.h"
@@ -20,7 +21,7 @@ namespace {
 constexpr int kChunk = 32768;  // elements per block
 constexpr int kThreads = 256;
 
-struct OptTensor {  // mirrors sct_opt_tensor in the header (64 bytes)
+struct OptTensor {  // mirrors sct_opt_tensor in the header (80 bytes)
   float* p;
   const float* g;
   float* m;
@@ -31,8 +32,10 @@ struct OptTensor {  // mirrors sct_opt_tensor in the header (64 bytes)
   float wd;
   int seg;
   int pad;
+  __nv_bfloat16* shadow;  // nullable: bf16 copy of p for the tensor-core GEMMs, refreshed with the update
+  long long pad2;
 };
-static_assert(sizeof(OptTensor) == 64, "table layout");
+static_assert(sizeof(OptTensor) == 80, "table layout");
 
 struct ClipInfo {
   float c_rest, c_disc, c_vuln, total;
@@ -138,6 +141,12 @@ opt_clip_adamw_kernel(const OptTensor* __restrict__ tab, const int2* __restrict_
       *reinterpret_cast<float4*>(t.p + i) = p;
       *reinterpret_cast<float4*>(t.m + i) = m;
       *reinterpret_cast<float4*>(t.v + i) = v;
+      if (t.shadow != nullptr) {
+        uint2 u;
+        u.x = pack_bf16(p.x, p.y);
+        u.y = pack_bf16(p.z, p.w);
+        *reinterpret_cast<uint2*>(t.shadow + i) = u;
+      }
     }
   } else {
     for (long long i = base + threadIdx.x; i < end; i += kThreads) {
@@ -146,6 +155,7 @@ opt_clip_adamw_kernel(const OptTensor* __restrict__ tab, const int2* __restrict_
       t.p[i] = p;
       t.m[i] = m;
       t.v[i] = v;
+      if (t.shadow != nullptr) t.shadow[i] = __float2bfloat16(p);
     }
   }
 }

@@ -65,14 +65,18 @@ class DropoutRng:
 class ShadowCache:
     """bf16 copies of fp32 parameters for the tensor-core GEMMs (private, non-persistent).
 
-    Fused optimisers (torch's and csrc/optim.cu) update parameters without bumping Tensor._version, so a
-    training forward re-casts every weight it touches once per pass (~1.2 GB of traffic for the full model) and
-    marks the copy as not reusable; inference re-casts such a copy on first use and then keeps it until the
-    parameter's version or storage changes (load_state_dict, .to()).  Buffers are reused, so their addresses are
-    stable across casts (captured CUDA graphs keep reading the right memory)."""
+    Fused optimisers (torch's and csrc/optim.cu) update parameters without bumping Tensor._version, so a training
+    forward cannot tell from the version whether a copy is stale.  Two ways a copy is known to be current:
+      * the library's own optimiser kernel rewrote it together with the weight (`mark_synced`, after every
+        `sct_clip_adamw_step` that was given the copy's address): the next forward uses it as is — no cast pass;
+      * it was cast earlier in the same pass.
+    Otherwise a training forward re-casts the weight on first use (once per pass), and inference re-casts a copy made
+    during training on first use and then keeps it until the parameter's version or storage changes
+    (load_state_dict, .to()).  Buffers are reused, so their addresses are stable across casts (captured CUDA graphs and
+    the optimiser's pointer table keep referring to the right memory)."""
 
     def __init__(self):
-        self._store = {}  # id(param) -> [version, bf16 buffer, data_ptr, reusable_in_eval]
+        self._store = {}  # id(param) -> [version, bf16 buffer, data_ptr, reusable_in_eval, synced_by_optimiser]
         self.training = False
         self._fresh = set()
 
@@ -80,11 +84,18 @@ class ShadowCache:
         self.training = refresh
         self._fresh.clear()
 
+    def _entry(self, p):
+        ent = self._store.get(id(p))
+        if ent is not None and ent[1].device == p.device and ent[2] == p.data_ptr() and ent[1].shape == p.shape:
+            return ent
+        return None
+
     def get(self, p: torch.Tensor) -> torch.Tensor:
         key = id(p)
-        ent = self._store.get(key)
-        same = ent is not None and ent[1].device == p.device and ent[2] == p.data_ptr() and ent[1].shape == p.shape
-        if same:
+        ent = self._entry(p)
+        if ent is not None:
+            if ent[4] and ent[0] == p._version:
+                return ent[1]
             if self.training:
                 if key in self._fresh:
                     return ent[1]
@@ -93,11 +104,23 @@ class ShadowCache:
         src = p.detach()
         src2 = src if src.dim() == 2 else src.view(1, -1)
         assert src2.is_contiguous()
-        buf = ent[1] if same else torch.empty(src.shape, dtype=BF16, device=p.device)
+        buf = ent[1] if ent is not None else torch.empty(src.shape, dtype=BF16, device=p.device)
         kn.cast_scale(src2, buf.view(src2.shape), 0, 1.0)
-        self._store[key] = [p._version, buf, p.data_ptr(), not self.training]
+        self._store[key] = [p._version, buf, p.data_ptr(), not self.training, False]
         self._fresh.add(key)
         return buf
+
+    def peek_ptr(self, p) -> int:
+        """Address of p's bf16 copy if it has one (for the optimiser's pointer table), else 0."""
+        ent = self._entry(p)
+        return ent[1].data_ptr() if ent is not None else 0
+
+    def mark_synced(self, params):
+        """The optimiser kernel has just rewritten the copies of `params` from the updated weights."""
+        for p in params:
+            ent = self._entry(p)
+            if ent is not None:
+                ent[0], ent[4] = p._version, True
 
     def clear(self):
         self._store.clear()

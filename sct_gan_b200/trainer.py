@@ -202,7 +202,7 @@ class FusedClipAdamW:
         if FusedClipAdamW._DT is None:
             FusedClipAdamW._DT = np.dtype([("p", "<u8"), ("g", "<u8"), ("m", "<u8"), ("v", "<u8"), ("step", "<u8"),
                                            ("numel", "<i8"), ("lr", "<f4"), ("wd", "<f4"), ("seg", "<i4"),
-                                           ("pad", "<i4")])
+                                           ("pad", "<i4"), ("shadow", "<u8"), ("pad2", "<i8")])
         self.np = np
         self.opt = optimizer
         self.max_norm = max_grad_norm
@@ -217,6 +217,7 @@ class FusedClipAdamW:
             else:
                 self.seg[p] = 0
         self._sig = None
+        self.shadows = None  # ops.ShadowCache whose bf16 weight copies the kernel keeps in step with the weights
         self._keep = []  # tables referenced by captured graphs must outlive them
         self.bufs = None
         self._eager, self._flip = [], 0
@@ -227,7 +228,7 @@ class FusedClipAdamW:
     def _alloc(self):
         """Pinned host + device buffers sized for every parameter (filled by _fill; no allocation afterwards)."""
         dev = self.all_params[0].device
-        tab_h = torch.zeros(len(self.all_params) * 64, dtype=torch.uint8).pin_memory()
+        tab_h = torch.zeros(len(self.all_params) * 80, dtype=torch.uint8).pin_memory()
         ck_h = torch.zeros((self.max_chunks, 2), dtype=torch.int32).pin_memory()
         return (tab_h, ck_h, torch.empty_like(tab_h, device=dev), torch.empty_like(ck_h, device=dev),
                 # scratch: [0:2] out2 (norm, stepped), [4:7] squared norms per clip scope, [8:8+chunks] chunk sums
@@ -262,14 +263,14 @@ class FusedClipAdamW:
                 idx = len(rows)
                 rows.append((p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
                              st["step"].data_ptr(), p.numel(), float(group["lr"]), float(group["weight_decay"]),
-                             self.seg[p], 0))
+                             self.seg[p], 0, self._shadow_ptr(p), 0))
                 for c in range((p.numel() + self.chunk - 1) // self.chunk):
                     chunks.append((idx, c))
         g0 = self.opt.param_groups[0]
         self.betas, self.eps = g0["betas"], float(g0["eps"])
         tab_h, ck_h, tab_d, ck_d, _ = self.bufs
         self.n_tensors, self.n_chunks = len(rows), len(chunks)
-        tab_h.numpy()[: self.n_tensors * 64] = np.array(rows, dtype=self._DT).view(np.uint8)
+        tab_h.numpy()[: self.n_tensors * 80] = np.array(rows, dtype=self._DT).view(np.uint8)
         ck_h.numpy()[: self.n_chunks] = np.array(chunks, dtype=np.int32)
         tab_d.copy_(tab_h, non_blocking=True)
         ck_d.copy_(ck_h, non_blocking=True)
@@ -279,8 +280,8 @@ class FusedClipAdamW:
         from . import kernels as kn
 
         capturing = torch.cuda.is_current_stream_capturing()
-        sig = tuple((p.grad.data_ptr(), g["lr"]) for g in self.opt.param_groups for p in g["params"]
-                    if p.grad is not None)
+        sig = tuple((p.grad.data_ptr(), g["lr"], self._shadow_ptr(p)) for g in self.opt.param_groups
+                    for p in g["params"] if p.grad is not None)
         if sig != self._sig or self.bufs is None:
             if not capturing:  # eager: gradients are fresh tensors every step -> refill, ping-ponging two buffer sets
                 if len(self._eager) < 2:  # so the previous step's asynchronous table upload is never overwritten
@@ -292,7 +293,12 @@ class FusedClipAdamW:
         tab_d, ck_d, scratch = self.bufs[2], self.bufs[3], self.bufs[4]
         kn.clip_adamw_step(tab_d, self.n_tensors, ck_d, self.n_chunks, loss.detach().float().reshape(1),
                            scratch[4:], scratch[0:2], self.max_norm, 0.3, 2.0, self.betas[0], self.betas[1], self.eps)
+        if self.shadows is not None:  # the kernel rewrote the bf16 shadows it was given together with the weights
+            self.shadows.mark_synced(p for g in self.opt.param_groups for p in g["params"] if p.grad is not None)
         return scratch[0].clone(), scratch[1] > 0.5
+
+    def _shadow_ptr(self, p):
+        return self.shadows.peek_ptr(p) if self.shadows is not None else 0
 
 
 class SmartContractTrainer:
@@ -354,6 +360,9 @@ class SmartContractTrainer:
         self.use_cuda_graph = use_cuda_graph and on_gpu
         self._fused_tail = FusedClipAdamW(self.optimizer, list(model.named_parameters()), use_gan, max_grad_norm) \
             if (fused_optimizer and on_gpu) else None
+        if (self._fused_tail is not None and isinstance(getattr(model, "_shadow", None), ops.ShadowCache)
+                and __import__("os").environ.get("SCT_OPT_SHADOWS", "1") != "0"):  # =0: A/B timing
+            self._fused_tail.shadows = model._shadow  # bf16 weight copies are refreshed by the optimiser kernel
         self._graphs = {}
         self.last = {}
 
