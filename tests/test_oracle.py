@@ -277,6 +277,42 @@ def test_eval_after_training_recasts_weight_shadows():
         ops.kn.cast_scale = real
 
 
+def test_weight_shadows_kept_in_step_by_the_optimiser_are_not_recast():
+    """ShadowCache + FusedClipAdamW contract (host logic): a copy the optimiser kernel rewrote (`mark_synced`) is used
+    as is by the next training and eval passes; a versioned update of the parameter invalidates it again."""
+    from sct_gan_b200 import ops
+
+    calls = []
+    real = ops.kn.cast_scale
+    ops.kn.cast_scale = lambda src, dst, col_off=0, scale=1.0: calls.append(1) or dst.copy_(src)
+    try:
+        w = torch.nn.Parameter(torch.randn(4, 8))
+        other = torch.nn.Parameter(torch.randn(2, 2))
+        sc = ops.ShadowCache()
+        assert sc.peek_ptr(w) == 0  # no copy yet: the optimiser table gets a null shadow pointer
+        sc.begin_step(refresh=True)
+        a = sc.get(w)
+        assert len(calls) == 1 and sc.peek_ptr(w) == a.data_ptr()
+        with torch.no_grad():  # what csrc/optim.cu does: weight and copy rewritten together, no version bump
+            w.data.add_(1.0)
+            a.copy_(w.detach())
+        sc.mark_synced([w, other])  # parameters without a copy are ignored
+        sc.begin_step(refresh=True)
+        assert sc.get(w).data_ptr() == a.data_ptr() and len(calls) == 1  # next training pass: no cast
+        sc.begin_step(refresh=False)
+        assert sc.get(w).data_ptr() == a.data_ptr() and len(calls) == 1  # eval: still current
+        with torch.no_grad():
+            w.mul_(2.0)  # versioned update from outside (load_state_dict, manual edit)
+        sc.begin_step(refresh=True)
+        sc.get(w)
+        assert len(calls) == 2  # stale: re-cast, and no longer marked as synced
+        sc.begin_step(refresh=True)
+        sc.get(w)
+        assert len(calls) == 3
+    finally:
+        ops.kn.cast_scale = real
+
+
 def test_vectorised_syntax_penalty_matches_reference_loops():
     """sct_gan_b200.syntax (vectorised device scan) against the oracle's restatement of the double loop of
     train.py:334-431, with a fake tokenizer (token -> small id) on id streams dense in the special tokens."""
