@@ -16,6 +16,15 @@
 // TMEM accumulator rows map 1:1 to threads (tcgen05.ld 32x32b), so the online softmax needs no
 // cross-thread reduction.  Masks are applied from the [B,Lk] key-padding bytes and the causal
 // predicate; dropout is regenerated from (seed, offset, element index).
+//
+// Kernels in this file:
+//   attn_fwd_kernel         forward, one CTA per (128-query tile, head, batch), two per SM; P returns to TMEM as the A
+//                           operand of P V; O leaves through a TMA store
+//   attn_decode_kernel      forward for Lq = 1 (generation): SIMT stream over the K/V cache
+//   attn_bwd_dvec_kernel    D = rowsum(dO * O)
+//   attn_bwd_dkdv_kernel    dK, dV per key tile (two MMA issuers, P^T in TMEM); also writes dS^T to a workspace
+//   attn_bwd_dq_ds_kernel   dQ = scale * dS K as a TMA -> tcgen05 stream over that workspace
+//   attn_bwd_dq_kernel      dQ by recomputation (workspace == NULL)
 #include <math.h>
 #include <stdlib.h>
 
