@@ -354,7 +354,7 @@ class SmartContractTrainer:
                             or "line_vuln_attention" in n or "vuln_type_attention" in n]
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
-        self.bucket_bytes = bucket_mb << 20
+        self.bucket_bytes = int(__import__("os").environ.get("SCT_DP_BUCKET_MB", bucket_mb)) << 20
         self._reducer = OverlappedGradReducer(list(model.parameters()), self.world, process_group, self.bucket_bytes) \
             if self.world > 1 else None
         self.use_cuda_graph = use_cuda_graph and on_gpu
