@@ -401,7 +401,7 @@ class SmartContractTransformer(nn.Module):
             # forward, so their backward overlaps with the decoder's as well (inside the step's CUDA graph the two
             # branches are independent until the encoder needs d(memory)).  Joined before the dict is returned.
             main = torch.cuda.current_stream()
-            if self._heads_stream is None:
+            if self._heads_stream is None or self._heads_stream.device != memory.device:
                 self._heads_stream = torch.cuda.Stream(device=memory.device)
             heads_stream = self._heads_stream
             heads_stream.wait_stream(main)
