@@ -416,6 +416,40 @@ def generate_greedy(sd, cfg, batch, n_new, dtype=torch.float32, apply_syntax_con
     return tgt, torch.stack(gaps, dim=1)
 
 
+def line_metrics_loops(line_logits, vulnerable_lines):
+    """Adaptive-threshold line metrics of train.py:1043-1140, restated literally (host decisions on `.item()` values).
+    Returns (accuracy, precision, recall, first_threshold, predictions_after_first_threshold)."""
+    probs = torch.sigmoid(line_logits)
+    base = torch.quantile(probs, 0.99).item()
+    if line_logits.mean().item() < -1.0:  # :1050-1055
+        threshold = max(min(base, 0.4), 0.1)
+    else:  # :1056-1059
+        threshold = max(min(base, 0.6), 0.3)
+    preds = (probs > threshold).float()  # :1062
+    n_first = preds.sum().item()  # :1065-1067 monitoring counters use this count
+    if preds.sum().item() > 10000:  # :1070-1076
+        preds = (probs > min(0.8, torch.quantile(probs, 0.995).item())).float()
+    if preds.sum().item() > 5000:  # :1079-1085
+        preds = (probs > min(0.9, torch.quantile(probs, 0.999).item())).float()
+    if preds.sum().item() == 0 and probs.max().item() > 0.1:  # :1088-1094
+        preds = (probs > min(0.3, probs.max().item() * 0.5)).float()
+    if preds.sum().item() == 0:  # :1097-1104
+        preds = (probs > max(0.01, probs.max().item() * 0.3)).float()
+    vl = vulnerable_lines
+    if preds.shape != vl.shape:  # :1121-1133
+        if preds.shape[0] == vl.shape[0] and preds.shape[1] == vl.shape[2] and preds.shape[2] == vl.shape[1]:
+            vl = vl.transpose(1, 2).contiguous()
+        else:
+            preds, vl = preds.view(-1), vl.view(-1)
+    correct = ((preds == vl.float()) & (vl.float() == 1)).sum().item()  # :1136
+    total_vulnerable = vl.sum().item()
+    predicted = preds.sum().item()
+    recall = correct / total_vulnerable if total_vulnerable > 0 else 0.0
+    precision = correct / predicted if predicted > 0 else 0.0
+    accuracy = (preds == vl.float()).sum().item() / preds.numel() if preds.numel() > 0 else 0.0
+    return accuracy, precision, recall, threshold, n_first
+
+
 def param_groups(names):
     """train.py:512-540: name-substring rules -> (group index, lr multiplier)."""
     mult = {0: 1.0, 1: 2.0, 2: 3.0, 3: 0.5}

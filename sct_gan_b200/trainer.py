@@ -79,6 +79,51 @@ def spatial_aware_focal_loss(pred, target, token_to_line, alpha, gamma, spatial_
     return focal.mean()
 
 
+_QUANTILES = {}
+
+
+def line_vulnerability_metrics(line_logits, vulnerable_lines):
+    """The adaptive-threshold line metrics of train.py:1043-1140 (logging only) without a single host decision: the
+    reference reads ~25 scalars back per batch (`quantile(...).item()`, `preds.sum().item()`, ...) to walk its cascade of
+    threshold fallbacks; here every branch is a device predicate and the three quantiles come from one sort.  Returns
+    device scalars: accuracy, precision, recall, threshold (the first, adaptive one) and predictions (the count after that
+    first threshold, which is what the reference's monitoring counters accumulate, train.py:1065-1067)."""
+    probs = torch.sigmoid(line_logits.float())
+    flat = probs.reshape(-1)
+    qs = _QUANTILES.get((flat.device, flat.dtype))
+    if qs is None:  # created on the first (eager) call: a host-to-device copy is not allowed inside a graph capture
+        qs = _QUANTILES[(flat.device, flat.dtype)] = torch.tensor([0.99, 0.995, 0.999], device=flat.device,
+                                                                 dtype=flat.dtype)
+    q = torch.quantile(flat, qs)
+    negative = line_logits.float().mean() < -1.0
+    threshold = torch.where(negative, q[0].clamp(max=0.4).clamp(min=0.1), q[0].clamp(max=0.6).clamp(min=0.3))
+    preds = probs > threshold
+    n_first = preds.sum()
+    preds = torch.where(n_first > 10000, probs > q[1].clamp(max=0.8), preds)
+    preds = torch.where(preds.sum() > 5000, probs > q[2].clamp(max=0.9), preds)
+    pmax = flat.max()
+    preds = torch.where((preds.sum() == 0) & (pmax > 0.1), probs > (pmax * 0.5).clamp(max=0.3), preds)
+    preds = torch.where(preds.sum() == 0, probs > (pmax * 0.3).clamp(min=0.01), preds)
+    vl = vulnerable_lines
+    if preds.shape != vl.shape:
+        if preds.shape[0] == vl.shape[0] and preds.shape[1] == vl.shape[2] and preds.shape[2] == vl.shape[1]:
+            vl = vl.transpose(1, 2)
+        else:
+            preds, vl = preds.reshape(-1), vl.reshape(-1)
+    pos = vl == 1
+    correct = (preds & pos).sum().float()
+    total_vulnerable = vl.float().sum()
+    predicted = preds.sum().float()
+    zero = torch.zeros((), device=flat.device)
+    return {
+        "line_vuln_accuracy": (preds == pos).float().mean() if preds.numel() > 0 else zero,
+        "line_vuln_precision": torch.where(predicted > 0, correct / predicted.clamp(min=1.0), zero),
+        "line_vuln_recall": torch.where(total_vulnerable > 0, correct / total_vulnerable.clamp(min=1.0), zero),
+        "line_vuln_threshold": threshold,
+        "line_vuln_predictions": n_first,
+    }
+
+
 def param_group_of(name: str, use_gan: bool) -> int:
     """train.py:518-527 name rules: 0 base, 1 contract heads, 2 line heads, 3 discriminator."""
     if "disc_" in name and use_gan:
@@ -316,8 +361,9 @@ class SmartContractTrainer:
     def __init__(self, model, learning_rate=1e-6, weight_decay=0.1, max_grad_norm=1.0, use_augmentation=False,
                  use_gan=False, line_vuln_weight=2.0, contract_vuln_weight=3.0, warmup_epochs=5,
                  compute_vuln_heads=True, process_group=None, bucket_mb=32, use_cuda_graph=False,
-                 fused_optimizer=True, syntax_rules=None):
+                 fused_optimizer=True, syntax_rules=None, line_metrics=False):
         self.model = model
+        self.line_metrics = line_metrics  # also return the adaptive-threshold line metrics of train.py:1043-1140
         self.use_augmentation = use_augmentation
         self.use_gan = use_gan
         self.max_grad_norm = max_grad_norm
@@ -425,6 +471,10 @@ class SmartContractTrainer:
             syntax_penalty = self.syntax_rules.penalty(out["target_ids"])
         losses = self.compute_losses(out, batch, syntax_penalty, n_lines)
         losses["syntax_penalty"] = syntax_penalty if torch.is_tensor(syntax_penalty) else None
+        if self.line_metrics and self.compute_vuln_heads:
+            with torch.no_grad():
+                losses.update(line_vulnerability_metrics(out["line_vulnerability_logits"].detach(),
+                                                         batch["vulnerable_lines"]))
         self.optimizer.zero_grad(set_to_none=True)
         losses["total_loss"].backward()
         self._allreduce_grads()

@@ -313,6 +313,33 @@ def test_weight_shadows_kept_in_step_by_the_optimiser_are_not_recast():
         ops.kn.cast_scale = real
 
 
+def test_line_metrics_device_predicates_match_reference_cascade():
+    """trainer.line_vulnerability_metrics (no host decision) against the oracle's literal restatement of the
+    adaptive-threshold cascade of train.py:1043-1140, on inputs that reach every branch."""
+    from oracle import sct_oracle as O
+    from sct_gan_b200.trainer import line_vulnerability_metrics
+
+    g = torch.Generator().manual_seed(11)
+    B, L, T = 4, 1024, 8
+    cases = {
+        "ordinary": torch.randn(B, L, T, generator=g),
+        "negative logits": torch.randn(B, L, T, generator=g) - 3.0,
+        "too many (conservative, then ultra)": torch.randn(B, L, T, generator=g) * 0.05 + 2.0,
+        "nothing above the 0.3 floor, fallback": torch.full((B, L, T), -0.9) + 0.01 * torch.randn(B, L, T, generator=g),
+        "tiny probabilities, ultra fallback": torch.full((B, L, T), -6.0) + 0.01 * torch.randn(B, L, T, generator=g),
+    }
+    for name, logits in cases.items():
+        for transposed in (False, True):
+            vl = (torch.rand(B, L, T, generator=g) < 0.02).float()
+            vl_in = vl.transpose(1, 2).contiguous() if transposed else vl  # the data set ships [B, types, lines]
+            ref = O.line_metrics_loops(logits, vl_in)
+            got = line_vulnerability_metrics(logits, vl_in)
+            mine = (got["line_vuln_accuracy"].item(), got["line_vuln_precision"].item(), got["line_vuln_recall"].item(),
+                    got["line_vuln_threshold"].item(), float(got["line_vuln_predictions"].item()))
+            for a_, b_ in zip(mine, ref):
+                assert abs(a_ - b_) < 1e-6 * max(1.0, abs(b_)), (name, transposed, mine, ref)
+
+
 def test_vectorised_syntax_penalty_matches_reference_loops():
     """sct_gan_b200.syntax (vectorised device scan) against the oracle's restatement of the double loop of
     train.py:334-431, with a fake tokenizer (token -> small id) on id streams dense in the special tokens."""
