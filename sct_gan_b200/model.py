@@ -476,6 +476,14 @@ class SmartContractTransformer(nn.Module):
         probs = torch.softmax(topv.masked_fill(remove, float("-inf")), dim=-1)
         return topi.gather(1, torch.multinomial(probs, 1))
 
+    @staticmethod
+    def _stop_update(stop_at, nxt, pos):
+        """The same rules as `_stop` evaluated on the device for step i = pos: (EOS or PAD anywhere and i > 50) or (every
+        sequence emitted EOS and i > 20); `stop_at` keeps the first step at which they held."""
+        eos = nxt == 2
+        cond = ((eos.any() | (nxt == 0).any()) & (pos > 50)) | (eos.all() & (pos > 20))
+        stop_at.copy_(torch.minimum(stop_at, torch.where(cond, pos, stop_at)))
+
     def _stop(self, nxt, i):
         """model.py:923-930 (batch-wide early stop; a host decision in the reference as well)."""
         stop = ((nxt == 2).any() | (nxt == 0).any()).item()
@@ -498,7 +506,8 @@ class SmartContractTransformer(nn.Module):
         max_len = min(self.max_length, 1024)
         steps = max_len - 1 if max_new_tokens is None else min(max_len - 1, max_new_tokens)
         t_max = (steps + 127) // 128 * 128
-        key = (B, S, t_max, bool(apply_syntax_constraints), bool(greedy), dev.index)
+        early_stop = max_new_tokens is None  # the reference's batch-wide stop rules (model.py:923-930)
+        key = (B, S, t_max, bool(apply_syntax_constraints), bool(greedy), dev.index, early_stop)
         cache = self.__dict__.setdefault("_decode_cache", {})
         ent = cache.get(key)
         layers = self.decoder.layers
@@ -511,6 +520,9 @@ class SmartContractTransformer(nn.Module):
                 "mem_kv": [torch.empty((B * S, 2 * d), dtype=BF16, device=dev) for _ in layers],
                 "src_kpm": torch.empty((B, S), dtype=torch.bool, device=dev),
                 "nxt": torch.zeros((B, 1), dtype=torch.long, device=dev),
+                # first step at which the stop rules held (t_max + 1 = never): evaluated on the device every step, read
+                # back every 16 steps instead of two .item() round trips per token
+                "stop_at": torch.full((1,), t_max + 1, dtype=torch.long, device=dev) if early_stop else None,
             }
             ent = cache[key] = {"st": st, "graph": None, "calls": 0}
         st = ent["st"]
@@ -519,6 +531,8 @@ class SmartContractTransformer(nn.Module):
         st["tgt"].fill_(1)
         st["kpm_self"].fill_(1)
         st["src_kpm"].copy_(src_kpm)
+        if early_stop:
+            st["stop_at"].fill_(t_max + 1)
         self._shadow.begin_step(refresh=False)
         for li, l in enumerate(layers):
             ca = l.multihead_attn
@@ -541,9 +555,11 @@ class SmartContractTransformer(nn.Module):
                 ent["graph"].replay()
             else:
                 self._decode_step(st, B, S, apply_syntax_constraints, greedy)
-            if max_new_tokens is None and self._stop(st["nxt"], i):
-                n_out = i + 2
-                break
+            if early_stop and (i % 16 == 15 or i == steps - 1):
+                hit = int(st["stop_at"].item())  # tokens decoded past the stop step are simply not returned
+                if hit <= i:
+                    n_out = hit + 2
+                    break
         ent["calls"] += 1
         return st["tgt"][:, :n_out].clone()
 
@@ -576,6 +592,8 @@ class SmartContractTransformer(nn.Module):
         nxt = self._sample(logits, ids, apply_syntax_constraints, greedy)
         st["nxt"].copy_(nxt)
         st["tgt"].index_copy_(1, pos + 1, nxt)
+        if st.get("stop_at") is not None:
+            self._stop_update(st["stop_at"], nxt, pos)
         pos.add_(1)
 
     @torch.no_grad()

@@ -340,6 +340,33 @@ def test_line_metrics_device_predicates_match_reference_cascade():
                 assert abs(a_ - b_) < 1e-6 * max(1.0, abs(b_)), (name, transposed, mine, ref)
 
 
+def test_device_stop_rule_matches_host_rule():
+    """model._stop_update (device-side early stop of the KV-cached generation loop) finds the same first stop step as
+    the reference's per-token host rule `_stop` (model.py:923-930)."""
+    from sct_gan_b200 import SmartContractTransformer
+
+    m = SmartContractTransformer.__new__(SmartContractTransformer)  # only the two rule methods are used
+    g = torch.Generator().manual_seed(2)
+    for trial in range(40):
+        B, steps = 3, 90
+        toks = torch.randint(3, 50, (steps, B, 1), generator=g)
+        kind = trial % 4
+        if kind == 0:    # one sequence emits EOS late: stops at the first such step after 50
+            toks[int(torch.randint(40, 80, (1,), generator=g)), 1, 0] = 2
+        elif kind == 1:  # everybody emits EOS between 21 and 50
+            toks[int(torch.randint(15, 45, (1,), generator=g)), :, 0] = 2
+        elif kind == 2:  # a PAD token
+            toks[int(torch.randint(30, 85, (1,), generator=g)), 2, 0] = 0
+        host = next((i for i in range(steps) if m._stop(toks[i], i)), None)
+        stop_at = torch.full((1,), steps + 1, dtype=torch.long)
+        pos = torch.zeros(1, dtype=torch.long)
+        for i in range(steps):
+            m._stop_update(stop_at, toks[i], pos)
+            pos.add_(1)
+        dev = int(stop_at) if int(stop_at) <= steps else None
+        assert dev == host, (trial, kind, dev, host)
+
+
 def test_vectorised_syntax_penalty_matches_reference_loops():
     """sct_gan_b200.syntax (vectorised device scan) against the oracle's restatement of the double loop of
     train.py:334-431, with a fake tokenizer (token -> small id) on id streams dense in the special tokens."""
