@@ -21,14 +21,14 @@ _f = C.c_float
 
 # name -> argtypes, mirrors include/sct_b200.h one to one
 SIGNATURES = {
-    "sct_embed_ln_pe_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _f, _f, _u64, _u64, _p],
-    "sct_embed_ln_pe_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _f, _f, _u64, _u64, _p],
-    "sct_add_dropout_ln_fwd": [_p, _p, _f, _p, _p, _p, _p, _p, _p, _i64, _i64, _f, _u64, _u64, _p],
-    "sct_add_dropout_ln_bwd": [_p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _i64, _i64, _f, _u64, _u64, _p],
-    "sct_ln_act_fwd": [_p, _p, _p, _p, _p, _i64, _i64, _f, _u64, _u64, _p],
-    "sct_ln_act_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _f, _u64, _u64, _p],
-    "sct_gelu_dropout_fwd": [_p, _p, _i64, _f, _u64, _u64, _p],
-    "sct_gelu_dropout_bwd": [_p, _p, _p, _i64, _f, _u64, _u64, _p],
+    "sct_embed_ln_pe_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _f, _f, _u64, _u64, _p, _p],
+    "sct_embed_ln_pe_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _f, _f, _u64, _u64, _p, _p],
+    "sct_add_dropout_ln_fwd": [_p, _p, _f, _p, _p, _p, _p, _p, _p, _i64, _i64, _f, _u64, _u64, _p, _p],
+    "sct_add_dropout_ln_bwd": [_p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _i64, _i64, _f, _u64, _u64, _p, _p],
+    "sct_ln_act_fwd": [_p, _p, _p, _p, _p, _i64, _i64, _f, _u64, _u64, _p, _p],
+    "sct_ln_act_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _f, _u64, _u64, _p, _p],
+    "sct_gelu_dropout_fwd": [_p, _p, _i64, _f, _u64, _u64, _p, _p],
+    "sct_gelu_dropout_bwd": [_p, _p, _p, _i64, _f, _u64, _u64, _p, _p],
     "sct_colsum_bf16": [_p, _i64, _p, _i64, _i64, _f, _p],
     "sct_cast_scale": [_p, _p, _i64, _p, _i64, _i64, _i64, _i64, _f, _p],
     "sct_seq_mean_fwd": [_p, _p, _p, _i64, _i64, _i64, _p],
@@ -38,20 +38,19 @@ SIGNATURES = {
     "sct_gemm_bf16_tn": [_p, _i64, _p, _i64, _p, _i64, _f, _i64, _i64, _i64, _i32, _p],
     "sct_gemm_bf16_tn_colsum": [_p, _i64, _p, _i64, _p, _i64, _p, _f, _i64, _i64, _i64, _i32, _p],
     "sct_attn_fwd": [_p, _i64, _p, _p, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _f, _f,
-                     _u64, _u64, _p],
+                     _u64, _u64, _p, _p],
     "sct_attn_fwd_strided": [_p, _i64, _p, _p, _i64, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _f,
-                             _f, _u64, _u64, _p],
+                             _f, _u64, _u64, _p, _p],
     "sct_attn_bwd": [_p, _i64, _p, _p, _i64, _p, _p, _i64, _p, _p, _p, _i64, _p, _p, _i64, _p, _i64, _i64,
-                     _i64, _i64, _i64, _i32, _f, _f, _u64, _u64, _p],
+                     _i64, _i64, _i64, _i32, _f, _f, _u64, _u64, _p, _p],
     "sct_attn_bwd_ws": [_p, _i64, _p, _p, _i64, _p, _p, _i64, _p, _p, _p, _i64, _p, _p, _i64, _p, _i64, _i64,
-                        _i64, _i64, _i64, _i32, _f, _f, _u64, _u64, _p, _i64, _p],
+                        _i64, _i64, _i64, _i32, _f, _f, _u64, _u64, _p, _p, _i64, _p],
     "sct_attn_bwd_workspace_bytes": [_i64, _i64, _i64, _i64],
     "sct_ce_rows": [_p, _p, _p, _p, _i64, _i64, _i64, _f, _i32, _p],
     "sct_small_linear_fwd": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p],
     "sct_small_linear_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p],
     "sct_gan_loss_fwd": [_p, _i64, _p, _p, _p],
     "sct_gan_loss_bwd": [_p, _i64, _p, _p, _p, _p, _p],
-    "sct_set_dropout_epoch_ptr": [_p],
     "sct_clip_adamw_step": [_p, _i32, _p, _i32, _p, _p, _p, _f, _f, _f, _f, _f, _f, _p],
 }
 NOARG = {"sct_opt_chunk_elems": _i32, "sct_version": _i32, "sct_device_check": _i32, "sct_debug_timeouts": _i32, "sct_last_error": C.c_char_p}
@@ -91,8 +90,7 @@ def last_error() -> str:
 
 
 # kernels launched per C-ABI call (sct_attn_bwd = D-vector + dK/dV + dQ, sct_seq_mean_fwd = memset + reduce, ...)
-KERNELS_PER_CALL = {"sct_clip_adamw_step": 4, "sct_attn_bwd": 3, "sct_attn_bwd_ws": 3, "sct_small_linear_bwd": 2, "sct_seq_mean_fwd": 2,
-                    "sct_set_dropout_epoch_ptr": 0}
+KERNELS_PER_CALL = {"sct_clip_adamw_step": 4, "sct_attn_bwd": 3, "sct_attn_bwd_ws": 3, "sct_small_linear_bwd": 2, "sct_seq_mean_fwd": 2}
 
 
 class Stats:

@@ -23,8 +23,11 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
-    "--use_fast_math",
 ]
+# --use_fast_math (approximate division / transcendentals, flush-to-zero) for the activation-side kernels only: the
+# optimiser (AdamW bias corrections, denormal-range second moments with eps = 1e-9) and the loss kernels keep IEEE
+# arithmetic so the update matches torch.optim.AdamW
+FAST_MATH = {"gemm.cu", "attn.cu", "rowwise.cu", "api.cu"}
 
 
 NVCC_FLAGS += os.environ.get("SCT_NVCC_EXTRA", "").split()  # e.g. -DSCT_ATTN_TRACE for instrumented builds
@@ -55,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         src, obj = pair
         if not force and _newer(obj, [src] + headers):
             return None
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *(["--use_fast_math"] if src.name in FAST_MATH else []), "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -1,8 +1,12 @@
 // sct_b200 — library-level plumbing behind the C ABI: thread-local error text, device queries and the
 // host-side tensor-map (TMA descriptor) factory.  See include/sct_b200.h for the contract.
+#include <map>
 #include <mutex>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
+#include <string>
+#include <utility>
 
 #include "../../include/sct_b200.h"
 #include "common.cuh"
@@ -18,10 +22,13 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::mutex g_once_mutex;  // guards every once-flag / cache below (backward runs on autograd worker threads)
+
 int num_sms() {
   static int cached[64] = {0};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  std::lock_guard<std::mutex> lock(g_once_mutex);
   if (cached[dev] == 0) {
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
@@ -29,6 +36,30 @@ int num_sms() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+int ensure_dyn_smem(const void* func, int bytes) {
+  int dev = 0;
+  SCT_CUDA(cudaGetDevice(&dev));
+  static std::map<std::pair<const void*, int>, int> done;  // (kernel, device) -> bytes granted
+  std::lock_guard<std::mutex> lock(g_once_mutex);
+  auto key = std::make_pair(func, dev);
+  auto it = done.find(key);
+  if (it != done.end() && it->second >= bytes) return 0;
+  SCT_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done[key] = bytes;
+  return 0;
+}
+
+int env_int(const char* name, int dflt) {
+  static std::map<std::string, int> cache;
+  std::lock_guard<std::mutex> lock(g_once_mutex);
+  auto it = cache.find(name);
+  if (it != cache.end()) return it->second;
+  const char* e = getenv(name);
+  const int v = (e != nullptr && e[0] != 0) ? atoi(e) : dflt;
+  cache[name] = v;
+  return v;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -104,9 +135,6 @@ int make_tmap_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0
   return 0;
 }
 
-static const unsigned long long* g_epoch_ptr = nullptr;
-const unsigned long long* dropout_epoch_ptr() { return g_epoch_ptr; }
-
 // per-translation-unit bounded-wait flags (see common.cuh)
 int gemm_timeout_flag();
 int attn_timeout_flag();
@@ -126,11 +154,6 @@ int32_t sct_device_check(void) {
   SCT_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   SCT_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
   SCT_CHECK(major == 10, "sct_b200 needs an sm_100-class device (B200); found sm_%d%d", major, minor);
-  return 0;
-}
-
-int32_t sct_set_dropout_epoch_ptr(const uint64_t* dev_epoch) {
-  sct::g_epoch_ptr = reinterpret_cast<const unsigned long long*>(dev_epoch);
   return 0;
 }
 

@@ -1195,7 +1195,7 @@ int make_qkv_map(CUtensorMap* m, const void* ptr, int64_t ld, int64_t B, int64_t
 }
 
 int fill_params(AttnParams& p, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int32_t causal, float scale,
-                const uint8_t* kpm, float p_drop, uint64_t seed, uint64_t offset) {
+                const uint8_t* kpm, float p_drop, uint64_t seed, uint64_t offset, const uint64_t* epoch) {
   SCT_CHECK(B > 0 && H > 0 && Lq > 0 && Lk > 0, "empty attention problem");
   SCT_CHECK(B <= 65535 && H <= 65535, "grid overflow");
   SCT_CHECK(!causal || Lq == Lk, "causal attention requires Lq == Lk");
@@ -1214,7 +1214,7 @@ int fill_params(AttnParams& p, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int
     p.key0 = (uint32_t)z;
     p.key1 = (uint32_t)(z >> 32);
   }
-  p.epoch = dropout_epoch_ptr();
+  p.epoch = reinterpret_cast<const unsigned long long*>(epoch);
   const double full = (double)(1u << kDropBits);
   double t = (double)p_drop * full + 0.5;
   if (t < 1.0) t = 1.0;  // p_drop > 0 drops at least 2^-kDropBits
@@ -1251,31 +1251,23 @@ extern "C" {
 int32_t sct_attn_fwd_strided(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
                              int64_t kv_batch_stride, void* o, int64_t ldo, float* lse2, const uint8_t* kpm,
                              int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t head_dim, int32_t causal,
-                             float scale, float p_drop, uint64_t seed, uint64_t offset, void* stream) {
+                             float scale, float p_drop, uint64_t seed, uint64_t offset, const uint64_t* epoch, void* stream) {
   SCT_CHECK(q && k && v && o, "null pointer");
   SCT_CHECK(head_dim == DH, "head_dim %lld unsupported (kernel is specialised for 96)", (long long)head_dim);
   SCT_CHECK(ldo % 8 == 0, "ldo must be a multiple of 8");
   AttnParams p;
-  if (int rc = fill_params(p, B, H, Lq, Lk, causal, scale, kpm, p_drop, seed, offset)) return rc;
+  if (int rc = fill_params(p, B, H, Lq, Lk, causal, scale, kpm, p_drop, seed, offset, epoch)) return rc;
   p.o = (__nv_bfloat16*)o;
   p.ldo = (int)ldo;
   p.lse2 = lse2;
   SCT_CHECK(kv_batch_stride == 0 || (kv_batch_stride >= Lk * ldkv && kv_batch_stride % 8 == 0),
             "kv_batch_stride must be 0 or a multiple of 8 >= Lk * ldkv");
-  static int use_dec = -1;  // SCT_ATTN_DECODE=0: tile kernel also for Lq = 1 (A/B timing)
-  if (use_dec < 0) {
-    const char* e = getenv("SCT_ATTN_DECODE");
-    use_dec = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
+  const int use_dec = env_int("SCT_ATTN_DECODE", 1);  // =0: tile kernel also for Lq = 1 (A/B timing)
   if (use_dec && Lq == 1 && p_drop == 0.f) {  // decode step: SIMT stream over the KV cache
     SCT_CHECK(ldq % 8 == 0 && ldkv % 8 == 0, "row pitches must be multiples of 8");
     const long long kv_bs = kv_batch_stride > 0 ? kv_batch_stride : Lk * ldkv;
     // more key groups per block for longer caches (measured at B = 128, H = 8: 128 threads win up to ~1024 cached rows)
-    static int dec_threads = 0;
-    if (dec_threads == 0) {
-      const char* e = getenv("SCT_ATTN_DECODE_THREADS");
-      dec_threads = e ? atoi(e) : -1;
-    }
+    const int dec_threads = env_int("SCT_ATTN_DECODE_THREADS", -1);
     const int nt = dec_threads > 0 ? dec_threads : (Lk <= 1024 ? 128 : 256);
     const dim3 grid((unsigned)H, (unsigned)B);
     if (nt == 128)
@@ -1294,11 +1286,7 @@ int32_t sct_attn_fwd_strided(const void* q, int64_t ldq, const void* k, const vo
   if (int rc = make_qkv_map(&to, o, ldo, B, Lq, H)) return rc;
   if (int rc = make_qkv_map(&tk, k, ldkv, B, Lk, H, kv_batch_stride)) return rc;
   if (int rc = make_qkv_map(&tv, v, ldkv, B, Lk, H, kv_batch_stride)) return rc;
-  static bool attr = false;
-  if (!attr) {
-    SCT_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
-    attr = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_fwd_kernel), FWD_SMEM)) return rc;
   dim3 grid((unsigned)((Lq + TILE - 1) / TILE), (unsigned)H, (unsigned)B);
   attn_fwd_kernel<<<grid, 256, FWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, to, p);
   SCT_LAUNCH_CHECK();
@@ -1308,18 +1296,18 @@ int32_t sct_attn_fwd_strided(const void* q, int64_t ldq, const void* k, const vo
 int32_t sct_attn_fwd(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* o,
                      int64_t ldo, float* lse2, const uint8_t* kpm, int64_t B, int64_t H, int64_t Lq,
                      int64_t Lk, int64_t head_dim, int32_t causal, float scale, float p_drop,
-                     uint64_t seed, uint64_t offset, void* stream) {
+                     uint64_t seed, uint64_t offset, const uint64_t* epoch, void* stream) {
   return sct_attn_fwd_strided(q, ldq, k, v, ldkv, 0, o, ldo, lse2, kpm, B, H, Lq, Lk, head_dim, causal, scale, p_drop,
-                              seed, offset, stream);
+                              seed, offset, epoch, stream);
 }
 
 int32_t sct_attn_bwd(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
                      const void* o, const void* d_o, int64_t ldo, const float* lse2, float* dvec,
                      void* dq, int64_t lddq, void* dk, void* dv, int64_t lddkv, const uint8_t* kpm,
                      int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t head_dim, int32_t causal,
-                     float scale, float p_drop, uint64_t seed, uint64_t offset, void* stream) {
+                     float scale, float p_drop, uint64_t seed, uint64_t offset, const uint64_t* epoch, void* stream) {
   return sct_attn_bwd_ws(q, ldq, k, v, ldkv, o, d_o, ldo, lse2, dvec, dq, lddq, dk, dv, lddkv, kpm, B, H, Lq, Lk,
-                         head_dim, causal, scale, p_drop, seed, offset, nullptr, 0, stream);
+                         head_dim, causal, scale, p_drop, seed, offset, epoch, nullptr, 0, stream);
 }
 
 int64_t sct_attn_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Lq, int64_t Lk) {
@@ -1331,7 +1319,7 @@ int32_t sct_attn_bwd_ws(const void* q, int64_t ldq, const void* k, const void* v
                         const void* o, const void* d_o, int64_t ldo, const float* lse2, float* dvec,
                         void* dq, int64_t lddq, void* dk, void* dv, int64_t lddkv, const uint8_t* kpm,
                         int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t head_dim, int32_t causal,
-                        float scale, float p_drop, uint64_t seed, uint64_t offset, void* workspace,
+                        float scale, float p_drop, uint64_t seed, uint64_t offset, const uint64_t* epoch, void* workspace,
                         int64_t workspace_bytes, void* stream) {
   SCT_CHECK(q && k && v && o && d_o && lse2 && dvec && dq && dk && dv, "null pointer");
   const bool use_ws = workspace != nullptr;
@@ -1342,7 +1330,7 @@ int32_t sct_attn_bwd_ws(const void* q, int64_t ldq, const void* k, const void* v
   SCT_CHECK(H * DH == 768 || H * DH <= ldo, "unexpected head layout");
   SCT_CHECK(lddq % 8 == 0 && lddkv % 8 == 0 && ldo % 8 == 0, "gradient pitches must be multiples of 8");
   AttnParams p;
-  if (int rc = fill_params(p, B, H, Lq, Lk, causal, scale, kpm, p_drop, seed, offset)) return rc;
+  if (int rc = fill_params(p, B, H, Lq, Lk, causal, scale, kpm, p_drop, seed, offset, epoch)) return rc;
   p.lse2 = const_cast<float*>(lse2);
   p.dvec = dvec;
   p.dq = (__nv_bfloat16*)dq; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv;
@@ -1375,13 +1363,9 @@ int32_t sct_attn_bwd_ws(const void* q, int64_t ldq, const void* k, const void* v
       return rc;
     p.write_ds = 1;
   }
-  static bool attr = false;
-  if (!attr) {
-    SCT_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD3_KV_SMEM));
-    SCT_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD3_Q_SMEM));
-    SCT_CUDA(cudaFuncSetAttribute(attn_bwd_dq_ds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ2_SMEM));
-    attr = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_bwd_dkdv_kernel), BWD3_KV_SMEM)) return rc;
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_bwd_dq_kernel), BWD3_Q_SMEM)) return rc;
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_bwd_dq_ds_kernel), DQ2_SMEM)) return rc;
   {
     dim3 grid((unsigned)((Lk + TILE - 1) / TILE), (unsigned)H, (unsigned)B);
     CUtensorMap tdk, tdv;

@@ -17,7 +17,12 @@ namespace sct {
 // ---------------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 int num_sms();
-const unsigned long long* dropout_epoch_ptr();  // device counter added to every dropout offset (nullable)
+// Library-wide once-state, shared by the Python thread and autograd worker threads (backward): both helpers are
+// guarded by one mutex (api.cu).
+//   ensure_dyn_smem: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device)
+//   env_int:         integer environment switch (A/B timing knobs), read once per name
+int ensure_dyn_smem(const void* func, int bytes);
+int env_int(const char* name, int dflt);
 
 #define SCT_CHECK(cond, ...)                                                                       \
   do {                                                                                             \

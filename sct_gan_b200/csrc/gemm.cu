@@ -428,11 +428,7 @@ int launch_impl(const void* A, int64_t lda, const void* B, int64_t ldb, void* D,
                 cudaStream_t stream) {
   using C = Cfg<BN, OUT_F32, CLUSTER>;
   auto kern = gemm_kernel<BN, A_MN, B_MN, OUT_F32, CLUSTER>;
-  static bool attr_set = false;  // benign race: idempotent call
-  if (!attr_set) {
-    SCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), C::SMEM_BYTES)) return rc;
   CUtensorMap tmA, tmB, tmD;
   int rc;
   if (!A_MN)
@@ -521,11 +517,7 @@ int launch_impl(const void* A, int64_t lda, const void* B, int64_t ldb, void* D,
 template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
 int launch(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd, const float* bias,
            float* colsum, float alpha, int64_t M, int64_t N, int64_t K, int k_splits_req, cudaStream_t stream) {
-  static int use_cluster = -1;
-  if (use_cluster < 0) {
-    const char* e = getenv("SCT_GEMM_PAIR");
-    use_cluster = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
+  const int use_cluster = env_int("SCT_GEMM_PAIR", 1);
   if constexpr (BN == 256) {
     if (use_cluster && M > BM)
       return launch_impl<BN, A_MN, B_MN, OUT_F32, 2>(A, lda, B, ldb, D, ldd, bias, colsum, alpha, M, N, K,
@@ -591,11 +583,7 @@ int32_t sct_gemm_bf16_tn_colsum(const void* A, int64_t lda, const void* B, int64
                                 void* stream) {
   if (int rc = sct::check_common(A, B, D, M, N, K)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static int tn_bn = -1;  // SCT_GEMM_TN_BN=128 forces the narrow tile (A/B timing)
-  if (tn_bn < 0) {
-    const char* e = getenv("SCT_GEMM_TN_BN");
-    tn_bn = e ? atoi(e) : 256;
-  }
+  const int tn_bn = sct::env_int("SCT_GEMM_TN_BN", 256);  // =128 forces the narrow tile (A/B timing)
   if (tn_bn == 256 && N >= 512)
     return sct::launch<256, true, true, true>(A, lda, B, ldb, D, ldd, nullptr, colsum, alpha, M, N, K, k_splits, st);
   return sct::launch<128, true, true, true>(A, lda, B, ldb, D, ldd, nullptr, colsum, alpha, M, N, K, k_splits, st);

@@ -53,6 +53,7 @@ ce_rows_kernel(__nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ t
     }
     return;
   }
+  if (tgt >= V) __trap();  // out-of-range class index: F.cross_entropy device-asserts here as well
   // pass 1: online (max, sum exp2) in the log2 domain
   float m = -INFINITY, s = 0.f;
   for (int c = tid * 8; c < V8; c += 256 * 8) {

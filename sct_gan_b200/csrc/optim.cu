@@ -58,6 +58,14 @@ __device__ __forceinline__ ClipInfo clip_info(const float* sq, const float* loss
   return ci;
 }
 
+// 16-byte vector path only when the element count AND every pointer allow it (views into larger storages, e.g. a
+// parameter that is a slice of a flat buffer, may be only 4-byte aligned)
+__device__ __forceinline__ bool vec4_ok(const OptTensor& t) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(t.p) | reinterpret_cast<uintptr_t>(t.g) |
+                      reinterpret_cast<uintptr_t>(t.m) | reinterpret_cast<uintptr_t>(t.v);
+  return (t.numel & 3) == 0 && (a & 15) == 0 && (reinterpret_cast<uintptr_t>(t.shadow) & 7) == 0;
+}
+
 __global__ void __launch_bounds__(kThreads)
 opt_sqnorm_kernel(const OptTensor* __restrict__ tab, const int2* __restrict__ chunks, float* __restrict__ part) {
   __shared__ float red[kThreads / 32];
@@ -66,7 +74,7 @@ opt_sqnorm_kernel(const OptTensor* __restrict__ tab, const int2* __restrict__ ch
   const long long base = (long long)ck.y * kChunk;
   const long long end = min(base + kChunk, t.numel);
   float s = 0.f;
-  if ((t.numel & 3) == 0) {
+  if (vec4_ok(t)) {
     for (long long i = base + threadIdx.x * 4; i < end; i += kThreads * 4) {
       const float4 g = *reinterpret_cast<const float4*>(t.g + i);
       s += (g.x * g.x + g.y * g.y) + (g.z * g.z + g.w * g.w);
@@ -128,7 +136,7 @@ opt_clip_adamw_kernel(const OptTensor* __restrict__ tab, const int2* __restrict_
   const float inv_sqrt_bias2 = rsqrtf(1.0f - powf(b2, step));
   const long long base = (long long)ck.y * kChunk;
   const long long end = min(base + kChunk, t.numel);
-  if ((t.numel & 3) == 0) {
+  if (vec4_ok(t)) {
     for (long long i = base + threadIdx.x * 4; i < end; i += kThreads * 4) {
       float4 g = *reinterpret_cast<const float4*>(t.g + i);
       float4 p = *reinterpret_cast<float4*>(t.p + i);

@@ -34,11 +34,11 @@ __device__ __forceinline__ DropCfg resolve_epoch(DropCfg dc) {
   return dc;
 }
 
-__host__ inline DropCfg make_drop(float p, uint64_t seed, uint64_t offset) {
+__host__ inline DropCfg make_drop(float p, uint64_t seed, uint64_t offset, const uint64_t* epoch) {
   DropCfg c;
   c.seed = seed;
   c.offset = offset;
-  c.epoch = dropout_epoch_ptr();
+  c.epoch = reinterpret_cast<const unsigned long long*>(epoch);
   double t = (double)p * 65536.0 + 0.5;
   if (t < 0) t = 0;
   if (t > 65535.0) t = 65535.0;
@@ -747,10 +747,10 @@ extern "C" {
 int32_t sct_embed_ln_pe_fwd(const int64_t* ids, const float* table, const float* gamma,
                             const float* beta, const float* pe, float* out_f32, void* out_bf16,
                             float* stats, int64_t n_tok, int64_t seq_len, int64_t vocab, int64_t d,
-                            float scale, float p_drop, uint64_t seed, uint64_t offset, void* stream) {
+                            float scale, float p_drop, uint64_t seed, uint64_t offset, const uint64_t* epoch, void* stream) {
   SCT_CHECK(ids && table && gamma && beta && pe && stats && (out_f32 || out_bf16), "null pointer");
   SCT_CHECK(n_tok > 0 && seq_len > 0, "empty input (n_tok=%lld seq_len=%lld)", (long long)n_tok, (long long)seq_len);
-  const DropCfg dc = make_drop(p_drop, seed, offset);
+  const DropCfg dc = make_drop(p_drop, seed, offset, epoch);
   const int blocks = (int)((n_tok + kWarpsPerBlock - 1) / kWarpsPerBlock);
   cudaStream_t st = (cudaStream_t)stream;
   DISPATCH_NV(d, (embed_ln_pe_fwd_kernel<NV><<<blocks, kWarpsPerBlock * 32, 0, st>>>(
@@ -763,10 +763,10 @@ int32_t sct_embed_ln_pe_fwd(const int64_t* ids, const float* table, const float*
 int32_t sct_embed_ln_pe_bwd(const float* g_f32, const void* g_bf16, const int64_t* ids,
                             const float* table, const float* gamma, const float* stats,
                             float* dtable, float* dgamma, float* dbeta, int64_t n_tok, int64_t vocab,
-                            int64_t d, float scale, float p_drop, uint64_t seed, uint64_t offset,
+                            int64_t d, float scale, float p_drop, uint64_t seed, uint64_t offset, const uint64_t* epoch,
                             void* stream) {
   SCT_CHECK((g_f32 || g_bf16) && ids && table && gamma && stats && dtable && dgamma && dbeta, "null pointer");
-  const DropCfg dc = make_drop(p_drop, seed, offset);
+  const DropCfg dc = make_drop(p_drop, seed, offset, epoch);
   const int blocks = persistent_blocks((int)n_tok);
   cudaStream_t st = (cudaStream_t)stream;
   DISPATCH_NV(d, (embed_ln_pe_bwd_kernel<NV><<<blocks, kWarpsPerBlock * 32, 0, st>>>(
@@ -779,26 +779,18 @@ int32_t sct_embed_ln_pe_bwd(const float* g_f32, const void* g_bf16, const int64_
 int32_t sct_add_dropout_ln_fwd(const float* x, const void* branch, float alpha, const float* gamma,
                                const float* beta, float* x_out, void* y_ln, void* y_cast,
                                float* stats, int64_t n_rows, int64_t d, float p_drop, uint64_t seed,
-                               uint64_t offset, void* stream) {
+                               uint64_t offset, const uint64_t* epoch, void* stream) {
   SCT_CHECK(x || branch, "need x or branch");
   SCT_CHECK(!y_ln || (gamma && beta && stats), "LayerNorm output requested without gamma/beta/stats");
   SCT_CHECK(n_rows > 0, "empty input");
-  const DropCfg dc = make_drop(p_drop, seed, offset);
+  const DropCfg dc = make_drop(p_drop, seed, offset, epoch);
   const int blocks = (int)((n_rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
   cudaStream_t st = (cudaStream_t)stream;
-  static int staged = -1;  // SCT_LN_STAGED=0 selects the plain one-row-per-warp kernel (A/B timing)
-  if (staged < 0) {
-    const char* e = getenv("SCT_LN_STAGED");
-    staged = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
+  const int staged = env_int("SCT_LN_STAGED", 1);  // =0 selects the plain one-row-per-warp kernel (A/B timing)
   if (staged && d == 768 && n_rows >= 4096) {
     constexpr int NV = 6;
     constexpr int smem = kWarpsPerBlock * kLnSlots * (NV * 128 * 6) + kWarpsPerBlock * kLnSlots * 8;
-    static bool attr = false;
-    if (!attr) {
-      SCT_CUDA(cudaFuncSetAttribute(add_dropout_ln_fwd_staged_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr = true;
-    }
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(add_dropout_ln_fwd_staged_kernel<NV>), smem)) return rc;
     int pb = 2 * num_sms();
     if (pb > blocks) pb = blocks;
     add_dropout_ln_fwd_staged_kernel<NV><<<pb, kWarpsPerBlock * 32, smem, st>>>(
@@ -818,10 +810,10 @@ int32_t sct_add_dropout_ln_bwd(const float* g_xout, const void* g_yln, const voi
                                const float* xprime, const float* stats, const float* gamma,
                                float alpha, float* g_x, void* g_branch, float* dgamma, float* dbeta,
                                int64_t n_rows, int64_t d, float p_drop, uint64_t seed,
-                               uint64_t offset, void* stream) {
+                               uint64_t offset, const uint64_t* epoch, void* stream) {
   SCT_CHECK(!g_yln || (xprime && stats && gamma && dgamma && dbeta), "LN backward needs x', stats, gamma, dgamma, dbeta");
   SCT_CHECK(g_x || g_branch, "no output requested");
-  const DropCfg dc = make_drop(p_drop, seed, offset);
+  const DropCfg dc = make_drop(p_drop, seed, offset, epoch);
   const int blocks = persistent_blocks((int)n_rows);
   cudaStream_t st = (cudaStream_t)stream;
   DISPATCH_NV(d, (add_dropout_ln_bwd_kernel<NV><<<blocks, kWarpsPerBlock * 32, 0, st>>>(
@@ -832,10 +824,10 @@ int32_t sct_add_dropout_ln_bwd(const float* g_xout, const void* g_yln, const voi
 }
 
 int32_t sct_ln_act_fwd(const void* z, const float* gamma, const float* beta, void* h, float* stats,
-                       int64_t n_rows, int64_t d, float p_drop, uint64_t seed, uint64_t offset,
+                       int64_t n_rows, int64_t d, float p_drop, uint64_t seed, uint64_t offset, const uint64_t* epoch,
                        void* stream) {
   SCT_CHECK(z && gamma && beta && h && stats, "null pointer");
-  const DropCfg dc = make_drop(p_drop, seed, offset);
+  const DropCfg dc = make_drop(p_drop, seed, offset, epoch);
   const int blocks = (int)((n_rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
   cudaStream_t st = (cudaStream_t)stream;
   DISPATCH_NV(d, (ln_act_fwd_kernel<NV><<<blocks, kWarpsPerBlock * 32, 0, st>>>(
@@ -846,9 +838,9 @@ int32_t sct_ln_act_fwd(const void* z, const float* gamma, const float* beta, voi
 
 int32_t sct_ln_act_bwd(const void* g_h, const void* z, const float* stats, const float* gamma,
                        const float* beta, void* g_z, float* dgamma, float* dbeta, int64_t n_rows,
-                       int64_t d, float p_drop, uint64_t seed, uint64_t offset, void* stream) {
+                       int64_t d, float p_drop, uint64_t seed, uint64_t offset, const uint64_t* epoch, void* stream) {
   SCT_CHECK(g_h && z && stats && gamma && beta && g_z && dgamma && dbeta, "null pointer");
-  const DropCfg dc = make_drop(p_drop, seed, offset);
+  const DropCfg dc = make_drop(p_drop, seed, offset, epoch);
   const int blocks = persistent_blocks((int)n_rows);
   cudaStream_t st = (cudaStream_t)stream;
   DISPATCH_NV(d, (ln_act_bwd_kernel<NV><<<blocks, kWarpsPerBlock * 32, 0, st>>>(
@@ -859,10 +851,10 @@ int32_t sct_ln_act_bwd(const void* g_h, const void* z, const float* stats, const
 }
 
 int32_t sct_gelu_dropout_fwd(const void* z, void* h, int64_t n, float p_drop, uint64_t seed,
-                             uint64_t offset, void* stream) {
+                             uint64_t offset, const uint64_t* epoch, void* stream) {
   SCT_CHECK(z && h, "null pointer");
   SCT_CHECK(n % 8 == 0, "element count %lld not a multiple of 8", (long long)n);
-  const DropCfg dc = make_drop(p_drop, seed, offset);
+  const DropCfg dc = make_drop(p_drop, seed, offset, epoch);
   const long long n8 = n / 8;
   long long blocks = (n8 + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
@@ -874,10 +866,10 @@ int32_t sct_gelu_dropout_fwd(const void* z, void* h, int64_t n, float p_drop, ui
 }
 
 int32_t sct_gelu_dropout_bwd(const void* g_h, const void* z, void* g_z, int64_t n, float p_drop,
-                             uint64_t seed, uint64_t offset, void* stream) {
+                             uint64_t seed, uint64_t offset, const uint64_t* epoch, void* stream) {
   SCT_CHECK(g_h && z && g_z, "null pointer");
   SCT_CHECK(n % 8 == 0, "element count %lld not a multiple of 8", (long long)n);
-  const DropCfg dc = make_drop(p_drop, seed, offset);
+  const DropCfg dc = make_drop(p_drop, seed, offset, epoch);
   const long long n8 = n / 8;
   long long blocks = (n8 + 255) / 256;
   const long long cap = (long long)num_sms() * 16;

@@ -28,6 +28,14 @@ def _ptr(t, align=16):
     return t.data_ptr()
 
 
+def _eptr(t):
+    """Per-call dropout epoch: a device int64 tensor the kernel reads at run time (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.dtype == torch.int64
+    return t.data_ptr()
+
+
 def _sptr(t):
     """Pointer to a device scalar / small fp32 vector (4-byte alignment is enough)."""
     return _ptr(t, 4)
@@ -47,7 +55,7 @@ def _rows2d(t, dtype, name):
 
 
 # ---------------------------------------------------------------------------------------------- K1
-def embed_ln_pe_fwd(ids, table, gamma, beta, pe, seq_len, scale, p_drop=0.0, seed=0, offset=0,
+def embed_ln_pe_fwd(ids, table, gamma, beta, pe, seq_len, scale, p_drop=0.0, seed=0, offset=0, epoch=None,
                     want_f32=True, want_bf16=True):
     ids = _chk(ids, torch.int64, "ids")
     n_tok = ids.numel()
@@ -60,12 +68,12 @@ def embed_ln_pe_fwd(ids, table, gamma, beta, pe, seq_len, scale, p_drop=0.0, see
     stats = torch.empty((n_tok, 2), dtype=F32, device=dev)
     _lib.call("sct_embed_ln_pe_fwd", _ptr(ids), _ptr(table), _ptr(gamma), _ptr(beta), _ptr(pe),
               _ptr(out_f32), _ptr(out_bf16), _ptr(stats), n_tok, seq_len, vocab, d, float(scale),
-              float(p_drop), seed, offset, _stream())
+              float(p_drop), seed, offset, _eptr(epoch), _stream())
     return out_f32, out_bf16, stats
 
 
 def embed_ln_pe_bwd(g, ids, table, gamma, stats, dtable, dgamma, dbeta, scale, p_drop=0.0, seed=0,
-                    offset=0):
+                    offset=0, epoch=None):
     """dtable / dgamma / dbeta (fp32) are accumulated into."""
     vocab, d = table.shape
     n_tok = ids.numel()
@@ -74,12 +82,12 @@ def embed_ln_pe_bwd(g, ids, table, gamma, stats, dtable, dgamma, dbeta, scale, p
     assert g.is_contiguous() and g.numel() == n_tok * d
     _lib.call("sct_embed_ln_pe_bwd", _ptr(g_f32), _ptr(g_bf16), _ptr(ids), _ptr(table), _ptr(gamma),
               _ptr(stats), _ptr(dtable), _ptr(dgamma), _ptr(dbeta), n_tok, vocab, d, float(scale),
-              float(p_drop), seed, offset, _stream())
+              float(p_drop), seed, offset, _eptr(epoch), _stream())
 
 
 # --------------------------------------------------------------------------------------------- K4a
 def add_dropout_ln_fwd(x, branch, alpha, gamma, beta, want_x=True, want_ln=True, want_cast=False,
-                       p_drop=0.0, seed=0, offset=0):
+                       p_drop=0.0, seed=0, offset=0, epoch=None):
     ref = x if x is not None else branch
     n_rows, d = ref.shape
     dev = ref.device
@@ -95,12 +103,12 @@ def add_dropout_ln_fwd(x, branch, alpha, gamma, beta, want_x=True, want_ln=True,
                                             + (4 if want_x else 0) + (2 if want_ln else 0) + (2 if want_cast else 0))))
     _lib.call("sct_add_dropout_ln_fwd", _ptr(x), _ptr(branch), float(alpha), _ptr(gamma), _ptr(beta),
               _ptr(x_out), _ptr(y_ln), _ptr(y_cast), _ptr(stats), n_rows, d, float(p_drop), seed,
-              offset, _stream())
+              offset, _eptr(epoch), _stream())
     return x_out, y_ln, y_cast, stats
 
 
 def add_dropout_ln_bwd(g_xout, g_yln, g_ycast, xprime, stats, gamma, alpha, dgamma, dbeta,
-                       want_gx=True, want_gbranch=True, p_drop=0.0, seed=0, offset=0):
+                       want_gx=True, want_gbranch=True, p_drop=0.0, seed=0, offset=0, epoch=None):
     ref = next(t for t in (g_xout, g_yln, g_ycast) if t is not None)
     n_rows, d = ref.shape
     dev = ref.device
@@ -108,41 +116,41 @@ def add_dropout_ln_bwd(g_xout, g_yln, g_ycast, xprime, stats, gamma, alpha, dgam
     g_branch = torch.empty((n_rows, d), dtype=BF16, device=dev) if want_gbranch else None
     _lib.call("sct_add_dropout_ln_bwd", _ptr(g_xout), _ptr(g_yln), _ptr(g_ycast), _ptr(xprime),
               _ptr(stats), _ptr(gamma), float(alpha), _ptr(g_x), _ptr(g_branch), _ptr(dgamma),
-              _ptr(dbeta), n_rows, d, float(p_drop), seed, offset, _stream())
+              _ptr(dbeta), n_rows, d, float(p_drop), seed, offset, _eptr(epoch), _stream())
     return g_x, g_branch
 
 
-def ln_act_fwd(z, gamma, beta, p_drop=0.0, seed=0, offset=0):
+def ln_act_fwd(z, gamma, beta, p_drop=0.0, seed=0, offset=0, epoch=None):
     _chk(z, BF16, "z")
     n_rows, d = z.shape
     h = torch.empty_like(z)
     stats = torch.empty((n_rows, 2), dtype=F32, device=z.device)
     _lib.call("sct_ln_act_fwd", _ptr(z), _ptr(gamma), _ptr(beta), _ptr(h), _ptr(stats), n_rows, d,
-              float(p_drop), seed, offset, _stream())
+              float(p_drop), seed, offset, _eptr(epoch), _stream())
     return h, stats
 
 
-def ln_act_bwd(g_h, z, stats, gamma, beta, dgamma, dbeta, p_drop=0.0, seed=0, offset=0):
+def ln_act_bwd(g_h, z, stats, gamma, beta, dgamma, dbeta, p_drop=0.0, seed=0, offset=0, epoch=None):
     _chk(g_h, BF16, "g_h")
     n_rows, d = z.shape
     g_z = torch.empty_like(z)
     _lib.call("sct_ln_act_bwd", _ptr(g_h), _ptr(z), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(g_z),
-              _ptr(dgamma), _ptr(dbeta), n_rows, d, float(p_drop), seed, offset, _stream())
+              _ptr(dgamma), _ptr(dbeta), n_rows, d, float(p_drop), seed, offset, _eptr(epoch), _stream())
     return g_z
 
 
-def gelu_dropout_fwd(z, p_drop=0.0, seed=0, offset=0):
+def gelu_dropout_fwd(z, p_drop=0.0, seed=0, offset=0, epoch=None):
     _chk(z, BF16, "z")
     h = torch.empty_like(z)
-    _lib.call("sct_gelu_dropout_fwd", _ptr(z), _ptr(h), z.numel(), float(p_drop), seed, offset, _stream())
+    _lib.call("sct_gelu_dropout_fwd", _ptr(z), _ptr(h), z.numel(), float(p_drop), seed, offset, _eptr(epoch), _stream())
     return h
 
 
-def gelu_dropout_bwd(g_h, z, p_drop=0.0, seed=0, offset=0):
+def gelu_dropout_bwd(g_h, z, p_drop=0.0, seed=0, offset=0, epoch=None):
     _chk(g_h, BF16, "g_h"), _chk(z, BF16, "z")
     g_z = torch.empty_like(z)
     _lib.call("sct_gelu_dropout_bwd", _ptr(g_h), _ptr(z), _ptr(g_z), z.numel(), float(p_drop), seed,
-              offset, _stream())
+              offset, _eptr(epoch), _stream())
     return g_z
 
 
@@ -246,7 +254,7 @@ def gemm_tn(a, b, out, alpha=1.0, k_splits=0, colsum=None):
 
 
 # ---------------------------------------------------------------------------------------------- K3
-def attn_fwd(q, k, v, B, H, Lq, Lk, kpm=None, causal=False, scale=None, p_drop=0.0, seed=0, offset=0,
+def attn_fwd(q, k, v, B, H, Lq, Lk, kpm=None, causal=False, scale=None, p_drop=0.0, seed=0, offset=0, epoch=None,
              head_dim=96, kv_batch_stride=0):
     """q [B*Lq, ld], k/v [B*Lk, ld] 2-D bf16 views (may be column slices of a packed projection).
     kv_batch_stride (elements) > 0: k/v are views into a [B, T_max, ld] cache of which rows [0, Lk) are used."""
@@ -264,12 +272,12 @@ def attn_fwd(q, k, v, B, H, Lq, Lk, kpm=None, causal=False, scale=None, p_drop=0
     _lib.call("sct_attn_fwd_strided", _ptr(q), ldq, _ptr(k), _ptr(v), ldk, int(kv_batch_stride), _ptr(o), o.stride(0),
               _ptr(lse2),
               kpm.data_ptr() if kpm is not None else None, B, H, Lq, Lk, head_dim, int(causal),
-              float(scale), float(p_drop), seed, offset, _stream())
+              float(scale), float(p_drop), seed, offset, _eptr(epoch), _stream())
     return o, lse2
 
 
 def attn_bwd(q, k, v, o, d_o, lse2, B, H, Lq, Lk, dq, dk, dv, kpm=None, causal=False, scale=None,
-             p_drop=0.0, seed=0, offset=0, head_dim=96, ws_slot=0):
+             p_drop=0.0, seed=0, offset=0, epoch=None, head_dim=96, ws_slot=0):
     """dq [B*Lq, ld], dk/dv [B*Lk, ld] are written (2-D bf16 views, e.g. slices of a packed buffer)."""
     q, ldq = _rows2d(q, BF16, "q")
     k, ldk = _rows2d(k, BF16, "k")
@@ -288,7 +296,7 @@ def attn_bwd(q, k, v, o, d_o, lse2, B, H, Lq, Lk, dq, dk, dv, kpm=None, causal=F
     _lib.call("sct_attn_bwd_ws", _ptr(q), ldq, _ptr(k), _ptr(v), ldk, _ptr(o), _ptr(d_o), o.stride(0),
               _ptr(lse2), _ptr(dvec), _ptr(dq), lddq, _ptr(dk), _ptr(dv), lddk,
               kpm.data_ptr() if kpm is not None else None, B, H, Lq, Lk, head_dim, int(causal),
-              float(scale), float(p_drop), seed, offset, ws.data_ptr() if ws is not None else None, ws_bytes,
+              float(scale), float(p_drop), seed, offset, _eptr(epoch), ws.data_ptr() if ws is not None else None, ws_bytes,
               _stream())
 
 

@@ -23,13 +23,16 @@ BF16, F32 = torch.bfloat16, torch.float32
 class DropoutRng:
     """(seed, offset) source for the counter-based dropout of the kernels.
 
-    `seed` is fixed per process (from torch's seed), `offset` numbers the dropout sites of one forward pass
-    (reset by begin_step), and a device-resident epoch counter — bumped once per training forward ON THE
-    DEVICE, so that it also advances when the step is replayed from a CUDA graph — is added to the offset by
-    the kernels at run time (sct_set_dropout_epoch_ptr).  One forward -> backward at a time: the backward
-    must run before the next training forward bumps the epoch."""
+    `seed` is fixed per model (from torch's seed), `offset` numbers the dropout sites of one forward pass
+    (reset by begin_step), and a device-resident epoch counter owned by the MODEL — bumped once per training
+    forward ON THE DEVICE, so that it also advances when the step is replayed from a CUDA graph — is folded in
+    by the kernels at run time.  The counter's tensor is handed to every kernel call (the C ABI's `epoch`
+    argument) and kept in the op's autograd context, so a backward always replays the masks of its own
+    forward even if another model ran a forward in between; the library holds no dropout state.  Per model:
+    the backward must run before that model's next training forward bumps its epoch."""
     seed = 0x5C7B200
     counter = 0
+    epoch = None
 
     @classmethod
     def reseed(cls, seed: int):
@@ -41,8 +44,6 @@ class DropoutRng:
         """Start a training forward of `owner` (the module): site counter to 0, its device epoch += 1.  The
         epoch counter and the seed (torch.initial_seed() when the module first trains) belong to the module,
         so a freshly built model under the same torch seed reproduces the same masks."""
-        from . import _lib
-
         ep = getattr(owner, "_drop_epoch", None)
         if ep is None or ep.device != device:
             ep = torch.zeros(2, dtype=torch.int64, device=device)  # [0] = epoch (16-byte allocation)
@@ -52,14 +53,14 @@ class DropoutRng:
                 rank = torch.distributed.get_rank()  # replicas see different samples: give them different masks too
             owner._drop_seed = (torch.initial_seed() * 1000003 + rank * 7919 + 0x5C7B200) & 0x7FFFFFFFFFFFFFFF
         cls.seed = owner._drop_seed
-        _lib.call("sct_set_dropout_epoch_ptr", ep.data_ptr())
+        cls.epoch = ep
         ep[:1].add_(1)
         cls.counter = 0
 
     @classmethod
     def draw(cls):
         cls.counter += 1
-        return cls.seed, cls.counter
+        return cls.seed, cls.counter, cls.epoch
 
 
 class ShadowCache:
@@ -132,19 +133,19 @@ class EmbedLnPe(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, ids, table, gamma, beta, pe, seq_len, scale, p_drop, want_f32, want_bf16):
-        seed, off = DropoutRng.draw() if p_drop > 0 else (0, 0)
+        seed, off, ep = DropoutRng.draw() if p_drop > 0 else (0, 0, None)
         ids_flat = ids.reshape(-1).contiguous()
         out_f32, out_bf16, stats = kn.embed_ln_pe_fwd(ids_flat, table.detach(), gamma.detach(), beta.detach(),
-                                                      pe, seq_len, scale, p_drop, seed, off, want_f32, want_bf16)
+                                                      pe, seq_len, scale, p_drop, seed, off, ep, want_f32, want_bf16)
         ctx.save_for_backward(ids_flat, table, gamma, stats)
-        ctx.cfg = (scale, p_drop, seed, off)
+        ctx.cfg = (scale, p_drop, seed, off, ep)
         ctx.set_materialize_grads(False)
         return out_f32, out_bf16
 
     @staticmethod
     def backward(ctx, g_f32, g_bf16):
         ids_flat, table, gamma, stats = ctx.saved_tensors
-        scale, p_drop, seed, off = ctx.cfg
+        scale, p_drop, seed, off, ep = ctx.cfg
         if g_f32 is not None and g_bf16 is not None:
             g = g_f32 + g_bf16.float()
         else:
@@ -154,7 +155,7 @@ class EmbedLnPe(torch.autograd.Function):
         dbeta = torch.zeros_like(gamma)
         if g is not None:
             kn.embed_ln_pe_bwd(g.contiguous(), ids_flat, table.detach(), gamma.detach(), stats, dtable, dgamma,
-                               dbeta, scale, p_drop, seed, off)
+                               dbeta, scale, p_drop, seed, off, ep)
         return None, dtable, dgamma, dbeta, None, None, None, None, None, None
 
 
@@ -171,15 +172,15 @@ class ResidualLn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, branch, gamma, beta, alpha, p_drop, mode, want_x):
         use_drop = p_drop > 0 and branch is not None
-        seed, off = DropoutRng.draw() if use_drop else (0, 0)
+        seed, off, ep = DropoutRng.draw() if use_drop else (0, 0, None)
         p = p_drop if use_drop else 0.0
         g_ = gamma.detach() if gamma is not None else None
         b_ = beta.detach() if beta is not None else None
         need_xprime = want_x or mode == "ln"
         x_out, y_ln, y_cast, stats = kn.add_dropout_ln_fwd(
             x, branch, alpha, g_, b_, want_x=need_xprime, want_ln=(mode == "ln"), want_cast=(mode == "cast"),
-            p_drop=p, seed=seed, offset=off)
-        ctx.mode, ctx.alpha, ctx.drop = mode, alpha, (p, seed, off)
+            p_drop=p, seed=seed, offset=off, epoch=ep)
+        ctx.mode, ctx.alpha, ctx.drop = mode, alpha, (p, seed, off, ep)
         ctx.has_x, ctx.has_branch = x is not None, branch is not None
         if mode == "ln":
             ctx.save_for_backward(x_out, stats, gamma)
@@ -188,7 +189,7 @@ class ResidualLn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_xout, g_second):
-        p, seed, off = ctx.drop
+        p, seed, off, ep = ctx.drop
         dgamma = dbeta = None
         g_yln = g_ycast = None
         xprime = stats = gamma = None
@@ -208,7 +209,7 @@ class ResidualLn(torch.autograd.Function):
             g_xout, g_yln, g_ycast, xprime if g_yln is not None else None, stats if g_yln is not None else None,
             gamma.detach() if g_yln is not None else None, ctx.alpha, dgamma if g_yln is not None else None,
             dbeta if g_yln is not None else None, want_gx=ctx.has_x, want_gbranch=ctx.has_branch,
-            p_drop=p, seed=seed, offset=off)
+            p_drop=p, seed=seed, offset=off, epoch=ep)
         return g_x, g_branch, dgamma, dbeta, None, None, None, None
 
 
@@ -221,18 +222,18 @@ class LnAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, z, gamma, beta, p_drop):
-        seed, off = DropoutRng.draw() if p_drop > 0 else (0, 0)
-        h, stats = kn.ln_act_fwd(z, gamma.detach(), beta.detach(), p_drop, seed, off)
+        seed, off, ep = DropoutRng.draw() if p_drop > 0 else (0, 0, None)
+        h, stats = kn.ln_act_fwd(z, gamma.detach(), beta.detach(), p_drop, seed, off, ep)
         ctx.save_for_backward(z, stats, gamma, beta)
-        ctx.drop = (p_drop, seed, off)
+        ctx.drop = (p_drop, seed, off, ep)
         return h
 
     @staticmethod
     def backward(ctx, g_h):
         z, stats, gamma, beta = ctx.saved_tensors
-        p, seed, off = ctx.drop
+        p, seed, off, ep = ctx.drop
         dgamma, dbeta = torch.zeros_like(gamma), torch.zeros_like(beta)
-        g_z = kn.ln_act_bwd(g_h.contiguous(), z, stats, gamma.detach(), beta.detach(), dgamma, dbeta, p, seed, off)
+        g_z = kn.ln_act_bwd(g_h.contiguous(), z, stats, gamma.detach(), beta.detach(), dgamma, dbeta, p, seed, off, ep)
         return g_z, dgamma, dbeta, None
 
 
@@ -245,17 +246,17 @@ class GeluDropout(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, z, p_drop):
-        seed, off = DropoutRng.draw() if p_drop > 0 else (0, 0)
-        h = kn.gelu_dropout_fwd(z, p_drop, seed, off)
+        seed, off, ep = DropoutRng.draw() if p_drop > 0 else (0, 0, None)
+        h = kn.gelu_dropout_fwd(z, p_drop, seed, off, ep)
         ctx.save_for_backward(z)
-        ctx.drop = (p_drop, seed, off)
+        ctx.drop = (p_drop, seed, off, ep)
         return h
 
     @staticmethod
     def backward(ctx, g_h):
         (z,) = ctx.saved_tensors
-        p, seed, off = ctx.drop
-        return kn.gelu_dropout_bwd(g_h.contiguous(), z, p, seed, off), None
+        p, seed, off, ep = ctx.drop
+        return kn.gelu_dropout_bwd(g_h.contiguous(), z, p, seed, off, ep), None
 
 
 def gelu_dropout(z, p_drop=0.0):
@@ -340,23 +341,23 @@ class SelfAttention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, B, H, L, kpm, causal, p_drop):
         d = qkv.shape[1] // 3
-        seed, off = DropoutRng.draw() if p_drop > 0 else (0, 0)
+        seed, off, ep = DropoutRng.draw() if p_drop > 0 else (0, 0, None)
         o, lse2 = kn.attn_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], B, H, L, L, kpm=kpm, causal=causal,
-                              p_drop=p_drop, seed=seed, offset=off, head_dim=d // H)
+                              p_drop=p_drop, seed=seed, offset=off, epoch=ep, head_dim=d // H)
         ctx.save_for_backward(qkv, o, lse2, kpm if kpm is not None else torch.empty(0))
-        ctx.cfg = (B, H, L, causal, p_drop, seed, off, kpm is not None)
+        ctx.cfg = (B, H, L, causal, p_drop, seed, off, kpm is not None, ep)
         ctx.ws_slot = kn.current_ws_slot()
         return o
 
     @staticmethod
     def backward(ctx, d_o):
         qkv, o, lse2, kpm = ctx.saved_tensors
-        B, H, L, causal, p_drop, seed, off, has_kpm = ctx.cfg
+        B, H, L, causal, p_drop, seed, off, has_kpm, ep = ctx.cfg
         d = qkv.shape[1] // 3
         dqkv = torch.empty_like(qkv)
         kn.attn_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], o, d_o.contiguous(), lse2, B, H, L, L,
                     dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:], kpm=kpm if has_kpm else None, causal=causal,
-                    p_drop=p_drop, seed=seed, offset=off, head_dim=d // H, ws_slot=ctx.ws_slot)
+                    p_drop=p_drop, seed=seed, offset=off, epoch=ep, head_dim=d // H, ws_slot=ctx.ws_slot)
         return dqkv, None, None, None, None, None, None
 
 
@@ -366,24 +367,24 @@ class CrossAttention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, kv, B, H, Lq, Lk, kpm, p_drop):
         d = q.shape[1]
-        seed, off = DropoutRng.draw() if p_drop > 0 else (0, 0)
+        seed, off, ep = DropoutRng.draw() if p_drop > 0 else (0, 0, None)
         o, lse2 = kn.attn_fwd(q, kv[:, :d], kv[:, d:], B, H, Lq, Lk, kpm=kpm, causal=False, p_drop=p_drop,
-                              seed=seed, offset=off, head_dim=d // H)
+                              seed=seed, offset=off, epoch=ep, head_dim=d // H)
         ctx.save_for_backward(q, kv, o, lse2, kpm if kpm is not None else torch.empty(0))
-        ctx.cfg = (B, H, Lq, Lk, p_drop, seed, off, kpm is not None)
+        ctx.cfg = (B, H, Lq, Lk, p_drop, seed, off, kpm is not None, ep)
         ctx.ws_slot = kn.current_ws_slot()
         return o
 
     @staticmethod
     def backward(ctx, d_o):
         q, kv, o, lse2, kpm = ctx.saved_tensors
-        B, H, Lq, Lk, p_drop, seed, off, has_kpm = ctx.cfg
+        B, H, Lq, Lk, p_drop, seed, off, has_kpm, ep = ctx.cfg
         d = q.shape[1]
         dq = torch.empty_like(q)
         dkv = torch.empty_like(kv)
         kn.attn_bwd(q, kv[:, :d], kv[:, d:], o, d_o.contiguous(), lse2, B, H, Lq, Lk, dq, dkv[:, :d], dkv[:, d:],
                     kpm=kpm if has_kpm else None, causal=False, p_drop=p_drop, seed=seed, offset=off,
-                    head_dim=d // H, ws_slot=ctx.ws_slot)
+                    epoch=ep, head_dim=d // H, ws_slot=ctx.ws_slot)
         return dq, dkv, None, None, None, None, None, None
 
 

@@ -35,10 +35,29 @@ def contract_level_focal_loss(pred, target, alpha=0.05, gamma=4.0):
     return (focal * penalty).mean()
 
 
-def spatial_penalty(pred, target, token_to_line, n_lines=None):
+class _AllReduceSum(torch.autograd.Function):
+    """SUM all-reduce whose backward is the SUM all-reduce of the incoming gradients (every rank's loss depends on every
+    rank's contribution to the reduced tensor)."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        y = x.clone()
+        dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+        return g, None
+
+
+def spatial_penalty(pred, target, token_to_line, n_lines=None, dp=None):
     """SpatialAwareFocalLoss._compute_spatial_penalty (train.py:174-245) without the B*1024-iteration
     Python loop.  The reference treats the flattened batch as ONE sequence when token_to_line has as many
-    entries as pred has rows (i.e. S == 1024) and returns zeros otherwise; row i then gets
+    entries as pred has rows (i.e. S == 1024) and returns zeros otherwise (`dp` = process group: per-line sums are
+    all-reduced so that a sharded batch gives the single-process numbers; needs `n_lines`); row i then gets
     0.1 * mean_j sigmoid(pred_j) over all j != i with |line_j - line_i| <= 2, if those j hold any positive
     target.  Lines are small integers, so per-line sums + a 5-wide window give the same numbers in O(N)."""
     total, C = pred.shape
@@ -46,15 +65,24 @@ def spatial_penalty(pred, target, token_to_line, n_lines=None):
         return torch.zeros_like(pred)
     tl = token_to_line.reshape(-1).long()
     if n_lines is None:  # read the line range back like the reference's .item() calls
-        lo = int(tl.min().item())
+        rng = torch.stack([-tl.min(), tl.max()])
+        if dp is not None:  # every rank must build the same [L + 4, .] tables
+            dist.all_reduce(rng, op=dist.ReduceOp.MAX, group=dp)
+        lo, hi = -int(rng[0].item()), int(rng[1].item())
         tl = tl - lo
-        L = int(tl.max().item()) + 1
+        L = hi - lo + 1
     else:  # caller knows token_to_line.max() + 1 on the host (lines are numbered from 0): no device sync
         L = int(n_lines)
     sig = torch.sigmoid(pred)
     cnt = torch.zeros(L + 4, device=pred.device, dtype=pred.dtype).index_add_(0, tl + 2, torch.ones_like(tl, dtype=pred.dtype))
     s_sig = torch.zeros(L + 4, C, device=pred.device, dtype=pred.dtype).index_add_(0, tl + 2, sig)
     s_tgt = torch.zeros(L + 4, device=pred.device, dtype=pred.dtype).index_add_(0, tl + 2, target.sum(dim=1))
+    if dp is not None:
+        # data parallel: the reference compares line numbers across the WHOLE flattened batch, so the per-line sums are
+        # global quantities: one small [L + 4, C + 2] all-reduce (differentiable: other ranks' rows see this rank's
+        # sigmoids) makes every row's penalty equal to the single-process value on the concatenated batch
+        packed = _AllReduceSum.apply(torch.cat([s_sig, cnt.unsqueeze(1), s_tgt.unsqueeze(1)], dim=1), dp)
+        s_sig, cnt, s_tgt = packed[:, :C], packed[:, C], packed[:, C + 1]
 
     def window(x):
         return x[0:L] + x[1:L + 1] + x[2:L + 2] + x[3:L + 3] + x[4:L + 4]
@@ -67,7 +95,7 @@ def spatial_penalty(pred, target, token_to_line, n_lines=None):
     return torch.where(live.unsqueeze(1), mean * 0.1, torch.zeros_like(mean))
 
 
-def spatial_aware_focal_loss(pred, target, token_to_line, alpha, gamma, spatial_weight, n_lines=None):
+def spatial_aware_focal_loss(pred, target, token_to_line, alpha, gamma, spatial_weight, n_lines=None, dp=None):
     """SpatialAwareFocalLoss.forward (train.py:128-172)."""
     probs = torch.sigmoid(pred)
     bce = _bce(pred, target)
@@ -75,7 +103,7 @@ def spatial_aware_focal_loss(pred, target, token_to_line, alpha, gamma, spatial_
     focal = focal + torch.where(target == 1.0, torch.relu(0.3 - probs) * 0.5, torch.zeros_like(probs))
     focal = focal + torch.where(target == 0.0, torch.relu(probs - 0.5) * 0.2, torch.zeros_like(probs))
     if token_to_line is not None:  # spatial_weight is 0.2 / 0.1 / 0.05, never 0 (train.py:568-573, 1174-1184)
-        focal = focal + spatial_weight * spatial_penalty(pred, target, token_to_line, n_lines)
+        focal = focal + spatial_weight * spatial_penalty(pred, target, token_to_line, n_lines, dp)
     return focal.mean()
 
 
@@ -316,6 +344,10 @@ class FusedClipAdamW:
         tab_h, ck_h, tab_d, ck_d, _ = self.bufs
         self.n_tensors, self.n_chunks = len(rows), len(chunks)
         tab_h.numpy()[: self.n_tensors * 80] = np.array(rows, dtype=self._DT).view(np.uint8)
+        # which parameter group each table row belongs to + the (lr, wd) it was filled with: refresh_hparams()
+        self._row_group = np.array([gi for gi, g in enumerate(self.opt.param_groups) for p in g["params"]
+                                    if p.grad is not None], dtype=np.int64)
+        self._hp = [(float(g["lr"]), float(g["weight_decay"])) for g in self.opt.param_groups]
         ck_h.numpy()[: self.n_chunks] = np.array(chunks, dtype=np.int32)
         tab_d.copy_(tab_h, non_blocking=True)
         ck_d.copy_(ck_h, non_blocking=True)
@@ -325,7 +357,7 @@ class FusedClipAdamW:
         from . import kernels as kn
 
         capturing = torch.cuda.is_current_stream_capturing()
-        sig = tuple((p.grad.data_ptr(), g["lr"], self._shadow_ptr(p)) for g in self.opt.param_groups
+        sig = tuple((p.grad.data_ptr(), g["lr"], g["weight_decay"], self._shadow_ptr(p)) for g in self.opt.param_groups
                     for p in g["params"] if p.grad is not None)
         if sig != self._sig or self.bufs is None:
             if not capturing:  # eager: gradients are fresh tensors every step -> refill, ping-ponging two buffer sets
@@ -341,6 +373,24 @@ class FusedClipAdamW:
         if self.shadows is not None:  # the kernel rewrote the bf16 shadows it was given together with the weights
             self.shadows.mark_synced(p for g in self.opt.param_groups for p in g["params"] if p.grad is not None)
         return scratch[0].clone(), scratch[1] > 0.5
+
+    def captured_bufs(self):
+        """What a captured graph needs to follow later lr / weight-decay changes: its pinned table, the row -> group map
+        and the values it currently holds."""
+        return {"tab_h": self.bufs[0], "n": self.n_tensors, "row_group": self._row_group, "hp": list(self._hp)}
+
+    def refresh_hparams(self, cap):
+        """Before a graph replay: if a scheduler (ReduceLROnPlateau, train.py:543-550) or the user changed any group's
+        lr / weight_decay, rewrite those two columns of the graph's PINNED table in place — the graph re-uploads the
+        table on every replay.  The device is drained first so that a step still in flight keeps the old values."""
+        hp = [(float(g["lr"]), float(g["weight_decay"])) for g in self.opt.param_groups]
+        if cap is None or hp == cap["hp"]:
+            return
+        torch.cuda.current_stream().synchronize()
+        view = cap["tab_h"].numpy()[: cap["n"] * 80].view(self._DT)
+        view["lr"] = self.np.array([h[0] for h in hp], dtype=self.np.float32)[cap["row_group"]]
+        view["wd"] = self.np.array([h[1] for h in hp], dtype=self.np.float32)[cap["row_group"]]
+        cap["hp"] = hp
 
     def _shadow_ptr(self, p):
         return self.shadows.peek_ptr(p) if self.shadows is not None else 0
@@ -383,11 +433,17 @@ class SmartContractTrainer:
         self.focal = torch.tensor([0.25, 2.0, 0.2], device=dev)
         self._focal_has = torch.tensor([0.1, 1.5, 0.1], device=dev)
         self._focal_none = torch.tensor([0.05, 1.0, 0.05], device=dev)
+        self._w_line = torch.zeros((), device=dev)  # see _refresh_scalars
+        self._w_line_host = None
         groups = [[], [], [], []]
         for n, p in model.named_parameters():
             groups[param_group_of(n, use_gan)].append(p)
-        lr = min(learning_rate, 1e-4)  # train.py:598-601
-        pg = [{"params": g, "lr": lr * m} for g, m in zip(groups, self.LR_MULT) if g]
+        # train.py:530-540 (x1 / x2 / x3 / x0.5 per group) and the guard of train.py:598-601: a base learning rate above
+        # 1e-4 sets EVERY group to a flat 1e-4 (the multipliers are dropped)
+        if learning_rate > 1e-4:
+            pg = [{"params": g, "lr": 1e-4} for g in groups if g]
+        else:
+            pg = [{"params": g, "lr": learning_rate * m} for g, m in zip(groups, self.LR_MULT) if g]
         on_gpu = dev.type == "cuda"
         self.optimizer = torch.optim.AdamW(pg, weight_decay=weight_decay, betas=(0.9, 0.98), eps=1e-9,
                                            fused=on_gpu, capturable=on_gpu and use_cuda_graph)
@@ -413,8 +469,22 @@ class SmartContractTrainer:
         self.last = {}
 
     # ------------------------------------------------------------------------------------------
+    def _refresh_scalars(self):
+        """Host-side training state the reference changes between steps (train.py:872, 906-907, 1030-1041, 1536-1621:
+        current_epoch -> warm-up factor, stability_factor, line_loss_scale; LR schedulers -> param_groups[i]['lr']) is
+        kept in DEVICE memory the step reads at run time, so a captured CUDA graph follows it: the line-loss weight is
+        a device scalar refreshed here (outside the graph) whenever its host value moved, the per-group lr / weight
+        decay live in the optimiser table the graph re-uploads on every replay (FusedClipAdamW.refresh_hparams)."""
+        warm = min(1.0, (self.current_epoch + 1) / self.warmup_epochs)
+        v = float(self.line_vuln_weight * warm * self.stability_factor * self.line_loss_scale)
+        if v != self._w_line_host:
+            self._w_line.fill_(v)
+            self._w_line_host = v
+
     def compute_losses(self, out, batch, syntax_penalty=0.0, n_lines=None):
         dev = out["gen_ce_loss"].device
+        if not (dev.type == "cuda" and torch.cuda.is_current_stream_capturing()):
+            self._refresh_scalars()
         gen = out["gen_ce_loss"] + 0.5 * syntax_penalty
         res = {"gen_loss": gen}
         if self.compute_vuln_heads:
@@ -424,25 +494,38 @@ class SmartContractTrainer:
             if lvl.shape != vl.shape and lvl.shape[1] == vl.shape[2] and lvl.shape[2] == vl.shape[1]:
                 vl = vl.transpose(1, 2).contiguous()
             t2l = batch.get("token_to_line")
+            dp = (self.pg if self.pg is not None else dist.group.WORLD) if self.world > 1 else None
             lv = spatial_aware_focal_loss(lvl.reshape(-1, lvl.shape[-1]), vl.reshape(-1, lvl.shape[-1]).float(),
                                           t2l.reshape(-1) if t2l is not None else None, self.focal[0], self.focal[1],
-                                          self.focal[2], n_lines)
-            self._pending_has_line = vl.sum() > 0  # applied after the optimiser step, like train.py:1174-1184
-            cv = torch.clamp(cv, min=0.0001)
-            lv = torch.clamp(lv, min=0.000001)
-            lv = torch.where(lv > 5.0, lv * 0.1, torch.where(lv > 1.0, lv * 0.5, lv))  # train.py:1189-1194
+                                          self.focal[2], n_lines, dp)
+            has_line = (vl.sum() > 0).float()
         else:
             cv = lv = torch.zeros((), device=dev)
-        warm = min(1.0, (self.current_epoch + 1) / self.warmup_epochs)
-        w_line = self.line_vuln_weight * warm * self.stability_factor * self.line_loss_scale
+            has_line = torch.zeros((), device=dev)
+        z = out.get("discriminator_logits") if self.use_gan else None
+        c_in = None
+        cv_g, lv_g = cv.detach(), lv.detach()  # the values every data-dependent branch below looks at
+        if self.world > 1:
+            # Data parallel: ONE 4-element all-reduce makes every data-dependent branch of the step take the decision
+            # the single-process reference takes on the concatenated batch — the mean discriminator confidence
+            # (train.py:1217, 0.3 / 0.8 branches), the contract / line losses seen by the floors and the > 1 / > 5
+            # rescale (train.py:1185-1194; equal shards: the global mean loss is the mean of the local ones) and the
+            # "batch held a vulnerable line" flag of the focal-loss switch (train.py:1174-1184).
+            conf_l = torch.sigmoid(z.detach().float()).mean() if z is not None else torch.zeros((), device=dev)
+            stats = torch.stack([conf_l.float(), cv_g.float(), lv_g.float(), has_line.float()])
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.pg)
+            c_in = (stats[0:1] / self.world) if z is not None else None
+            cv_g, lv_g, has_line = stats[1] / self.world, stats[2] / self.world, stats[3]
+        if self.compute_vuln_heads:
+            self._pending_has_line = has_line > 0  # applied after the optimiser step, like train.py:1174-1184
+            # floors (train.py:1185-1186: torch.max with a constant => no gradient below the floor) and the rescale of
+            # train.py:1189-1194, decided on the (global) loss value and applied to the local term
+            cv = torch.where(cv_g > 0.0001, cv, torch.full_like(cv, 0.0001))
+            lv = torch.where(lv_g > 0.000001, lv, torch.full_like(lv, 0.000001))
+            lv = lv * torch.where(lv_g > 5.0, 0.1, torch.where(lv_g > 1.0, 0.5, 1.0)).to(lv.dtype)
+        w_line = self._w_line  # device scalar: line_vuln_weight * warm-up * stability_factor * line_loss_scale
         d_loss = adv = conf = None
-        if self.use_gan and out.get("discriminator_logits") is not None:
-            z = out["discriminator_logits"]
-            c_in = None
-            if self.world > 1:  # global mean confidence so every rank takes the single-GPU branch
-                c_in = torch.sigmoid(z.detach().float()).mean().reshape(1)
-                dist.all_reduce(c_in, op=dist.ReduceOp.SUM, group=self.pg)
-                c_in /= self.world
+        if z is not None:
             d_loss, adv, conf = ops.gan_loss(z, c_in)
         if self.use_augmentation and self.use_gan:
             total = 0.5 * gen + 0.25 * cv * self.contract_vuln_weight + 0.2 * lv * w_line + 0.05 * d_loss
@@ -538,15 +621,20 @@ class SmartContractTrainer:
             graph = torch.cuda.CUDAGraph()
             if self._fused_tail is not None:
                 self._fused_tail.prepare_for_capture()
+            self._refresh_scalars()
             torch.cuda.synchronize()
             n0 = _lib.Stats.launches
             with torch.cuda.graph(graph):
                 res = self._step_body(static, syntax_penalty, n_lines)
-            ent = self._graphs[key] = (graph, static, res, _lib.Stats.launches - n0)
+            ent = self._graphs[key] = (graph, static, res, _lib.Stats.launches - n0,
+                                       self._fused_tail.captured_bufs() if self._fused_tail is not None else None)
             _lib.Stats.launches = n0
             if self._fused_tail is not None:
                 self._fused_tail.bufs, self._fused_tail._sig = None, None  # eager steps must not touch the graph's tables
-        graph, static, res, n_launch = ent
+        graph, static, res, n_launch, opt_bufs = ent
+        self._refresh_scalars()
+        if self._fused_tail is not None:
+            self._fused_tail.refresh_hparams(opt_bufs)
         for k, v in tens.items():  # pinned host tensors land directly in the graph's input buffers
             if static[k].data_ptr() != v.data_ptr():
                 static[k].copy_(v, non_blocking=True)

@@ -155,7 +155,7 @@ def test_cabi_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(str(_lib.LIB_PATH))
     for name in declared:
         assert hasattr(lib, name), name
-    assert _lib.load().sct_version() == 100
+    assert _lib.load().sct_version() == 200
 
 
 def test_line_heads_vectorised_match_oracle_loops():
@@ -220,15 +220,15 @@ def test_cabi_argument_errors_are_reported_without_a_gpu():
     from sct_gan_b200 import _lib
 
     lib = _lib.load()
-    rc = lib.sct_embed_ln_pe_fwd(None, None, None, None, None, None, None, None, 8, 4, 10, 768, 1.0, 0.0, 0, 0, None)
+    rc = lib.sct_embed_ln_pe_fwd(None, None, None, None, None, None, None, None, 8, 4, 10, 768, 1.0, 0.0, 0, 0, None, None)
     assert rc != 0 and "null pointer" in _lib.last_error()
     buf = (C.c_float * 8)()
     p = C.cast(buf, C.c_void_p)
     rc = lib.sct_gemm_bf16_nt(p, 8, p, 8, p, 8, None, 1.0, 0, 128, 64, 128, None)
     assert rc != 0 and "empty GEMM" in _lib.last_error()
-    rc = lib.sct_attn_fwd(p, 768, p, p, 768, p, 768, None, None, 1, 8, 16, 16, 64, 0, 0.125, 0.0, 0, 0, None)
+    rc = lib.sct_attn_fwd(p, 768, p, p, 768, p, 768, None, None, 1, 8, 16, 16, 64, 0, 0.125, 0.0, 0, 0, None, None)
     assert rc != 0 and "head_dim" in _lib.last_error()
-    rc = lib.sct_add_dropout_ln_fwd(p, None, 1.0, None, None, p, None, None, None, 4, 100, 0.0, 0, 0, None)
+    rc = lib.sct_add_dropout_ln_fwd(p, None, 1.0, None, None, p, None, None, None, 4, 100, 0.0, 0, 0, None, None)
     assert rc != 0 and "unsupported row width" in _lib.last_error()
     rc = lib.sct_ce_rows(p, p, p, p, 4, 10, 9, 1.0, 0, None)
     assert rc != 0 and "pitch" in _lib.last_error()
@@ -238,7 +238,7 @@ def test_cabi_argument_errors_are_reported_without_a_gpu():
     need = lib.sct_attn_bwd_workspace_bytes(2, 8, 100, 300)
     assert need == 2 * 8 * 300 * 128 * 2  # [B*H][Lk][Lq rounded up to 64] bf16
     rc = lib.sct_attn_bwd_ws(p, 768, p, p, 768, p, p, 768, p, p, p, 768, p, p, 768, None, 2, 8, 100, 300, 96, 0, 0.1,
-                             0.0, 0, 0, p, need - 1, None)
+                             0.0, 0, 0, None, p, need - 1, None)
     assert rc != 0 and "workspace too small" in _lib.last_error()
 
 
