@@ -57,8 +57,102 @@ class ResidualLineFeatureExtractor(nn.Module):
         return y + 0.1 * x
 
 
-def _mlp(dims_acts):
-    return nn.Sequential(*dims_acts)
+# ---------------------------------------------------------------------------------------------------
+# Sub-module shims.  inference.py does not only call `model(...)`: it drives `model.encoder(x,
+# src_key_padding_mask=)`, `model.ast_attention(query=, key=, value=, key_padding_mask=) -> (out, weights)`,
+# `model.cross_attention(...)` and `model.decoder(tgt, memory, tgt_mask=, memory_key_padding_mask=)` directly
+# (/root/reference/SCT-GAN/inference.py:558, 563-577, 1150-1155, 1263, 1272-1277).  These subclasses keep the torch
+# module classes' parameters and state_dict keys (they only override `forward`) and send those calls through the
+# same sm_100a kernels as `SmartContractTransformer.forward` — no stock nn.Transformer* / cuDNN path, no CPU path.
+# ---------------------------------------------------------------------------------------------------
+def _owner_of(mod):
+    owner = mod.__dict__.get("_sct_owner")
+    owner = owner() if owner is not None else None
+    if owner is None:
+        raise RuntimeError("this module runs only as a sub-module of sct_gan_b200.SmartContractTransformer")
+    return owner
+
+
+def _need_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f"sct_gan_b200 {what} runs on a B200 only (no CPU fallback): move the tensors to cuda")
+
+
+class FusedTransformerEncoder(nn.TransformerEncoder):
+    """`model.encoder(src, src_key_padding_mask=~mask)` (model.py:424-428, inference.py:558): [B, S, d] fp32 in/out."""
+
+    def forward(self, src, mask=None, src_key_padding_mask=None, is_causal=None):
+        owner = _owner_of(self)
+        _need_cuda(src, "encoder")
+        if mask is not None or is_causal:
+            raise NotImplementedError("encoder attn_mask is not part of the SCT-GAN path (only src_key_padding_mask)")
+        B, S, d = src.shape
+        owner._begin_pass(src.device)
+        kpm = src_key_padding_mask.bool().contiguous() if src_key_padding_mask is not None else None
+        mem, _ = owner._encode(src.reshape(B * S, d).float().contiguous(), B, S, kpm)
+        ops.DropoutRng.detach_sites(owner)
+        return mem.view(B, S, d)
+
+
+class FusedTransformerDecoder(nn.TransformerDecoder):
+    """`model.decoder(tgt, memory, tgt_mask=causal | None, memory_key_padding_mask=~src_mask)` (model.py:949-954,
+    inference.py:1150-1155, 1272-1277).  Returns the residual stream [B, T, d] fp32 WITHOUT output_norm, like
+    nn.TransformerDecoder(norm=None).  tgt_mask must be None or the square-subsequent mask (float -inf / bool upper
+    triangle): the kernel applies the causal predicate itself, the mask tensor is only checked."""
+
+    def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
+                memory_key_padding_mask=None, tgt_is_causal=None, memory_is_causal=False):
+        owner = _owner_of(self)
+        _need_cuda(tgt, "decoder")
+        if memory_mask is not None or tgt_key_padding_mask is not None or memory_is_causal:
+            raise NotImplementedError("decoder: only tgt_mask (causal) and memory_key_padding_mask are on the SCT-GAN path")
+        B, T, d = tgt.shape
+        S = memory.shape[1]
+        causal = False
+        if tgt_mask is not None:
+            m = tgt_mask if tgt_mask.dtype == torch.bool else (tgt_mask == float("-inf"))
+            want = torch.ones((T, T), dtype=torch.bool, device=m.device).triu(1)
+            ok = m.shape == (T, T) and bool((m == want).all())
+            if ok and tgt_mask.dtype != torch.bool:
+                ok = bool((tgt_mask.masked_fill(m, 0.0) == 0).all())
+            if not ok:
+                raise NotImplementedError("decoder tgt_mask must be None or generate_square_subsequent_mask(T)")
+            causal = True
+        owner._begin_pass(tgt.device)
+        _, mem_b = ops.residual_ln(memory.reshape(B * S, d).float().contiguous(), None, None, None, mode="cast", want_x=False)
+        kpm = memory_key_padding_mask.bool().contiguous() if memory_key_padding_mask is not None else None
+        x = owner._decode(tgt.reshape(B * T, d).float().contiguous(), mem_b, B, T, S, kpm, causal=causal,
+                          final_norm=False)
+        ops.DropoutRng.detach_sites(owner)
+        return x.view(B, T, d)
+
+
+class FusedMultiheadAttention(nn.MultiheadAttention):
+    """`att(query=, key=, value=, key_padding_mask=) -> (out, None)` for ast_attention / cross_attention /
+    disc_path_attention (model.py:431-448, 1186; inference.py:563-577): [B, L, d] fp32 in/out, key is value.  The
+    averaged attention weights nn.MultiheadAttention would return are discarded by every caller
+    (model.py:433, 443, 1186) and are never materialised here: the second element is None."""
+
+    def forward(self, query, key, value, key_padding_mask=None, need_weights=True, attn_mask=None,
+                average_attn_weights=True, is_causal=False):
+        owner = _owner_of(self)
+        _need_cuda(query, "attention")
+        if attn_mask is not None or is_causal:
+            raise NotImplementedError("attn_mask is not part of the SCT-GAN path for this module")
+        if key is not value and not (key.data_ptr() == value.data_ptr() and key.shape == value.shape):
+            raise NotImplementedError("key and value must be the same tensor (as at every SCT-GAN call site)")
+        B, Lq, d = query.shape
+        Lk = key.shape[1]
+        owner._begin_pass(query.device)
+        _, qb = ops.residual_ln(query.reshape(B * Lq, d).float().contiguous(), None, None, None, mode="cast", want_x=False)
+        if key is query:
+            kb = qb
+        else:
+            _, kb = ops.residual_ln(key.reshape(B * Lk, d).float().contiguous(), None, None, None, mode="cast", want_x=False)
+        kpm = key_padding_mask.bool().contiguous() if key_padding_mask is not None else None
+        o = owner._mha_cross(qb, kb, self, B, Lq, Lk, kpm)
+        ops.DropoutRng.detach_sites(owner)
+        return o.float().view(B, Lq, d), None
 
 
 class SmartContractTransformer(nn.Module):
@@ -77,10 +171,10 @@ class SmartContractTransformer(nn.Module):
         self.path_embedding = self.ast_embedding
         enc_layer = nn.TransformerEncoderLayer(d_model=d, nhead=nhead, dim_feedforward=dim_feedforward,
                                                dropout=dropout, batch_first=True, activation="gelu", norm_first=True)
-        self.encoder = nn.TransformerEncoder(enc_layer, num_layers=num_encoder_layers, enable_nested_tensor=False)
+        self.encoder = FusedTransformerEncoder(enc_layer, num_layers=num_encoder_layers, enable_nested_tensor=False)
         dec_layer = nn.TransformerDecoderLayer(d_model=d, nhead=nhead, dim_feedforward=dim_feedforward,
                                                dropout=dropout, batch_first=True, activation="gelu", norm_first=True)
-        self.decoder = nn.TransformerDecoder(dec_layer, num_layers=num_decoder_layers)
+        self.decoder = FusedTransformerDecoder(dec_layer, num_layers=num_decoder_layers)
         self.output_norm = nn.LayerNorm(d)
         self.output_dropout = nn.Dropout(dropout)
         self.output_layer = nn.Linear(d, vocab_size)
@@ -104,15 +198,15 @@ class SmartContractTransformer(nn.Module):
             nn.Sequential(nn.Linear(d // 2, d // 4), nn.GELU(), nn.Dropout(0.1), nn.Linear(d // 4, 1))
             for _ in range(num_vulnerability_types)])
         self._debug_mode = False
-        self.ast_attention = nn.MultiheadAttention(d, nhead, dropout=dropout, batch_first=True)
-        self.cross_attention = nn.MultiheadAttention(d, nhead, dropout=dropout, batch_first=True)
+        self.ast_attention = FusedMultiheadAttention(d, nhead, dropout=dropout, batch_first=True)
+        self.cross_attention = FusedMultiheadAttention(d, nhead, dropout=dropout, batch_first=True)
         self.feature_fusion = nn.Sequential(
             nn.Linear(2 * d, d), nn.LayerNorm(d), nn.GELU(), nn.Dropout(dropout),
             nn.Linear(d, d // 2), nn.LayerNorm(d // 2), nn.GELU(), nn.Dropout(dropout),
             nn.Linear(d // 2, d))
         self.use_gan = use_gan
         if use_gan:
-            self.disc_path_attention = nn.MultiheadAttention(d, nhead, dropout=dropout, batch_first=True)
+            self.disc_path_attention = FusedMultiheadAttention(d, nhead, dropout=dropout, batch_first=True)
             self.disc_grammar_embedding = nn.Embedding(vocab_size, d)  # never used in forward (model.py:249)
             self.disc_grammar_projection = nn.Linear(d, d)
             self.disc_feature_extractor = nn.Sequential(
@@ -131,6 +225,12 @@ class SmartContractTransformer(nn.Module):
         for p in self.feature_fusion.parameters():  # model.py:285-286: clamp parameter grads to +-1
             p.register_hook(self.hook_fn)
         self._shadow = ops.ShadowCache()
+        import weakref
+
+        for sub in (self.encoder, self.decoder, self.ast_attention, self.cross_attention,
+                    getattr(self, "disc_path_attention", None)):
+            if sub is not None:  # plain attribute (not a registered sub-module / buffer): no cycle in state_dict
+                sub.__dict__["_sct_owner"] = weakref.ref(self)
         self._heads_stream = None
         # training: vulnerability heads on a side stream, overlapped with the decoder (SCT_HEADS_SIDE_STREAM=0: A/B timing)
         self.heads_side_stream = __import__("os").environ.get("SCT_HEADS_SIDE_STREAM", "1") != "0"
@@ -172,6 +272,21 @@ class SmartContractTransformer(nn.Module):
         self.current_epoch = epoch
 
     # ------------------------------------------------------------------------------ fused blocks
+    def _begin_pass(self, device, whole_forward=False):
+        """Start of a pass through the kernels: bf16 weight copies are re-validated; in training mode `forward`
+        advances the model's dropout epoch (device counter: also advances under CUDA-graph replay) and numbers its
+        dropout sites from 0.  A sub-module shim called on its own (inference.py's direct `model.encoder(...)` calls)
+        must NOT move the epoch — the backward of an earlier shim call would then regenerate different masks — so
+        its sites continue a separate host-side numbering instead (fresh masks per call, epoch untouched)."""
+        self._shadow.begin_step(refresh=self.training)
+        if not self.training:
+            return
+        if whole_forward:
+            self._step_counter += 1
+            ops.DropoutRng.begin_step(self, device)
+        else:
+            ops.DropoutRng.attach(self, device)
+
     def _p(self):
         return self.dropout_p if self.training else 0.0
 
@@ -237,20 +352,25 @@ class SmartContractTransformer(nn.Module):
         z = self._lin(ops.ln_act(z, ff[5].weight, ff[5].bias, p), ff[8])
         return ops.residual_ln(mem, z, None, None, 0.1, 0.0, "cast")
 
-    def _decode(self, x, mem_b, B, T, S, src_kpm):
+    def _decode(self, x, mem_b, B, T, S, src_kpm, causal=True, final_norm=True):
         """nn.TransformerDecoder, norm_first (torch transformer.py:1131-1205) + output_norm/output_dropout.
-        Returns the bf16 rows fed to the vocab projection."""
+        Returns the bf16 rows fed to the vocab projection; with final_norm=False the fp32 residual stream of the
+        last layer instead (what `model.decoder(...)` itself returns: the stack has norm=None)."""
         p = self._p()
         layers = self.decoder.layers
         _, y = ops.residual_ln(x, None, layers[0].norm1.weight, layers[0].norm1.bias, mode="ln", want_x=False)
         for i, layer in enumerate(layers):
-            a = self._mha_self(y, layer.self_attn, B, T, None, True)
+            a = self._mha_self(y, layer.self_attn, B, T, None, causal)
             x, y = ops.residual_ln(x, a, layer.norm2.weight, layer.norm2.bias, 1.0, p, "ln")
             c = self._mha_cross(y, mem_b, layer.multihead_attn, B, T, S, src_kpm)
             x, y = ops.residual_ln(x, c, layer.norm3.weight, layer.norm3.bias, 1.0, p, "ln")
             f = self._ffn(y, layer)
-            nxt = layers[i + 1].norm1 if i + 1 < len(layers) else self.output_norm
-            x, y = ops.residual_ln(x, f, nxt.weight, nxt.bias, 1.0, p, "ln", want_x=(i + 1 < len(layers)))
+            last = i + 1 == len(layers)
+            if last and not final_norm:
+                x, _ = ops.residual_ln(x, f, None, None, 1.0, p, "none")
+                return x
+            nxt = layers[i + 1].norm1 if not last else self.output_norm
+            x, y = ops.residual_ln(x, f, nxt.weight, nxt.bias, 1.0, p, "ln", want_x=not last)
         if p > 0:
             _, y = ops.residual_ln(None, y, None, None, 1.0, p, "cast", want_x=False)
         return y
@@ -378,10 +498,7 @@ class SmartContractTransformer(nn.Module):
             raise RuntimeError("sct_gan_b200 runs on a B200 only (no CPU fallback): move the batch to cuda")
         B, S = input_ids.shape
         d = self.d_model
-        self._shadow.begin_step(refresh=self.training)
-        if self.training:
-            self._step_counter += 1
-            ops.DropoutRng.begin_step(self, input_ids.device)
+        self._begin_pass(input_ids.device, whole_forward=True)
         x, _ = self._embed(input_ids, self.embedding, self.embedding_norm, True, False)
         src_mask = attention_mask.bool() if attention_mask is not None else \
             torch.ones((B, S), dtype=torch.bool, device=input_ids.device)

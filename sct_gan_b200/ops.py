@@ -58,6 +58,20 @@ class DropoutRng:
         cls.counter = 0
 
     @classmethod
+    def attach(cls, owner, device):
+        """Draw the following sites from `owner`'s stream WITHOUT advancing its epoch (sub-module shims): the site
+        numbering continues from a per-model counter kept apart from the numbers `forward` uses."""
+        if getattr(owner, "_drop_epoch", None) is None or owner._drop_epoch.device != device:
+            cls.begin_step(owner, device)  # first use: creates the epoch tensor and the seed
+        cls.seed, cls.epoch = owner._drop_seed, owner._drop_epoch
+        nxt = getattr(owner, "_shim_sites", 0x8000)
+        cls.counter = nxt if nxt < 0xF0000 else 0x8000
+
+    @classmethod
+    def detach_sites(cls, owner):
+        owner._shim_sites = cls.counter
+
+    @classmethod
     def draw(cls):
         cls.counter += 1
         return cls.seed, cls.counter, cls.epoch

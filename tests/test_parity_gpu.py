@@ -393,3 +393,147 @@ def test_fused_clip_adamw_matches_torch_and_oracle(cuda_dev, scale):
         if p.grad is not None:
             assert ob.state[p]["step"].item() == expect_steps
     assert torch.equal(mb.dead, base.dead) and len(ob.state[mb.dead]) == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# Sub-module shims: inference.py drives the model's parts directly; those calls must run the CUDA path too.
+def test_inference_py_direct_submodule_calls_match_oracle(cuda_dev):
+    """Replays /root/reference/SCT-GAN/inference.py:542-606 (`_process_single_window`: embeddings -> model.encoder ->
+    model.ast_attention -> model.cross_attention -> model.feature_fusion) and :1144-1160 (one generation step:
+    model.decoder with the bool upper-triangular tgt_mask -> output_norm -> output_layer) statement by statement on
+    the drop-in module and compares with the oracle's restatement of model.py."""
+    import math
+
+    from oracle import sct_oracle as O
+    from sct_gan_b200 import _lib
+
+    g = torch.load(GOLDEN[0], map_location="cpu", weights_only=False)
+    model, sd, batch = build(g)
+    cfg = g["cfg"]
+    n0 = _lib.Stats.launches
+    with torch.no_grad():
+        input_ids, ast_input_ids = batch["input_ids"], batch["ast_input_ids"]
+        attention_mask, ast_attention_mask = batch["attention_mask"], batch["ast_attention_mask"]
+        contract_emb = model.embedding(input_ids) * math.sqrt(model.d_model)
+        contract_emb = model.embedding_dropout(contract_emb)
+        contract_emb = model.embedding_norm(contract_emb)
+        contract_emb = model.pos_encoder(contract_emb.transpose(0, 1)).transpose(0, 1)
+        ast_emb = model.ast_embedding(ast_input_ids) * math.sqrt(model.d_model)
+        ast_emb = model.ast_embedding_dropout(ast_emb)
+        ast_emb = model.ast_embedding_norm(ast_emb)
+        ast_emb = model.pos_encoder(ast_emb.transpose(0, 1)).transpose(0, 1)
+        src_mask = attention_mask.bool()
+        memory = model.encoder(contract_emb, src_key_padding_mask=~src_mask)
+        ast_attention_mask = ast_attention_mask.bool()
+        ast_attn_output, w = model.ast_attention(query=memory, key=ast_emb, value=ast_emb,
+                                                 key_padding_mask=~ast_attention_mask)
+        assert w is None
+        memory = memory + 0.1 * ast_attn_output
+        cross_attn_output, _ = model.cross_attention(query=memory, key=ast_emb, value=ast_emb,
+                                                     key_padding_mask=~ast_attention_mask)
+        fused_features = model.feature_fusion(torch.cat([memory, 0.1 * cross_attn_output], dim=-1))
+        memory = memory + 0.1 * fused_features
+        # inference.py:1144-1160
+        tgt = batch["target_ids"][:, :17]
+        tgt_mask = torch.triu(torch.ones(tgt.size(1), tgt.size(1)), diagonal=1).bool().to(tgt.device)
+        tgt_mask = tgt_mask.masked_fill(tgt_mask == 1, float("-inf"))
+        tgt_emb = model.embedding(tgt) * math.sqrt(model.d_model)
+        tgt_emb = model.embedding_dropout(tgt_emb)
+        tgt_emb = model.embedding_norm(tgt_emb)
+        tgt_emb = model.pos_encoder(tgt_emb.transpose(0, 1)).transpose(0, 1)
+        out = model.decoder(tgt_emb, memory, tgt_mask=tgt_mask, memory_key_padding_mask=~src_mask)
+        out = model.output_norm(out)
+        out = model.output_dropout(out)
+        logits = model.output_layer(out[:, -1, :])
+        # float causal mask (model.generate_square_subsequent_mask) and tgt_mask=None for one token (:1272-1277)
+        out_f = model.decoder(tgt_emb, memory, tgt_mask=model.generate_square_subsequent_mask(tgt.size(1)).to(tgt.device),
+                              memory_key_padding_mask=~src_mask)
+        one = model.decoder(tgt_emb[:, :1], memory, tgt_mask=None, memory_key_padding_mask=~src_mask)
+    assert _lib.Stats.launches - n0 > 40  # the sm_100a kernels ran (no stock nn.Transformer path)
+    cb = {k: v.cpu() for k, v in batch.items()}
+    mem_ref, src_kpm = O.encode_memory(sd, cfg, cb, torch.float32)
+    assert rel_l2(memory, mem_ref) < 2e-2
+    tx = O.embed(sd, "embedding", "embedding_norm", cb["target_ids"][:, :17], cfg["d_model"], torch.float32)
+    dec_ref = O.decoder(sd, tx, mem_ref, src_kpm, cfg, torch.float32)
+    assert rel_l2(out_f, dec_ref) < 2e-2
+    ref_logits = O.linear(O.layer_norm(dec_ref, sd["output_norm.weight"], sd["output_norm.bias"])[:, -1, :],
+                          sd["output_layer.weight"], sd["output_layer.bias"])
+    assert rel_l2(logits, ref_logits) < 2e-2
+    assert rel_l2(one[:, 0], dec_ref[:, 0]) < 2e-2  # the first position only sees itself: causal == unmasked
+    with pytest.raises(NotImplementedError):
+        model.decoder(tgt_emb, memory, tgt_mask=torch.zeros(17, 17, device=tgt.device).bool().fill_(True))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.encoder(contract_emb.cpu())
+
+
+def test_captured_step_follows_epoch_and_lr_changes(cuda_dev):
+    """host scalars the reference changes during training — current_epoch (warm-up factor of the
+    line loss, train.py:906-907), stability_factor / line_loss_scale (:1030-1041) and the optimiser's lr
+    (ReduceLROnPlateau, :543-550) — must act on a CAPTURED step exactly as on an eager one."""
+    from oracle import sct_oracle as O
+    from sct_gan_b200 import SmartContractTrainer, SmartContractTransformer
+
+    cfg = {**O.DEFAULT_CFG, **dict(num_encoder_layers=1, num_decoder_layers=1, dim_feedforward=256,
+                                   max_length=128, vocab_size=512, dropout=0.0)}
+    batch = O.make_batch(2, 64, 32, 512, seed=3, device="cuda")
+    n_lines = int(batch["token_to_line"].max()) + 1
+
+    def run(use_graph):
+        torch.manual_seed(5)
+        m = SmartContractTransformer(**cfg)
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        m.load_state_dict(O.synth_state_dict(shapes, 3))
+        m = m.cuda()
+        tr = SmartContractTrainer(m, learning_rate=1e-5, use_augmentation=True, use_gan=True, use_cuda_graph=use_graph)
+        log = []
+        for step in range(7):
+            if step == 3:  # after capture (step 1 = warm-up, step 2 = capture): epoch, scale and lr all move
+                tr.current_epoch = 4
+                tr.line_loss_scale = 0.5
+                for gq in tr.optimizer.param_groups:
+                    gq["lr"] *= 50.0
+            if step == 5:
+                tr.stability_factor = 0.25
+                for gq in tr.optimizer.param_groups:
+                    gq["lr"] = 0.0
+            res = tr.train_step(batch, n_lines=n_lines)
+            log.append((res["total_loss"].item(), res["line_vuln_loss"].item()))
+        return log, m.output_layer.bias.detach().clone(), m.encoder.layers[0].linear1.weight.detach().clone()
+
+    eager, eb, ew = run(False)
+    graph, gb, gw = run(True)
+    for (a, la), (b, lb) in zip(eager, graph):
+        assert abs(a - b) < 1e-4 * abs(a) and abs(la - lb) < 1e-4 * abs(la) + 1e-9, (eager, graph)
+    # warm-up factor 0.2 -> 1.0 (x 0.5 scale) must be visible in the total loss of the captured run
+    assert abs(graph[3][0] - graph[2][0]) > 1e-4 * abs(graph[2][0])
+    assert (eb - gb).abs().max().item() < 1e-6 and (ew - gw).abs().max().item() < 1e-6
+    # lr = 0 for the last two steps: identical losses there (weights frozen), in both modes
+    assert abs(graph[5][0] - graph[6][0]) < 1e-6 * abs(graph[5][0])
+
+
+def test_two_models_interleaved_keep_their_own_dropout_masks(cuda_dev):
+    """the dropout epoch is a per-call argument captured at forward time, so a second model's
+    forward between a model's forward and backward cannot change the masks that backward regenerates.  With masks
+    consistent, d loss / d x of a dropout-residual site equals the finite difference of the SAME masked function."""
+    from sct_gan_b200 import ops
+
+    class Owner:  # stands in for a module: DropoutRng keeps its state on the owner
+        pass
+
+    a, b = Owner(), Owner()
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(64, 768, device=dev, generator=g)
+    br = torch.randn(64, 768, device=dev, generator=g).bfloat16().requires_grad_(True)
+    ops.DropoutRng.begin_step(a, dev)
+    xa, _ = ops.residual_ln(x, br, None, None, 1.0, 0.5, "none")
+    # another model trains in between (several forwards: its epoch differs from a's)
+    for _ in range(3):
+        ops.DropoutRng.begin_step(b, dev)
+        ops.residual_ln(x, br.detach(), None, None, 1.0, 0.5, "none")
+    xa.sum().backward()
+    keep_fwd = ((xa - x).abs() > 0)  # where the branch survived in the forward
+    keep_bwd = br.grad.float().abs() > 0
+    live = br.detach().float().abs() > 0
+    assert torch.equal(keep_fwd & live, keep_bwd & live)
+    assert 0.4 < keep_bwd.float().mean().item() < 0.6
