@@ -97,7 +97,7 @@ class Stats:
     """Launch accounting + optional per-call CUDA-event timing (bench.py's roofline leg).
 
     `launches` counts device kernels launched through the C ABI.  With `events` set to a list, every call
-    whose name is in `timed` is bracketed by CUDA events recorded on the launching (current torch) stream
+    whose name is in `timed` (None = every call) is bracketed by CUDA events recorded on the launching (current torch) stream
     and appended as (name, work, start_event, end_event), `work` being the call's algorithmic flops/bytes
     supplied by the wrapper through `annotate`."""
     launches = 0
@@ -118,7 +118,7 @@ def call(name: str, *args) -> None:
     fn = getattr(load(), name)
     ev = Stats.events
     name = STAT_NAME.get(name, name)
-    if ev is not None and name in Stats.timed:
+    if ev is not None and (Stats.timed is None or name in Stats.timed):
         import torch
 
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -128,6 +128,7 @@ def call(name: str, *args) -> None:
         ev.append((name, Stats._work, e0, e1))
     else:
         rc = fn(*args)
+    Stats._work = 0.0  # a call that does not annotate must not inherit the previous call's work
     Stats.launches += KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         raise RuntimeError(f"{name} failed (rc={rc}): {last_error()}")

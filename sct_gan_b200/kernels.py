@@ -66,6 +66,8 @@ def embed_ln_pe_fwd(ids, table, gamma, beta, pe, seq_len, scale, p_drop=0.0, see
     out_f32 = torch.empty((n_tok, d), dtype=F32, device=dev) if want_f32 else None
     out_bf16 = torch.empty((n_tok, d), dtype=BF16, device=dev) if want_bf16 else None
     stats = torch.empty((n_tok, 2), dtype=F32, device=dev)
+    # algorithmic bytes per token: id + fp32 table row + outputs + (mean, rstd)
+    _lib.Stats.annotate(float(n_tok) * (8 + 4 * d + (4 * d if want_f32 else 0) + (2 * d if want_bf16 else 0) + 8))
     _lib.call("sct_embed_ln_pe_fwd", _ptr(ids), _ptr(table), _ptr(gamma), _ptr(beta), _ptr(pe),
               _ptr(out_f32), _ptr(out_bf16), _ptr(stats), n_tok, seq_len, vocab, d, float(scale),
               float(p_drop), seed, offset, _eptr(epoch), _stream())
@@ -80,6 +82,8 @@ def embed_ln_pe_bwd(g, ids, table, gamma, stats, dtable, dgamma, dbeta, scale, p
     g_f32 = g if g.dtype == F32 else None
     g_bf16 = g if g.dtype == BF16 else None
     assert g.is_contiguous() and g.numel() == n_tok * d
+    # dY + re-gathered fp32 row + fp32 read-modify-write scatter into the table gradient + stats
+    _lib.Stats.annotate(float(n_tok) * (g.element_size() * d + 4 * d + 8 * d + 8 + 8))
     _lib.call("sct_embed_ln_pe_bwd", _ptr(g_f32), _ptr(g_bf16), _ptr(ids), _ptr(table), _ptr(gamma),
               _ptr(stats), _ptr(dtable), _ptr(dgamma), _ptr(dbeta), n_tok, vocab, d, float(scale),
               float(p_drop), seed, offset, _eptr(epoch), _stream())
@@ -114,6 +118,9 @@ def add_dropout_ln_bwd(g_xout, g_yln, g_ycast, xprime, stats, gamma, alpha, dgam
     dev = ref.device
     g_x = torch.empty((n_rows, d), dtype=F32, device=dev) if want_gx else None
     g_branch = torch.empty((n_rows, d), dtype=BF16, device=dev) if want_gbranch else None
+    _lib.Stats.annotate(float(n_rows * d) * ((4 if g_xout is not None else 0) + (2 if g_yln is not None else 0)
+                                             + (2 if g_ycast is not None else 0) + (4 if xprime is not None else 0)
+                                             + (4 if want_gx else 0) + (2 if want_gbranch else 0)))
     _lib.call("sct_add_dropout_ln_bwd", _ptr(g_xout), _ptr(g_yln), _ptr(g_ycast), _ptr(xprime),
               _ptr(stats), _ptr(gamma), float(alpha), _ptr(g_x), _ptr(g_branch), _ptr(dgamma),
               _ptr(dbeta), n_rows, d, float(p_drop), seed, offset, _eptr(epoch), _stream())
@@ -125,6 +132,7 @@ def ln_act_fwd(z, gamma, beta, p_drop=0.0, seed=0, offset=0, epoch=None):
     n_rows, d = z.shape
     h = torch.empty_like(z)
     stats = torch.empty((n_rows, 2), dtype=F32, device=z.device)
+    _lib.Stats.annotate(float(n_rows * d) * 4)
     _lib.call("sct_ln_act_fwd", _ptr(z), _ptr(gamma), _ptr(beta), _ptr(h), _ptr(stats), n_rows, d,
               float(p_drop), seed, offset, _eptr(epoch), _stream())
     return h, stats
@@ -134,6 +142,7 @@ def ln_act_bwd(g_h, z, stats, gamma, beta, dgamma, dbeta, p_drop=0.0, seed=0, of
     _chk(g_h, BF16, "g_h")
     n_rows, d = z.shape
     g_z = torch.empty_like(z)
+    _lib.Stats.annotate(float(n_rows * d) * 6)
     _lib.call("sct_ln_act_bwd", _ptr(g_h), _ptr(z), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(g_z),
               _ptr(dgamma), _ptr(dbeta), n_rows, d, float(p_drop), seed, offset, _eptr(epoch), _stream())
     return g_z
@@ -142,6 +151,7 @@ def ln_act_bwd(g_h, z, stats, gamma, beta, dgamma, dbeta, p_drop=0.0, seed=0, of
 def gelu_dropout_fwd(z, p_drop=0.0, seed=0, offset=0, epoch=None):
     _chk(z, BF16, "z")
     h = torch.empty_like(z)
+    _lib.Stats.annotate(float(z.numel()) * 4)
     _lib.call("sct_gelu_dropout_fwd", _ptr(z), _ptr(h), z.numel(), float(p_drop), seed, offset, _eptr(epoch), _stream())
     return h
 
@@ -149,6 +159,7 @@ def gelu_dropout_fwd(z, p_drop=0.0, seed=0, offset=0, epoch=None):
 def gelu_dropout_bwd(g_h, z, p_drop=0.0, seed=0, offset=0, epoch=None):
     _chk(g_h, BF16, "g_h"), _chk(z, BF16, "z")
     g_z = torch.empty_like(z)
+    _lib.Stats.annotate(float(z.numel()) * 6)
     _lib.call("sct_gelu_dropout_bwd", _ptr(g_h), _ptr(z), _ptr(g_z), z.numel(), float(p_drop), seed,
               offset, _eptr(epoch), _stream())
     return g_z
@@ -159,6 +170,7 @@ def colsum_bf16(x, out, scale=1.0):
     x, ld = _rows2d(x, BF16, "x")
     M, N = x.shape
     _chk(out, F32, "out")
+    _lib.Stats.annotate(float(M * N) * 2)
     _lib.call("sct_colsum_bf16", _ptr(x), ld, _ptr(out), M, N, float(scale), _stream())
 
 
@@ -169,6 +181,7 @@ def cast_scale(src, dst, col_off=0, scale=1.0):
     dst, ld = _rows2d(dst, BF16, "dst")
     f = src if src.dtype == F32 else None
     b = src if src.dtype == BF16 else None
+    _lib.Stats.annotate(float(rows * cols) * (src.element_size() + 2))
     _lib.call("sct_cast_scale", _ptr(f, 8), _ptr(b, 8), src.stride(0), _ptr(dst, 8), rows, cols, ld, col_off,
               float(scale), _stream())
 
@@ -176,6 +189,7 @@ def cast_scale(src, dst, col_off=0, scale=1.0):
 def seq_mean_fwd(x, y, B, S, d):
     ref = x if x is not None else y
     out = torch.empty((B, d), dtype=F32, device=ref.device)
+    _lib.Stats.annotate(float(B * S * d) * ((4 if x is not None else 0) + (2 if y is not None else 0)))
     _lib.call("sct_seq_mean_fwd", _ptr(x), _ptr(y), _ptr(out), B, S, d, _stream())
     return out
 
@@ -184,6 +198,7 @@ def seq_mean_bwd(g, B, S, d, want_f32=False, want_bf16=True):
     _chk(g, F32, "g")
     gx = torch.empty((B * S, d), dtype=F32, device=g.device) if want_f32 else None
     gy = torch.empty((B * S, d), dtype=BF16, device=g.device) if want_bf16 else None
+    _lib.Stats.annotate(float(B * S * d) * ((4 if want_f32 else 0) + (2 if want_bf16 else 0)))
     _lib.call("sct_seq_mean_bwd", _ptr(g), _ptr(gx), _ptr(gy), B, S, d, _stream())
     return gx, gy
 
@@ -349,6 +364,7 @@ def ce_rows(logits, targets, V, grad_scale=1.0, write_grad=True):
     _chk(targets, torch.int64, "targets")
     row_loss = torch.empty(rows, dtype=F32, device=logits.device)
     row_lse = torch.empty(rows, dtype=F32, device=logits.device)
+    _lib.Stats.annotate(float(rows) * V * (4 if write_grad else 2))  # read once (+ write the gradient once)
     _lib.call("sct_ce_rows", _ptr(logits), _ptr(targets), _ptr(row_loss), _ptr(row_lse), rows, V, ld,
               float(grad_scale), int(write_grad), _stream())
     return row_loss, row_lse
@@ -363,6 +379,7 @@ def small_linear_fwd(x, w, bias, out_bf16=False):
     xf = x if x.dtype == F32 else None
     xb = x if x.dtype == BF16 else None
     y = torch.empty((M, N), dtype=BF16 if out_bf16 else F32, device=x.device)
+    _lib.Stats.annotate(float(N * K) * 4 + float(M * K) * x.element_size() + float(M * N) * y.element_size())
     _lib.call("sct_small_linear_fwd", _ptr(xf), _ptr(xb), _ptr(w), _ptr(bias), None if out_bf16 else _ptr(y),
               _ptr(y) if out_bf16 else None, M, N, K, _stream())
     return y
@@ -379,6 +396,7 @@ def small_linear_bwd(dy, x, w, need_dx=True, dx_bf16=False):
     dw = torch.empty((N, K), dtype=F32, device=x.device)
     db = torch.empty((N,), dtype=F32, device=x.device)
     dx = torch.empty((M, K), dtype=BF16 if dx_bf16 else F32, device=x.device) if need_dx else None
+    _lib.Stats.annotate(float(N * K) * 8 + float(M * K) * 2 * x.element_size() + float(M * N) * dy.element_size())
     _lib.call("sct_small_linear_bwd", _ptr(dyf), _ptr(dyb), _ptr(xf), _ptr(xb), _ptr(w),
               _ptr(dx) if (need_dx and not dx_bf16) else None, _ptr(dx) if (need_dx and dx_bf16) else None,
               _ptr(dw), _ptr(db), M, N, K, _stream())
@@ -400,8 +418,10 @@ def gan_loss_bwd(z, c, g_d, g_adv):
 
 # ------------------------------------------------------------------------------------- optimiser tail
 def clip_adamw_step(table, n_tensors, chunks, n_chunks, loss, sqnorm3, out2, max_norm, disc_mult, vuln_mult,
-                    beta1, beta2, eps):
+                    beta1, beta2, eps, n_elems=0):
     """table: uint8 device tensor of n_tensors sct_opt_tensor records; chunks: int32 [n_chunks, 2]."""
+    # norm pass reads g; update pass reads g, p, m, v and writes p, m, v (+ the bf16 weight copy): 34 B / parameter
+    _lib.Stats.annotate(float(n_elems) * 34)
     _lib.call("sct_clip_adamw_step", _ptr(table), n_tensors, _ptr(chunks, 8), n_chunks, _sptr(loss), _sptr(sqnorm3),
               _sptr(out2), float(max_norm), float(disc_mult), float(vuln_mult), float(beta1), float(beta2),
               float(eps), _stream())

