@@ -300,7 +300,7 @@ def claim_stdout():
 
 # kernel family -> (roofline class, unit); everything a C-ABI call can be is listed (bench `by_call`)
 TENSOR_CALLS = ("sct_gemm_bf16_nt", "sct_gemm_bf16_nn", "sct_gemm_bf16_tn", "sct_attn_fwd_strided", "sct_attn_bwd",
-                "sct_gemm_bf16_nt_act", "sct_gemm_bf16_nn_act", "sct_vocab_ce_fwd", "sct_vocab_ce_bwd")
+                "sct_gemm_bf16_nt_gelu", "sct_gemm_bf16_nn_mul")
 
 
 def traffic_record():
@@ -381,6 +381,7 @@ def main():
     ap.add_argument("--ncu-step", action="store_true",
                     help="warm up, then run ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     ap.add_argument("--torch-profile", default=None, help="write a torch.profiler table of one step to this file and exit")
+    ap.add_argument("--trace", default=None, help="write a chrome trace (CUPTI kernel timeline) of two steps and exit")
     args = ap.parse_args()
     CFG.update(CONFIGS[args.config], name=args.config)
     if args.batch:
@@ -448,6 +449,15 @@ def main():
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
         emit({"ncu_step": "done", "launches_per_step_through_cabi": _lib.Stats.launches // (W + 1)})
+        return
+    if args.trace:
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(2):
+                trainer.train_step(batch, n_lines=n_lines)
+            torch.cuda.synchronize()
+        prof.export_chrome_trace(args.trace)
         return
     if args.torch_profile:
         from torch.profiler import ProfilerActivity, profile

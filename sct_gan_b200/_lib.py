@@ -36,6 +36,8 @@ SIGNATURES = {
     "sct_gemm_bf16_nt": [_p, _i64, _p, _i64, _p, _i64, _p, _f, _i64, _i64, _i64, _i32, _p],
     "sct_gemm_bf16_nn": [_p, _i64, _p, _i64, _p, _i64, _p, _f, _i64, _i64, _i64, _i32, _p],
     "sct_gemm_bf16_tn": [_p, _i64, _p, _i64, _p, _i64, _f, _i64, _i64, _i64, _i32, _p],
+    "sct_gemm_bf16_nt_gelu": [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _f, _u64, _u64, _p, _p],
+    "sct_gemm_bf16_nn_mul": [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _p],
     "sct_gemm_bf16_tn_colsum": [_p, _i64, _p, _i64, _p, _i64, _p, _f, _i64, _i64, _i64, _i32, _p],
     "sct_attn_fwd": [_p, _i64, _p, _p, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _f, _f,
                      _u64, _u64, _p, _p],

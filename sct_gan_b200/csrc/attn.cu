@@ -61,10 +61,12 @@ struct AttnParams {
 };
 
 // ---- attention-probability dropout -------------------------------------------------------------
-// kDropBits: resolution of the drop probability (p is rounded to a multiple of 2^-12: 0.3 -> 0.30005; the scale uses the
-// realised keep probability, so the expectation is exact).  Every bit is one round of the bit-sliced generator, i.e.
-// 4 integer instructions per 32 probabilities, in the forward AND in both backward kernels.
-constexpr int kDropBits = 12;
+// kDropBits: resolution of the drop probability (p is rounded to a multiple of 2^-8: 0.3 -> 77/256 = 0.3008; the scale
+// uses the realised keep probability, so the expectation is exact).  Every bit is one round of the bit-sliced
+// generator, i.e. 4 integer instructions per 32 probabilities, in the forward AND in both backward kernels — and
+// integer / logic instructions run at half rate on sm_100 (tools/micro/alu_rates.cu: LOP3 / PRMT / IMAD 64 per clock
+// per SM against 128 for FFMA), so every round costs as much pipe time as 8 multiply-adds per 32 scores.
+constexpr int kDropBits = 8;
 // keep(b,h,q,k) <=> u(b,h,q,k) >= thresh.  The kDropBits-bit uniforms of 32 consecutive keys of one query
 // row are generated bit-sliced: 16 cheap xorshift-multiply words off one strong hash of (stream key,
 // b*H+h, q, k/32); a 16-step bitwise comparator (one LOP3 per word) then yields the 32 keep bits at
@@ -339,16 +341,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (m_run == -INFINITY || m_new > m_run + 8.0f) m_next = fmaxf(m_run, m_new);
     const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_next);
     const float m_eff = (m_next == -INFINITY) ? 0.f : m_next;
-    float rs = 0.f;
+    // packed fp32 arithmetic (FFMA2 / FADD2: two scores per instruction) for the scale-and-shift and the row sum
+    const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_eff, -m_eff);
+    float2 rs2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int kb = 0; kb < 2; ++kb) {
       const uint32_t kw = keep_word(p, dkey, bh, (uint32_t)q, (uint32_t)((kv0 + c_base) >> 5) + kb);
       float pv[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float e = exp2f(fmaf(__uint_as_float(sr[kb * 32 + i]), p.scale_log2, -m_eff));
-        rs += e;
-        pv[i] = (kw & (1u << i)) ? e : 0.f;
+      for (int i = 0; i < 32; i += 2) {
+        const float2 x = __ffma2_rn(make_float2(__uint_as_float(sr[kb * 32 + i]), __uint_as_float(sr[kb * 32 + i + 1])),
+                                    sc2, nm2);
+        const float2 e = make_float2(exp2f(x.x), exp2f(x.y));
+        rs2 = __fadd2_rn(rs2, e);
+        pv[i] = (kw & (1u << i)) ? e.x : 0.f;
+        pv[i + 1] = (kw & (2u << i)) ? e.y : 0.f;
       }
       // P (bf16, dropped) goes straight back to TMEM as the A operand of the P V product: packed two keys per
       // column over S columns [0, 64), which every thread has read by now (the max exchange above is a block-wide
@@ -361,7 +368,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_st8(tS + lane_sel + hf * 32 + kb * 16 + g8 * 8, pk);
       }
     }
-    l_run = l_run * alpha + rs;
+    l_run = l_run * alpha + (rs2.x + rs2.y);
     m_run = m_next;
     // rescale the running output when some row of this warp raised its max (rare after tile 0)
     if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
@@ -791,6 +798,66 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
+// One [128 keys x 64 queries] half tile of the dK/dV kernel's arithmetic: S^T and dP^T (TMEM, fp32) -> P^T (packed bf16,
+// back to TMEM: A operand of dV += P^T dO) and dS^T (bf16, shared memory: A operand of dK += dS^T Q and source of the
+// workspace store).  Thread = key row r; four 16-query chunks, the TMEM loads of chunk cc + 1 in flight while chunk cc
+// is in the ALUs.  Per score: P = exp2(s * c - lse), m = keep ? 1 / (1 - p) : 0, P~ = P * m, dS = P * (dP * m - D) as
+// packed fp32 pairs (FFMA2 / FMUL2: ~5 instructions per score instead of ~13 scalar ones; the statistics arrive
+// NEGATED in shared memory so they are plain FFMA2 addends).
+template <bool DIAG, bool ROWMASK>
+__device__ __forceinline__ void dkdv_half_tile(uint32_t tST, uint32_t tDPT, uint32_t tPT, uint32_t lane_sel,
+                                               uint32_t sDSTh, const float* __restrict__ nlse,
+                                               const float* __restrict__ ndv, uint32_t kw0, uint32_t kw1, int r, int hh,
+                                               bool row_valid, float scale_log2, float inv_keep) {
+  uint32_t rs[2][16], rp[2][16];
+  tmem_ld16(tST + lane_sel, rs[0]);
+  tmem_ld16(tDPT + lane_sel, rp[0]);
+  const float2 sc2 = make_float2(scale_log2, scale_log2);
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    const int c0 = cc * 16;
+    const uint32_t kw = (cc < 2 ? kw0 : kw1) >> ((cc & 1) * 16);
+    tmem_ld_wait();
+    if (cc + 1 < 4) {
+      tmem_ld16(tST + lane_sel + c0 + 16, rs[(cc + 1) & 1]);
+      tmem_ld16(tDPT + lane_sel + c0 + 16, rp[(cc + 1) & 1]);
+    }
+    const uint32_t (&s_)[16] = rs[cc & 1];
+    const uint32_t (&p_)[16] = rp[cc & 1];
+    float pd[16], ds[16];
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      const float2 nl = *reinterpret_cast<const float2*>(nlse + c0 + i);
+      const float2 nd = *reinterpret_cast<const float2*>(ndv + c0 + i);
+      const float2 x = __ffma2_rn(make_float2(__uint_as_float(s_[i]), __uint_as_float(s_[i + 1])), sc2, nl);
+      float2 pr = make_float2(exp2f(x.x), exp2f(x.y));
+      if (DIAG) {  // causal: key r sees queries >= r only
+        if (r > hh * 64 + c0 + i) pr.x = 0.f;
+        if (r > hh * 64 + c0 + i + 1) pr.y = 0.f;
+      }
+      if (ROWMASK) {
+        pr.x = row_valid ? pr.x : 0.f;
+        pr.y = row_valid ? pr.y : 0.f;
+      }
+      const float2 dm = make_float2((kw & (1u << i)) ? inv_keep : 0.f, (kw & (2u << i)) ? inv_keep : 0.f);
+      const float2 u = __ffma2_rn(make_float2(__uint_as_float(p_[i]), __uint_as_float(p_[i + 1])), dm, nd);
+      const float2 d = __fmul2_rn(pr, u);
+      const float2 pk = __fmul2_rn(pr, dm);
+      ds[i] = d.x;
+      ds[i + 1] = d.y;
+      pd[i] = pk.x;
+      pd[i + 1] = pk.y;
+    }
+    {  // P^T chunk -> TMEM (8 packed columns per 16 queries): the A operand of the dV MMA, no shared-memory trip
+      uint32_t pk[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(pd[2 * i], pd[2 * i + 1]);
+      tmem_st8(tPT + lane_sel + cc * 8, pk);
+    }
+    store_row16_sw128(sDSTh, r, c0, ds);  // dS^T chunk -> shared memory: A operand of the dK MMA and workspace store
+  }
+}
+
 // ---- dK/dV: one CTA per (key tile, head, batch); query tiles stream through in 64-query halves ----
 //   S^T_h = K Q_h^T, dP^T_h = V dO_h^T (TMEM, rows = keys) -> P^T_h, dS^T_h (bf16, smem)
 //   -> dV += P^T_h dO_h, dK += dS^T_h Q_h
@@ -869,8 +936,9 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       for (int i = 0; i < 4; ++i) {
         const int c = lane * 4 + i, qq = q0 + c;
         const long long o = ((long long)b * p.H + h) * p.Lq + qq;
-        lse_s[st * 128 + c] = qq < p.Lq ? p.lse2[o] : INFINITY;
-        dv_s[st * 128 + c] = qq < p.Lq ? p.dvec[o] : 0.f;
+        // negated: the arithmetic warps use them as the addend of packed FFMA2s (exp2(s * c - lse), dP * m - D)
+        lse_s[st * 128 + c] = qq < p.Lq ? -p.lse2[o] : -INFINITY;
+        dv_s[st * 128 + c] = qq < p.Lq ? -p.dvec[o] : 0.f;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_stf + 8 * st);
@@ -975,49 +1043,17 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tc_fence_after();
       const bool diag = p.causal && (qi == jt);
       if (it > 0) mbar_wait(bar_gd + 8 * hh, (it - 1) & 1);  // P^T_h / dS^T_h buffers free again
-      // four 16-query chunks; the TMEM loads of chunk cc + 1 are in flight while chunk cc is in the ALUs
-      uint32_t rs[2][16], rp[2][16];
-      tmem_ld16(tST + lane_sel, rs[0]);
-      tmem_ld16(tDPT + lane_sel, rp[0]);
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c0 = cc * 16;
-        const uint32_t kw = (cc < 2 ? kw0 : kw1) >> ((cc & 1) * 16);
-        tmem_ld_wait();
-        if (cc + 1 < 4) {
-          tmem_ld16(tST + lane_sel + c0 + 16, rs[(cc + 1) & 1]);
-          tmem_ld16(tDPT + lane_sel + c0 + 16, rp[(cc + 1) & 1]);
-        }
-        const uint32_t (&s_)[16] = rs[cc & 1];
-        const uint32_t (&p_)[16] = rp[cc & 1];
-        float pd[16], ds[16];
-        if (row_valid) {
-          float pr[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            pr[i] = exp2f(fmaf(__uint_as_float(s_[i]), p.scale_log2, -lse_s[st * 128 + hh * 64 + c0 + i]));
-          if (diag) {  // warp-uniform: only the diagonal tile pays for the causal comparison
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (r > hh * 64 + c0 + i) pr[i] = 0.f;
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float dm = (kw & (1u << i)) ? p.inv_keep : 0.f;
-            pd[i] = pr[i] * dm;
-            ds[i] = pr[i] * fmaf(__uint_as_float(p_[i]), dm, -dv_s[st * 128 + hh * 64 + c0 + i]);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pd[i] = ds[i] = 0.f;
-        }
-        {  // P^T chunk -> TMEM (8 packed columns per 16 queries): the A operand of the dV MMA, no shared-memory trip
-          uint32_t pk[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(pd[2 * i], pd[2 * i + 1]);
-          tmem_st8(tPT + lane_sel + cc * 8, pk);
-        }
-        store_row16_sw128(sDSTh, r, c0, ds);  // dS^T chunk -> shared memory: A operand of the dK MMA and workspace store
+      // warp-uniform variants: only the diagonal tile pays for the causal comparison, only warps that hold a masked /
+      // out-of-range key row pay for the row select
+      const float* nlse = lse_s + st * 128 + hh * 64;
+      const float* ndv = dv_s + st * 128 + hh * 64;
+      const bool rowmask = !__all_sync(0xffffffffu, row_valid);
+      if (diag) {
+        if (rowmask) dkdv_half_tile<true, true>(tST, tDPT, tPT, lane_sel, sDSTh, nlse, ndv, kw0, kw1, r, hh, row_valid, p.scale_log2, p.inv_keep);
+        else dkdv_half_tile<true, false>(tST, tDPT, tPT, lane_sel, sDSTh, nlse, ndv, kw0, kw1, r, hh, row_valid, p.scale_log2, p.inv_keep);
+      } else {
+        if (rowmask) dkdv_half_tile<false, true>(tST, tDPT, tPT, lane_sel, sDSTh, nlse, ndv, kw0, kw1, r, hh, row_valid, p.scale_log2, p.inv_keep);
+        else dkdv_half_tile<false, false>(tST, tDPT, tPT, lane_sel, sDSTh, nlse, ndv, kw0, kw1, r, hh, row_valid, p.scale_log2, p.inv_keep);
       }
       tmem_st_wait();
       fence_proxy_async_smem();

@@ -39,10 +39,32 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 256;
+constexpr int kThreads = 256;      // plain kernel: TMA, MMA, 4 epilogue warps, 2 column-sum warps (wgrad)
+constexpr int kThreadsEpi = 320;   // fused-epilogue kernels: TMA, MMA, 8 epilogue warps (two per TMEM lane quadrant)
 constexpr int kSmemLimit = 232448;  // 227 KB
 
+// Fused epilogues (SURVEY §8b epilogue enum) for the feed-forward block.
+//   EPI_GELU_FWD: the first linear also applies the activation.  z = A W^T + b stays in registers; the kernel stores
+//     H = dropout(gelu(z)) (what linear2 consumes) and G = mask / (1 - p) * gelu'(z), the LOCAL DERIVATIVE of that
+//     activation + dropout, instead of z itself (torch transformer.py _ff_block: linear1 -> activation -> dropout).
+//     The separate gelu_dropout pass over [M, ff] disappears and nothing has to be recomputed in backward.
+//   EPI_MUL: the dgrad GEMM of the second linear turns dH = dY W2 into dZ = dH * G on the way out (one multiply per
+//     element, no transcendental, no mask regeneration).
+enum Epi { EPI_NONE = 0, EPI_GELU_FWD = 1, EPI_MUL = 2 };
+
+constexpr int kEpiDropBits = 8;  // drop probability resolved to 2^-8, as in the attention kernels
+struct EpiParams {
+  const __nv_bfloat16* z;  // EPI_MUL: elementwise multiplier G [M, ldz]
+  long long ldz;
+  uint32_t k0, k1;         // dropout stream key (seed, offset mixed on the host)
+  const unsigned long long* epoch;  // device-resident epoch folded into the key at run time (nullable)
+  uint32_t tmask[kEpiDropBits];     // bit i of the threshold spread over a word
+  uint32_t thresh;         // 0 = no dropout
+  float inv_keep;
+};
+
 struct GemmParams {
+  EpiParams epi;
   int M, N, K;
   int m_tiles, n_tiles, k_splits;
   int kb_total, kb_per_split;
@@ -52,7 +74,7 @@ struct GemmParams {
   float* colsum;      // nullable (MN-major A only), fp32 [M]: += alpha * sum_k A[k, m]
 };
 
-template <int BN, bool OUT_F32, int CLUSTER>
+template <int BN, bool OUT_F32, int CLUSTER, int EPI = EPI_NONE>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN / CLUSTER * BK * 2;  // this CTA's share of the B tile
@@ -60,11 +82,15 @@ struct Cfg {
   // Epilogue staging: two [128 rows x 128 B] blocks (64 bf16 / 32 fp32 columns each), ping-ponged chunk by chunk.
   // A full-tile staging buffer (64 KB at BN = 256) would leave only 3 pipeline stages, and the mainloop is
   // bound by the bytes it can keep in flight (measured: the MMA thread waited on `full` 44 % of the time).
-  static constexpr int C_BYTES = 2 * BM * 128;
+  // EPI_GELU_FWD stores two tensors per chunk (z and h): two ping-pong pairs.
+  static constexpr int C_BLOCKS = EPI == EPI_GELU_FWD ? 4 : 2;
+  static constexpr int C_BYTES = C_BLOCKS * BM * 128;
   static constexpr int AUX_BYTES = 1024;  // barriers + tmem ptr
-  static constexpr int STAGES_RAW = (kSmemLimit - 1024 - C_BYTES - AUX_BYTES - BN * 4) / STAGE_BYTES;
+  static constexpr int BIAS_BYTES = (EPI != EPI_NONE ? 2 : 1) * BN * 4;  // fused epilogues: one copy per accumulator stage
+  static constexpr int STAGES_RAW = (kSmemLimit - 1024 - C_BYTES - AUX_BYTES - BIAS_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + C_BYTES + AUX_BYTES + BN * 4;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + C_BYTES + AUX_BYTES + BIAS_BYTES;
+  static constexpr int THREADS = EPI != EPI_NONE ? kThreadsEpi : kThreads;
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages (256 or 512, powers of two)
   static_assert(STAGES >= 2, "pipeline too shallow");
 };
@@ -89,11 +115,63 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t) {
   return c;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool OUT_F32, int CLUSTER>
-__global__ void __launch_bounds__(kThreads, 1)
+// ---- fused-epilogue arithmetic --------------------------------------------------------------------------------
+// Exact-erf GELU (activation='gelu') to bf16 accuracy with ONE transcendental per element:
+//   Phi(x) = 0.5 (1 + erf(x / sqrt 2))  ~  0.5 (1 + tanh(x (a + b x^2)))      (a, b fitted against scipy's erf)
+// max |x Phi_fit - x Phi| = 2.7e-4 and max |d/dx| error = 8.7e-4 over the real line — below the bf16 rounding of the
+// stored results (half an ulp is 2e-3 at 1) — and tanh.approx.f32 is a single MUFU.  The derivative is the exact
+// derivative of the fitted function: gelu'(x) = Phi + 0.5 x (1 - t^2)(a + 3 b x^2), so forward and backward are a
+// consistent pair.  All multiplies / FMAs run as packed fp32 pairs (FFMA2 / FMUL2): ~11 instructions per element for
+// BOTH outputs, against ~15 + two MUFUs for the Abramowitz-Stegun erf of the stand-alone kernels — an epilogue warp
+// group has to finish its share of the 128 x 256 tile inside the mainloop of the next one.
+constexpr float kGa = 0.80015708f, kGb = 0.03470089f;
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// (gelu(v), gelu'(v)) for a pair of pre-activations
+__device__ __forceinline__ void gelu_pair(float2 v, float2& val, float2& grad) {
+  const float2 x2 = __fmul2_rn(v, v);
+  const float2 in = __fmul2_rn(v, __ffma2_rn(x2, make_float2(kGb, kGb), make_float2(kGa, kGa)));
+  const float2 t = make_float2(tanh_approx(in.x), tanh_approx(in.y));
+  const float2 phi = __ffma2_rn(t, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+  val = __fmul2_rn(v, phi);
+  // -0.5 x (a + 3 b x^2) and t^2 - 1: gelu' = Phi + [0.5 x (a + 3 b x^2)] (1 - t^2)
+  const float2 tn = __fmul2_rn(v, __ffma2_rn(x2, make_float2(-1.5f * kGb, -1.5f * kGb), make_float2(-0.5f * kGa, -0.5f * kGa)));
+  const float2 w = __ffma2_rn(t, t, make_float2(-1.f, -1.f));
+  grad = __ffma2_rn(tn, w, phi);
+}
+__device__ __forceinline__ uint32_t epi_fmix32(uint32_t h) {
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
+// 32 keep bits for columns [32 cb, 32 cb + 32) of row `row`: bit-sliced threshold comparison of kEpiDropBits-bit
+// uniforms (one strong hash per word, then one xorshift-multiply + one LOP3 per bit), ~1.5 instructions per element.
+// The forward and the backward epilogue own the same (row, 32-column block) and regenerate the identical word.
+__device__ __forceinline__ uint32_t epi_keep_word(const EpiParams& e, uint32_t k0, uint32_t k1, uint32_t row, uint32_t cb) {
+  if (e.thresh == 0) return 0xFFFFFFFFu;
+  uint32_t x = epi_fmix32((row * 0x9E3779B1u) ^ k0);
+  x = epi_fmix32(x ^ (cb * 0x85EBCA77u) ^ k1);
+  uint32_t lt = 0u;
+#pragma unroll
+  for (int i = 0; i < kEpiDropBits; ++i) {
+    x = (x ^ (x >> 15)) * 0x2C1B3C6Du;
+    const uint32_t nw = ~x, tm = e.tmask[i];
+    lt = (nw & lt) | (tm & (nw | lt));
+  }
+  return ~lt;
+}
+
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32, int CLUSTER, int EPI>
+__global__ void __launch_bounds__(EPI != EPI_NONE ? kThreadsEpi : kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
-  using C = Cfg<BN, OUT_F32, CLUSTER>;
+            const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2, const GemmParams p) {
+  using C = Cfg<BN, OUT_F32, CLUSTER, EPI>;
   constexpr int STAGES = C::STAGES;
   constexpr bool PAIR = CLUSTER == 2;
 
@@ -125,6 +203,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmD);
+    if (EPI == EPI_GELU_FWD) tma_prefetch_desc(&tmD2);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
@@ -132,7 +211,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_tempty + 8 * s, 4 * CLUSTER);  // one arrival per epilogue warp (of both CTAs of a pair)
+      mbar_init(bar_tempty + 8 * s, (EPI != EPI_NONE ? 8 : 4) * CLUSTER);  // one arrival per epilogue warp (of both CTAs of a pair)
     }
     fence_mbar_init();
   }
@@ -259,7 +338,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
-  } else if (warp >= 6) {
+  } else if (EPI == EPI_NONE && warp >= 6) {
     // ===================== column sums of A (warps 6, 7; wgrad only) =====================
     // The n_tiles items that share a row block see the same A tiles: item n_blk sums the k-blocks with
     // kb % n_tiles == n_blk, so the extra shared-memory reads are spread over all items.
@@ -318,6 +397,145 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
+  } else if (EPI != EPI_NONE) {
+    // ===================== fused epilogue (warps 2..9 = 256 threads) =====================
+    // The activation costs ~13 (forward) / ~20 (backward) instructions per element, and a lone warp per scheduler
+    // issues a dependent stream at ~0.25 instructions per clock (measured: four epilogue warps needed 23 k cycles for
+    // a 128 x 256 tile against the 5.8 k of a K = 768 mainloop).  Eight warps: two per TMEM lane quadrant; warp group
+    // g = (warp - 2) / 4 takes the 64-column chunks of parity g, with a staging block (pair) and a bulk-store queue of
+    // its own, so one group's arithmetic overlaps the other's store.
+    const int ew = warp - 2;       // 0..7
+    const int grp = ew >> 2;       // chunk parity
+    const int quad = warp & 3;     // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;
+    const int etid = ew * 32 + lane;
+    const bool store_thread = (ew & 3) == 0 && lane == 0;
+    int as = 0;
+    uint32_t aph = 0;
+    uint32_t ek0 = p.epi.k0, ek1 = p.epi.k1;
+    if (p.epi.thresh != 0 && p.epi.epoch != nullptr) {
+      const unsigned long long e = *p.epi.epoch;
+      ek0 ^= epi_fmix32((uint32_t)e * 0x9E3779B1u + 0x68E31DA4u);
+      ek1 += epi_fmix32((uint32_t)(e >> 32) ^ 0xB5297A4Du) + (uint32_t)e;
+    }
+    constexpr int NCHUNK = BN / 64;
+    constexpr int UNITS = NCHUNK;  // 32-column units this group handles per tile: NCHUNK / 2 chunks x 2 halves
+    const uint32_t blk_z = sC + grp * (BM * 128) + row * 128;  // H (forward) / dZ (backward) staging block of this group
+    const uint32_t blk_h = blk_z + 2 * (BM * 128);             // G staging block (forward only)
+    for (int t = item0; t < total_tiles; t += item_stride) {
+      TileCoord tc = decode_tile(p, t);
+      if (CLUSTER > 1) tc.m_blk = tc.m_blk * CLUSTER + crank;
+      const int n0 = tc.n_blk * BN;
+      const int m_glob = tc.m_blk * BM + row;  // global output row of this thread
+      // EPI_MUL: this row's multipliers of the first 32-column unit, requested before the accumulator is waited for
+      uint4 zq[4];
+      const __nv_bfloat16* zrow = p.epi.z + (long long)m_glob * p.epi.ldz + n0;
+      auto load_z = [&](uint4 (&dst)[4], int unit) {  // unit u -> chunk grp + 2 (u / 2), half u & 1
+        const int col = (grp + 2 * (unit >> 1)) * 64 + (unit & 1) * 32;
+        const uint4* zp = reinterpret_cast<const uint4*>(zrow + col);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          dst[q] = (m_glob < p.M && n0 + col + 8 * q < p.N) ? __ldg(zp + q) : make_uint4(0, 0, 0, 0);
+      };
+      if (EPI == EPI_MUL) load_z(zq, 0);
+      mbar_wait(bar_tfull + 8 * as, aph);
+      tc_fence_after();
+      float* bs_t = bias_s + as * BN;  // per accumulator stage: the other group may still be reading the previous tile's
+      for (int i = etid; i < BN; i += 256) {
+        const int n = n0 + i;
+        bs_t[i] = (p.bias != nullptr && n < p.N) ? p.bias[n] : 0.f;
+      }
+      named_bar_sync(1, 256);
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int u = 0; u < UNITS; ++u) {
+        const int cb = grp + 2 * (u >> 1), hf = u & 1;
+        if (hf == 0) {
+          // this group's previous store must have finished READING the staging block(s)
+          if (store_thread) tma_wait_group_read0();
+          named_bar_sync(2 + grp, 128);
+        }
+        uint4 zn[4];
+        if (EPI == EPI_MUL && u + 1 < UNITS) load_z(zn, u + 1);  // in flight while this unit is in the ALUs
+        uint32_t r[32];
+        tmem_ld32(t_addr + cb * 64 + hf * 32, r);
+        tmem_ld_wait();
+        if (u == UNITS - 1) {  // this warp's last read of the accumulator stage: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(cluster_map(bar_tempty + 8 * as, 0));
+            else mbar_arrive(bar_tempty + 8 * as);
+          }
+        }
+        const uint32_t kw = EPI == EPI_GELU_FWD
+                                ? epi_keep_word(p.epi, ek0, ek1, (uint32_t)m_glob, (uint32_t)((n0 + cb * 64) >> 5) + hf)
+                                : 0u;
+        const float* bs = bs_t + cb * 64 + hf * 32;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t sw = ((((hf * 4 + q) ^ (row & 7)) & 7) << 4);
+          if (EPI == EPI_GELU_FWD) {
+            float hv[8], gv[8];
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+              const float2 v = __ffma2_rn(make_float2(__uint_as_float(r[8 * q + e]), __uint_as_float(r[8 * q + e + 1])),
+                                          make_float2(p.alpha, p.alpha), make_float2(bs[8 * q + e], bs[8 * q + e + 1]));
+              const float2 dm = make_float2((kw & (1u << (8 * q + e))) ? p.epi.inv_keep : 0.f,
+                                            (kw & (2u << (8 * q + e))) ? p.epi.inv_keep : 0.f);
+              float2 val, grad;
+              gelu_pair(v, val, grad);
+              const float2 h2 = __fmul2_rn(val, dm), g2 = __fmul2_rn(grad, dm);
+              hv[e] = h2.x;
+              hv[e + 1] = h2.y;
+              gv[e] = g2.x;
+              gv[e + 1] = g2.y;
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk_z + sw), "r"(pack_bf16(hv[0], hv[1])),
+                         "r"(pack_bf16(hv[2], hv[3])), "r"(pack_bf16(hv[4], hv[5])), "r"(pack_bf16(hv[6], hv[7]))
+                         : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk_h + sw), "r"(pack_bf16(gv[0], gv[1])),
+                         "r"(pack_bf16(gv[2], gv[3])), "r"(pack_bf16(gv[4], gv[5])), "r"(pack_bf16(gv[6], gv[7]))
+                         : "memory");
+          } else {
+            const uint4 zu = zq[q];
+            const uint32_t zw[4] = {zu.x, zu.y, zu.z, zu.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 gm = make_float2(__uint_as_float(zw[e] << 16), __uint_as_float(zw[e] & 0xffff0000u));
+              const float2 d = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(r[8 * q + 2 * e]),
+                                                                 __uint_as_float(r[8 * q + 2 * e + 1])),
+                                                     make_float2(p.alpha, p.alpha)), gm);
+              o[e] = pack_bf16(d.x, d.y);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk_z + sw), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+                         "r"(o[3])
+                         : "memory");
+          }
+        }
+        if (EPI == EPI_MUL && u + 1 < UNITS) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) zq[q] = zn[q];
+        }
+        if (hf == 1) {
+          fence_proxy_async_smem();
+          named_bar_sync(2 + grp, 128);
+          if (store_thread) {
+            if (n0 + cb * 64 < p.N) {
+              tma_store_2d(&tmD, sC + grp * (BM * 128), n0 + cb * 64, tc.m_blk * BM);
+              if (EPI == EPI_GELU_FWD) tma_store_2d(&tmD2, sC + (2 + grp) * (BM * 128), n0 + cb * 64, tc.m_blk * BM);
+            }
+            tma_commit_group();
+          }
+        }
+      }
+      if (++as == 2) {
+        as = 0;
+        aph ^= 1;
+      }
+    }
+    if (store_thread) tma_wait_group0();
   } else {
     // ===================== epilogue (warps 2..5 = 128 threads) =====================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
@@ -422,12 +640,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // -----------------------------------------------------------------------------------------------
 // host launcher
 // -----------------------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN, bool OUT_F32, int CLUSTER>
+struct EpiArgs {  // host-side description of a fused epilogue (EPI_NONE: all zero)
+  void* d2 = nullptr;       // EPI_GELU_FWD: second output H [M, ldd2]
+  int64_t ldd2 = 0;
+  const void* z = nullptr;  // EPI_MUL: elementwise multiplier G [M, ldz]
+  int64_t ldz = 0;
+  float p_drop = 0.f;
+  uint64_t seed = 0, offset = 0;
+  const uint64_t* epoch = nullptr;
+};
+
+void fill_epi(EpiParams& e, const EpiArgs& a) {
+  e.z = (const __nv_bfloat16*)a.z;
+  e.ldz = a.ldz;
+  uint64_t zz = a.seed * 0x9E3779B97F4A7C15ull + a.offset * 0xD1B54A32D192ED03ull + 0x2545F4914F6CDD1Dull;
+  zz = (zz ^ (zz >> 30)) * 0xBF58476D1CE4E5B9ull;
+  zz = (zz ^ (zz >> 27)) * 0x94D049BB133111EBull;
+  zz ^= zz >> 31;
+  e.k0 = (uint32_t)zz;
+  e.k1 = (uint32_t)(zz >> 32);
+  e.epoch = reinterpret_cast<const unsigned long long*>(a.epoch);
+  const double full = (double)(1u << kEpiDropBits);
+  double t = (double)a.p_drop * full + 0.5;
+  if (t < 1.0) t = 1.0;
+  e.thresh = a.p_drop > 0.f ? (uint32_t)(t > full - 1.0 ? full - 1.0 : t) : 0u;
+  for (int i = 0; i < kEpiDropBits; ++i) e.tmask[i] = ((e.thresh >> i) & 1u) ? 0xFFFFFFFFu : 0u;
+  e.inv_keep = a.p_drop > 0.f ? (float)(full / (full - (double)e.thresh)) : 1.0f;
+}
+
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32, int CLUSTER, int EPI = EPI_NONE>
 int launch_impl(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd,
                 const float* bias, float* colsum, float alpha, int64_t M, int64_t N, int64_t K, int k_splits_req,
-                cudaStream_t stream) {
-  using C = Cfg<BN, OUT_F32, CLUSTER>;
-  auto kern = gemm_kernel<BN, A_MN, B_MN, OUT_F32, CLUSTER>;
+                cudaStream_t stream, const EpiArgs& ea = EpiArgs()) {
+  using C = Cfg<BN, OUT_F32, CLUSTER, EPI>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, OUT_F32, CLUSTER, EPI>;
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), C::SMEM_BYTES)) return rc;
   CUtensorMap tmA, tmB, tmD;
   int rc;
@@ -446,8 +692,14 @@ int launch_impl(const void* A, int64_t lda, const void* B, int64_t ldb, void* D,
   else
     rc = make_tmap_2d(&tmD, D, 2, false, N, M, ldd * 2, 64, BM, SWZ_128);
   if (rc) return rc;
+  CUtensorMap tmD2 = tmD;
+  if (EPI == EPI_GELU_FWD) {
+    rc = make_tmap_2d(&tmD2, ea.d2, 2, false, N, M, ea.ldd2 * 2, 64, BM, SWZ_128);
+    if (rc) return rc;
+  }
 
   GemmParams p;
+  fill_epi(p.epi, ea);
   p.M = (int)M;
   p.N = (int)N;
   p.K = (int)K;
@@ -491,12 +743,12 @@ int launch_impl(const void* A, int64_t lda, const void* B, int64_t ldb, void* D,
   const int total = p.m_tiles * p.n_tiles * p.k_splits;
   if (CLUSTER == 1) {
     const int grid = total < sms ? total : sms;
-    kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, tmD, p);
+    kern<<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmD, tmD2, p);
   } else {
     const int clusters = total < sms ? total : sms;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(clusters * CLUSTER));
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(C::THREADS);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -506,7 +758,7 @@ int launch_impl(const void* A, int64_t lda, const void* B, int64_t ldb, void* D,
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SCT_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, p));
+    SCT_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, tmD2, p));
   }
   SCT_LAUNCH_CHECK();
   return 0;
@@ -525,6 +777,14 @@ int launch(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int6
   }
   return launch_impl<BN, A_MN, B_MN, OUT_F32, 1>(A, lda, B, ldb, D, ldd, bias, colsum, alpha, M, N, K, k_splits_req,
                                                  stream);
+}
+
+template <bool B_MN, int EPI>
+int launch_epi(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd, const float* bias,
+               float alpha, int64_t M, int64_t N, int64_t K, cudaStream_t stream, const EpiArgs& ea) {
+  if (env_int("SCT_GEMM_PAIR", 1) && M > BM)
+    return launch_impl<256, false, B_MN, false, 2, EPI>(A, lda, B, ldb, D, ldd, bias, nullptr, alpha, M, N, K, 1, stream, ea);
+  return launch_impl<256, false, B_MN, false, 1, EPI>(A, lda, B, ldb, D, ldd, bias, nullptr, alpha, M, N, K, 1, stream, ea);
 }
 
 int check_common(const void* A, const void* B, const void* D, int64_t M, int64_t N, int64_t K) {
@@ -571,6 +831,31 @@ int32_t sct_gemm_bf16_nn(const void* A, int64_t lda, const void* W, int64_t ldw,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (bn == 256) return sct::launch<256, false, true, false>(A, lda, W, ldw, D, ldd, bias, nullptr, alpha, M, N, K, 1, st);
   return sct::launch<128, false, true, false>(A, lda, W, ldw, D, ldd, bias, nullptr, alpha, M, N, K, 1, st);
+}
+
+int32_t sct_gemm_bf16_nt_gelu(const void* A, int64_t lda, const void* W, int64_t ldw, void* H, int64_t ldh, void* G,
+                              int64_t ldg, const float* bias, int64_t M, int64_t N, int64_t K, float p_drop,
+                              uint64_t seed, uint64_t offset, const uint64_t* epoch, void* stream) {
+  if (int rc = sct::check_common(A, W, H, M, N, K)) return rc;
+  SCT_CHECK(G != nullptr, "null G output");
+  SCT_CHECK(N % 64 == 0, "fused GELU epilogue needs N %% 64 == 0 (N = %lld)", (long long)N);
+  SCT_CHECK(p_drop >= 0.f && p_drop < 1.f, "p_drop out of range");
+  sct::EpiArgs ea;
+  ea.d2 = G; ea.ldd2 = ldg; ea.p_drop = p_drop; ea.seed = seed; ea.offset = offset; ea.epoch = epoch;
+  return sct::launch_epi<false, sct::EPI_GELU_FWD>(A, lda, W, ldw, H, ldh, bias, 1.0f, M, N, K,
+                                                   static_cast<cudaStream_t>(stream), ea);
+}
+
+int32_t sct_gemm_bf16_nn_mul(const void* A, int64_t lda, const void* W, int64_t ldw, const void* G, int64_t ldg,
+                             void* D, int64_t ldd, int64_t M, int64_t N, int64_t K, void* stream) {
+  if (int rc = sct::check_common(A, W, D, M, N, K)) return rc;
+  SCT_CHECK(G != nullptr, "null G input");
+  SCT_CHECK(N % 64 == 0 && ldg % 8 == 0, "fused multiply epilogue needs N %% 64 == 0 and ldg %% 8 == 0");
+  SCT_CHECK((reinterpret_cast<uintptr_t>(G) & 15) == 0, "G must be 16-byte aligned");
+  sct::EpiArgs ea;
+  ea.z = G; ea.ldz = ldg;
+  return sct::launch_epi<true, sct::EPI_MUL>(A, lda, W, ldw, D, ldd, nullptr, 1.0f, M, N, K,
+                                             static_cast<cudaStream_t>(stream), ea);
 }
 
 int32_t sct_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int64_t ldb, float* D, int64_t ldd,

@@ -248,6 +248,40 @@ def gemm_nn(a, w, alpha=1.0, out=None, bn=None):
     return out
 
 
+def gemm_nt_gelu(a, w, bias, p_drop=0.0, seed=0, offset=0, epoch=None):
+    """(h, g): with z = a[M,K] @ w[N,K]^T + bias, h = dropout(gelu(z)) and g = mask / (1 - p) * gelu'(z) (bf16) —
+    linear1 + activation + dropout of the feed-forward block in one kernel (fused GEMM epilogue); g is the local
+    derivative the backward multiplies with (gemm_nn_mul)."""
+    a, lda = _rows2d(a, BF16, "a")
+    w, ldw = _rows2d(w, BF16, "w")
+    M, K = a.shape
+    N, K2 = w.shape
+    assert K == K2 and N % 64 == 0
+    h = torch.empty((M, N), dtype=BF16, device=a.device)
+    g = torch.empty((M, N), dtype=BF16, device=a.device)
+    if bias is not None:
+        _chk(bias, F32, "bias")
+    _lib.Stats.annotate(2.0 * M * N * K)
+    _lib.call("sct_gemm_bf16_nt_gelu", _ptr(a), lda, _ptr(w), ldw, _ptr(h), N, _ptr(g), N, _ptr(bias), M, N, K,
+              float(p_drop), seed, offset, _eptr(epoch), _stream())
+    return h, g
+
+
+def gemm_nn_mul(dy, w, g):
+    """dz[M,N] (bf16) = (dy[M,K] @ w[K,N]) * g[M,N] — dgrad of linear2 + backward of the activation and its dropout in
+    one kernel (g from gemm_nt_gelu)."""
+    dy, lda = _rows2d(dy, BF16, "dy")
+    w, ldw = _rows2d(w, BF16, "w")
+    g, ldg = _rows2d(g, BF16, "g")
+    M, K = dy.shape
+    K2, N = w.shape
+    assert K == K2 and g.shape == (M, N) and N % 64 == 0
+    dz = torch.empty((M, N), dtype=BF16, device=dy.device)
+    _lib.Stats.annotate(2.0 * M * N * K)
+    _lib.call("sct_gemm_bf16_nn_mul", _ptr(dy), lda, _ptr(w), ldw, _ptr(g), ldg, _ptr(dz), N, M, N, K, _stream())
+    return dz
+
+
 def gemm_tn(a, b, out, alpha=1.0, k_splits=0, colsum=None):
     """out[M,N] (fp32) += alpha * a[K,M]^T @ b[K,N]; colsum[M] (fp32, optional) += alpha * a.sum(0)"""
     a, lda = _rows2d(a, BF16, "a")

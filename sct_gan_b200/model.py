@@ -236,6 +236,7 @@ class SmartContractTransformer(nn.Module):
         self.heads_side_stream = __import__("os").environ.get("SCT_HEADS_SIDE_STREAM", "1") != "0"
         self._step_counter = 0
         self.heads_autocast = True  # bf16 matmuls for the PyTorch vulnerability heads on the GPU
+        self.fused_ffn = __import__("os").environ.get("SCT_FUSED_FFN", "1") != "0"  # =0: separate gelu_dropout kernels (A/B)
 
     # ------------------------------------------------------------------------------------ init
     def _init_weights(self):
@@ -314,15 +315,18 @@ class SmartContractTransformer(nn.Module):
         return self._lin(o, att.out_proj)
 
     def _mha_cross(self, yq, ykv, att: nn.MultiheadAttention, B, Lq, Lk, kpm):
-        d = self.d_model
-        q = self._lin_rows(yq, att.in_proj_weight, att.in_proj_bias, 0, d)
-        kv = self._lin_rows(ykv, att.in_proj_weight, att.in_proj_bias, d, 3 * d)
+        q, kv = ops.cross_proj(yq, ykv, att.in_proj_weight, att.in_proj_bias, self._w(att.in_proj_weight))
         o = ops.cross_attention(q, kv, B, self.nhead, Lq, Lk, kpm, att.dropout if self.training else 0.0)
         return self._lin(o, att.out_proj)
 
     def _ffn(self, y, layer):
-        h = ops.gelu_dropout(self._lin(y, layer.linear1), self._p())
-        return self._lin(h, layer.linear2)
+        l1, l2 = layer.linear1, layer.linear2
+        if self.fused_ffn and y.shape[0] > 128 and l1.out_features % 64 == 0 and l1.out_features >= 512 \
+                and l1.bias is not None and l2.bias is not None:
+            # activation + dropout inside the GEMM epilogues (forward: linear1's; backward: linear2's dgrad)
+            return ops.fused_ffn(y, l1, l2, self._w(l1.weight), self._w(l2.weight), self._p())
+        h = ops.gelu_dropout(self._lin(y, l1), self._p())  # skinny rows (decode step) / odd widths
+        return self._lin(h, l2)
 
     def _encode(self, x, B, S, kpm):
         """nn.TransformerEncoder, norm_first (torch transformer.py:944-983): x fp32 [B*S, d] -> memory."""

@@ -142,6 +142,87 @@ class ShadowCache:
 
 
 # ------------------------------------------------------------------------------------------------
+class GradArena:
+    """Zero-initialised fp32 gradient buffers for one training step, carved from ONE arena that is cleared by ONE
+    memset at the start of the step.
+
+    Every parameter gradient of the step is an accumulator (split-K wgrad GEMMs reduce-add into it, the embedding
+    backward scatter-adds, LayerNorm gamma / beta gradients are atomics), so each used to be a `torch.zeros` of its
+    own: 300+ fill kernels per step.  The trainer brackets a step with `begin()` / `end()`; autograd backward
+    functions call `zeros()` and get a view of the arena (same addresses every step: the optimiser's pointer table
+    stays valid, eager or captured).  Outside a bracket — or while the arena is still being sized by the first
+    step — `zeros()` is plain `torch.zeros`.  A parameter used at several sites of one step (the shared
+    `embedding.weight`: contract and target passes) gets ONE buffer: `zeros_for(param)` returns it again and the
+    second backward accumulates into it instead of producing a second 154 MB tensor for autograd to add."""
+
+    ALIGN = 64  # elements (256 bytes)
+
+    def __init__(self):
+        self.buf = None
+        self.off = 0
+        self.need = 0       # elements requested so far in the running step
+        self.need_last = 0  # ... in the largest completed step: what begin() sizes the arena for
+        self.active = False
+        self.shared = {}
+        self._old = []      # outgrown arenas stay alive: captured graphs may still point into them
+
+    def reserve(self, device):
+        """Allocate (outside any graph capture) what the last completed step asked for."""
+        if self.need_last > 0 and (self.buf is None or self.buf.device != device or self.need_last > self.buf.numel()):
+            assert not (device.type == "cuda" and torch.cuda.is_current_stream_capturing()), \
+                "gradient arena must be sized by an eager step before CUDA-graph capture"
+            if self.buf is not None:
+                self._old.append(self.buf)
+            self.buf = torch.empty(self.need_last, dtype=F32, device=device)
+
+    def begin(self, device):
+        if not (device.type == "cuda" and torch.cuda.is_current_stream_capturing()):
+            self.reserve(device)
+        self.off, self.need, self.shared = 0, 0, {}
+        self.active = True
+        if self.buf is not None:
+            self.buf.zero_()
+
+    def end(self):
+        self.active = False
+        self.shared = {}
+        self.need_last = max(self.need_last, self.need)
+
+    def zeros(self, shape, device):
+        if not self.active:
+            return torch.zeros(shape, dtype=F32, device=device)
+        n = 1
+        for s in shape:
+            n *= int(s)
+        n_al = (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.need += n_al
+        if self.buf is None or self.buf.device != device or self.off + n_al > self.buf.numel():
+            return torch.zeros(shape, dtype=F32, device=device)  # sizing pass (first step) / outgrown
+        out = self.buf[self.off:self.off + n].view(shape)
+        self.off += n_al
+        return out
+
+    def zeros_for(self, param, shape, device):
+        """(buffer, first): the accumulator of `param` for this step; `first` is False when an earlier backward of
+        the same step already returned it to autograd (return None for the parameter then)."""
+        if not self.active:
+            return torch.zeros(shape, dtype=F32, device=device), True
+        key = param if isinstance(param, int) else param.data_ptr()  # saved_tensors hands out fresh wrappers: key by address
+        ent = self.shared.get(key)
+        if ent is not None:
+            return ent, False
+        buf = self.zeros(shape, device)
+        self.shared[key] = buf
+        return buf, True
+
+
+ARENA = GradArena()
+
+
+def grad_zeros(shape, device):
+    return ARENA.zeros(tuple(shape), device)
+
+
 class EmbedLnPe(torch.autograd.Function):
     """K1: LayerNorm(dropout(table[ids] * sqrt(d))) + pe[s]  (model.py:412-421, 944-947)."""
 
@@ -152,6 +233,7 @@ class EmbedLnPe(torch.autograd.Function):
         out_f32, out_bf16, stats = kn.embed_ln_pe_fwd(ids_flat, table.detach(), gamma.detach(), beta.detach(),
                                                       pe, seq_len, scale, p_drop, seed, off, ep, want_f32, want_bf16)
         ctx.save_for_backward(ids_flat, table, gamma, stats)
+        ctx.beta_key = beta.data_ptr()
         ctx.cfg = (scale, p_drop, seed, off, ep)
         ctx.set_materialize_grads(False)
         return out_f32, out_bf16
@@ -164,12 +246,15 @@ class EmbedLnPe(torch.autograd.Function):
             g = g_f32 + g_bf16.float()
         else:
             g = g_f32 if g_f32 is not None else g_bf16
-        dtable = torch.zeros_like(table)
-        dgamma = torch.zeros_like(gamma)
-        dbeta = torch.zeros_like(gamma)
+        # the table / gamma / beta accumulators are shared by every pass that uses this embedding in the step
+        dtable, first = ARENA.zeros_for(table, table.shape, table.device)
+        dgamma, _ = ARENA.zeros_for(gamma, gamma.shape, gamma.device)
+        dbeta, _ = ARENA.zeros_for(ctx.beta_key, gamma.shape, gamma.device)
         if g is not None:
             kn.embed_ln_pe_bwd(g.contiguous(), ids_flat, table.detach(), gamma.detach(), stats, dtable, dgamma,
                                dbeta, scale, p_drop, seed, off, ep)
+        if not first:  # already handed to autograd by the other pass: accumulated in place
+            return None, None, None, None, None, None, None, None, None, None
         return None, dtable, dgamma, dbeta, None, None, None, None, None, None
 
 
@@ -211,8 +296,8 @@ class ResidualLn(torch.autograd.Function):
             xprime, stats, gamma = ctx.saved_tensors
             if g_second is not None:
                 g_yln = g_second.contiguous()
-            dgamma = torch.zeros_like(gamma)
-            dbeta = torch.zeros_like(gamma)
+            dgamma = grad_zeros(gamma.shape, gamma.device)
+            dbeta = grad_zeros(gamma.shape, gamma.device)
         elif ctx.mode == "cast" and g_second is not None:
             g_ycast = g_second.contiguous()
         if g_xout is None and g_yln is None and g_ycast is None:
@@ -246,7 +331,7 @@ class LnAct(torch.autograd.Function):
     def backward(ctx, g_h):
         z, stats, gamma, beta = ctx.saved_tensors
         p, seed, off, ep = ctx.drop
-        dgamma, dbeta = torch.zeros_like(gamma), torch.zeros_like(beta)
+        dgamma, dbeta = grad_zeros(gamma.shape, gamma.device), grad_zeros(beta.shape, beta.device)
         g_z = kn.ln_act_bwd(g_h.contiguous(), z, stats, gamma.detach(), beta.detach(), dgamma, dbeta, p, seed, off, ep)
         return g_z, dgamma, dbeta, None
 
@@ -333,9 +418,9 @@ class Linear(torch.autograd.Function):
             dx = kn.gemm_nn(dy, w_bf16)
         want_db = ctx.has_bias and ctx.needs_input_grad[2]
         if want_db:
-            db = torch.zeros(ld, dtype=F32, device=dy.device)
+            db = grad_zeros((ld,), dy.device)
         if ctx.needs_input_grad[1]:
-            dw = torch.zeros(ctx.w_shape, dtype=F32, device=dy.device)
+            dw = grad_zeros(ctx.w_shape, dy.device)
             kn.gemm_tn(dy, x, dw, colsum=db)  # bias gradient summed from the dY tiles of the wgrad GEMM
         elif want_db:
             kn.colsum_bf16(full, db)
@@ -346,6 +431,73 @@ class Linear(torch.autograd.Function):
 
 def linear(x, w_f32, bias, w_bf16):
     return Linear.apply(x, w_f32, bias, w_bf16)
+
+
+class FusedFFN(torch.autograd.Function):
+    """The feed-forward block linear2(dropout(gelu(linear1(y)))) (torch transformer.py _ff_block, model.py:56-77) as
+    GEMM launches only: the activation and its dropout run in linear1's epilogue, which also leaves their local
+    derivative g = mask / (1 - p) * gelu'(z) for the backward; linear2's dgrad multiplies with it on the way out — no
+    separate pass over the [rows, ff] activations in either direction."""
+
+    @staticmethod
+    def forward(ctx, y, w1_f32, b1, w1_bf16, w2_f32, b2, w2_bf16, p_drop):
+        seed, off, ep = DropoutRng.draw() if p_drop > 0 else (0, 0, None)
+        h, g = kn.gemm_nt_gelu(y, w1_bf16, b1.detach(), p_drop, seed, off, ep)
+        out = kn.gemm_nt(h, w2_bf16, b2.detach())
+        ctx.save_for_backward(y, g, h, w1_bf16, w2_bf16)
+        ctx.shapes = (w1_f32.shape, w2_f32.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, g, h, w1_bf16, w2_bf16 = ctx.saved_tensors
+        s1, s2 = ctx.shapes
+        dout = dout.contiguous()
+        dev = dout.device
+        dz = kn.gemm_nn_mul(dout, w2_bf16, g)
+        dw2, db2 = grad_zeros(s2, dev), grad_zeros((s2[0],), dev)
+        kn.gemm_tn(dout, h, dw2, colsum=db2)
+        dy = kn.gemm_nn(dz, w1_bf16) if ctx.needs_input_grad[0] else None
+        dw1, db1 = grad_zeros(s1, dev), grad_zeros((s1[0],), dev)
+        kn.gemm_tn(dz, y, dw1, colsum=db1)
+        return dy, dw1, db1, None, dw2, db2, None, None
+
+
+def fused_ffn(y, lin1, lin2, w1_bf16, w2_bf16, p_drop=0.0):
+    return FusedFFN.apply(y, lin1.weight, lin1.bias, w1_bf16, lin2.weight, lin2.bias, w2_bf16, p_drop)
+
+
+class CrossProj(torch.autograd.Function):
+    """The packed in-projection of a cross-attention (torch `_in_projection_packed`, functional.py:5798): q from rows
+    [0, d) of in_proj_weight applied to the query stream, k|v from rows [d, 3d) applied to the memory / path stream.
+    One autograd node for both, so the weight gradient is ONE [3d, d] buffer the two wgrad GEMMs write their row
+    ranges of (autograd on `weight[r0:r1]` slices pads each slice gradient into a zero [3d, d] tensor and adds)."""
+
+    @staticmethod
+    def forward(ctx, xq, xkv, w_f32, bias, w_bf16):
+        d = w_bf16.shape[1]
+        b = bias.detach()
+        q = kn.gemm_nt(xq, w_bf16[:d], b[:d])
+        kv = kn.gemm_nt(xkv, w_bf16[d:], b[d:])
+        ctx.save_for_backward(xq, xkv, w_bf16)
+        return q, kv
+
+    @staticmethod
+    def backward(ctx, dq, dkv):
+        xq, xkv, w_bf16 = ctx.saved_tensors
+        d = w_bf16.shape[1]
+        dq, dkv = dq.contiguous(), dkv.contiguous()
+        dxq = kn.gemm_nn(dq, w_bf16[:d]) if ctx.needs_input_grad[0] else None
+        dxkv = kn.gemm_nn(dkv, w_bf16[d:]) if ctx.needs_input_grad[1] else None
+        dw = grad_zeros(w_bf16.shape, dq.device)
+        db = grad_zeros((3 * d,), dq.device)
+        kn.gemm_tn(dq, xq, dw[:d], colsum=db[:d])
+        kn.gemm_tn(dkv, xkv, dw[d:], colsum=db[d:])
+        return dxq, dxkv, dw, db, None
+
+
+def cross_proj(xq, xkv, w_f32, bias, w_bf16):
+    return CrossProj.apply(xq, xkv, w_f32, bias, w_bf16)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -445,8 +597,8 @@ class VocabCE(torch.autograd.Function):
         row_loss = torch.empty(rows, dtype=F32, device=dev)
         row_lse = torch.empty(rows, dtype=F32, device=dev)
         dh = torch.empty_like(h) if need_grad else None
-        dw = torch.zeros((V, d), dtype=F32, device=dev) if need_grad else None
-        db = torch.zeros((V,), dtype=F32, device=dev) if (need_grad and bias is not None) else None
+        dw = grad_zeros((V, d), dev) if need_grad else None
+        db = grad_zeros((V,), dev) if (need_grad and bias is not None) else None
         inv = 1.0 / float(n_valid)
         b_ = bias.detach() if bias is not None else None
         for r0 in range(0, rows, chunk_rows):
@@ -471,7 +623,12 @@ class VocabCE(torch.autograd.Function):
     def backward(ctx, g_loss, _g_lse):
         dh, dw, db = ctx.saved_tensors
         g = g_loss.to(F32)
-        return (dh.float() * g).to(BF16), dw * g, (db * g) if ctx.has_bias else None, None, None, None, None
+        # in place: these tensors were produced by this op's forward for exactly this use
+        dh.mul_(g.to(BF16))
+        dw.mul_(g)
+        if ctx.has_bias:
+            db.mul_(g)
+        return dh, dw, db if ctx.has_bias else None, None, None, None, None
 
 
 def _vocab_chunk_rows(rows, d, V, device):

@@ -469,6 +469,7 @@ class SmartContractTrainer:
             self._fused_tail.shadows = model._shadow  # bf16 weight copies are refreshed by the optimiser kernel
         self._graphs = {}
         self.last = {}
+        self.use_grad_arena = on_gpu and __import__("os").environ.get("SCT_GRAD_ARENA", "1") != "0"  # =0: A/B timing
 
     # ------------------------------------------------------------------------------------------
     def _refresh_scalars(self):
@@ -546,6 +547,14 @@ class SmartContractTrainer:
             self._reducer.finish()  # buckets were launched from the gradient hooks while backward was running
 
     def _step_body(self, batch, syntax_penalty, n_lines):
+        if self.use_grad_arena:
+            ops.ARENA.begin(self._found_inf.device)  # one memset: every gradient accumulator of the step
+        try:
+            return self._step_body_inner(batch, syntax_penalty, n_lines)
+        finally:
+            ops.ARENA.end()
+
+    def _step_body_inner(self, batch, syntax_penalty, n_lines):
         model = self.model
         target_ids = batch["target_ids"] if self.use_augmentation else batch["input_ids"]
         out = model(input_ids=batch["input_ids"], attention_mask=batch["attention_mask"],
@@ -624,6 +633,8 @@ class SmartContractTrainer:
             if self._fused_tail is not None:
                 self._fused_tail.prepare_for_capture()
             self._refresh_scalars()
+            if self.use_grad_arena:
+                ops.ARENA.reserve(dev)  # sized by the eager warm-up step, allocated outside the capture
             torch.cuda.synchronize()
             n0 = _lib.Stats.launches
             with torch.cuda.graph(graph):

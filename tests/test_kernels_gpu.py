@@ -502,3 +502,79 @@ def test_attention_dropout_mask_fwd_bwd_identical(cuda_dev, causal):
     assert rel_l2(dv, unheads(vf.grad)) < 1.5e-2
     assert rel_l2(dk, unheads(kf.grad)) < 1.5e-2
     assert rel_l2(dq, unheads(qf.grad)) < 1.5e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# fused GEMM epilogues of the feed-forward block
+@pytest.mark.parametrize("M,N,K", [(1024, 2048, 768), (300, 512, 768), (4096 + 77, 2048, 768)])
+@pytest.mark.parametrize("p_drop", [0.0, 0.3])
+def test_gemm_fused_gelu_epilogues(cuda_dev, M, N, K, p_drop):
+    """sct_gemm_bf16_nt_gelu / sct_gemm_bf16_nn_mul against the unfused fp32 PyTorch chain linear -> F.gelu (exact
+    erf, as the reference's activation='gelu') -> dropout and its backward.  The dropout mask cannot be matched to
+    ATen's Philox stream: it is read off the kernel's own output (h == 0 where gelu(z) != 0), checked statistically,
+    for independence across rows and for h / g consistency.  Tolerance: bf16 outputs, tanh-fit GELU (2.7e-4 abs)."""
+    from sct_gan_b200 import kernels as kn
+
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    x = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w1 = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    b1 = torch.randn(N, device="cuda", generator=g) * 0.1
+    h, gd = kn.gemm_nt_gelu(x, w1, b1, p_drop, seed=7, offset=3)
+    zf = (x.float() @ w1.float().t() + b1).requires_grad_(True)
+    act = torch.nn.functional.gelu(zf)  # exact erf form
+    act.sum().backward()
+    g_ref, d_ref = act.detach(), zf.grad
+    keep = 1.0 - (77.0 / 256.0 if p_drop > 0 else 0.0)  # p is resolved to 2^-8; the scale uses the realised value
+    live = g_ref.abs() > 2e-2
+    if p_drop == 0.0:
+        mask = torch.ones_like(g_ref, dtype=torch.bool)
+    else:
+        mask = h.float().abs() > 0
+        frac = mask[live].float().mean().item()
+        assert abs(frac - keep) < 5e-3, frac
+        per_row = (mask & live).float().sum(dim=1) / live.float().sum(dim=1).clamp(min=1)
+        assert per_row.min().item() > keep - 0.2 and per_row.max().item() < keep + 0.2  # rows draw independently
+        h2, _ = kn.gemm_nt_gelu(x, w1, b1, p_drop, seed=7, offset=3)
+        assert torch.equal(h, h2)
+        h3, _ = kn.gemm_nt_gelu(x, w1, b1, p_drop, seed=7, offset=4)
+        assert not torch.equal(h, h3)
+        # h and g carry the same mask
+        assert torch.equal(mask & live & (d_ref.abs() > 2e-2), (gd.float().abs() > 0) & live & (d_ref.abs() > 2e-2))
+    mf = mask.float() / keep
+    assert rel_l2(h.float() * live, g_ref * mf * live) < 1e-2
+    assert (h.float() - g_ref * mf)[mask].abs().max().item() < 2e-2 * max(1.0, g_ref.abs().max().item() / keep)
+    assert rel_l2(gd.float() * mask, d_ref * mf) < 1e-2
+    assert (gd.float() - d_ref * mf)[mask].abs().max().item() < 2e-2 / keep
+    # backward GEMM: dz = (dy @ w2) * g
+    w2 = (torch.randn(K, N, device="cuda", generator=g) * 0.05).bfloat16()  # linear2.weight [K_out = K, N]
+    dy = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    dz = kn.gemm_nn_mul(dy, w2, gd)
+    dz_ref = (dy.float() @ w2.float()) * gd.float()
+    assert rel_l2(dz, dz_ref) < 1e-2
+    _no_timeouts()
+
+
+def test_fused_ffn_autograd_matches_unfused(cuda_dev):
+    """ops.fused_ffn (4 GEMMs, fused epilogues) against the unfused kernels path at p = 0: outputs and all gradients."""
+    import torch.nn as nn
+
+    from sct_gan_b200 import ops
+
+    torch.manual_seed(0)
+    l1, l2 = nn.Linear(768, 2048).cuda(), nn.Linear(2048, 768).cuda()
+    y = (torch.randn(1000, 768, device="cuda") * 0.7).bfloat16()
+    w1b, w2b = l1.weight.detach().bfloat16(), l2.weight.detach().bfloat16()
+    outs = []
+    for fused in (True, False):
+        for p in (*l1.parameters(), *l2.parameters()):
+            p.grad = None
+        yy = y.clone().requires_grad_(True)
+        if fused:
+            o = ops.fused_ffn(yy, l1, l2, w1b, w2b, 0.0)
+        else:
+            o = ops.linear(ops.gelu_dropout(ops.linear(yy, l1.weight, l1.bias, w1b), 0.0), l2.weight, l2.bias, w2b)
+        (o.float() * torch.linspace(-1, 1, 768, device="cuda")).sum().backward()
+        outs.append([o.float(), yy.grad.float(), l1.weight.grad.clone(), l1.bias.grad.clone(), l2.weight.grad.clone(),
+                     l2.bias.grad.clone()])
+    for a, b in zip(*outs):
+        assert ((a - b).norm() / b.norm()).item() < 1e-2
