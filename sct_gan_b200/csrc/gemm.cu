@@ -61,6 +61,8 @@ struct EpiParams {
   uint32_t tmask[kEpiDropBits];     // bit i of the threshold spread over a word
   uint32_t thresh;         // 0 = no dropout
   float inv_keep;
+  int debug;               // SCT_EPI_DBG (timing experiments only): 1 = skip the G store, 2 = skip the activation math,
+                           // 4 = skip the G loads
 };
 
 struct GemmParams {
@@ -82,8 +84,9 @@ struct Cfg {
   // Epilogue staging: two [128 rows x 128 B] blocks (64 bf16 / 32 fp32 columns each), ping-ponged chunk by chunk.
   // A full-tile staging buffer (64 KB at BN = 256) would leave only 3 pipeline stages, and the mainloop is
   // bound by the bytes it can keep in flight (measured: the MMA thread waited on `full` 44 % of the time).
-  // EPI_GELU_FWD stores two tensors per chunk (z and h): two ping-pong pairs.
-  static constexpr int C_BLOCKS = EPI == EPI_GELU_FWD ? 4 : 2;
+  // Fused epilogues use four blocks: EPI_GELU_FWD stores two tensors per chunk (H and G) for each of its two warp
+  // groups; EPI_MUL receives the multiplier chunk by TMA in the block it later stores the product from.
+  static constexpr int C_BLOCKS = EPI != EPI_NONE ? 4 : 2;
   static constexpr int C_BYTES = C_BLOCKS * BM * 128;
   static constexpr int AUX_BYTES = 1024;  // barriers + tmem ptr
   static constexpr int BIAS_BYTES = (EPI != EPI_NONE ? 2 : 1) * BN * 4;  // fused epilogues: one copy per accumulator stage
@@ -187,6 +190,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t bar_tempty = bar_tfull + 16;
   const uint32_t tmem_ptr_addr = bar_tempty + 16;
   const uint32_t bar_done = sAux + 512;  // [STAGES] colsum mode: the MMAs reading this stage have retired
+  const uint32_t bar_g = sAux + 640;     // [4] EPI_MUL: the multiplier chunk has landed in staging block i
   volatile uint32_t* tmem_ptr_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_addr - smem_base));
   float* bias_s = reinterpret_cast<float*>(smem_gen + (sAux + C::AUX_BYTES - smem_base));
@@ -203,12 +207,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmD);
-    if (EPI == EPI_GELU_FWD) tma_prefetch_desc(&tmD2);
+    if (EPI != EPI_NONE) tma_prefetch_desc(&tmD2);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
       mbar_init(bar_done + 8 * s, 1);
     }
+    for (int s = 0; s < 4; ++s) mbar_init(bar_g + 8 * s, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
       mbar_init(bar_tempty + 8 * s, (EPI != EPI_NONE ? 8 : 4) * CLUSTER);  // one arrival per epilogue warp (of both CTAs of a pair)
@@ -411,7 +416,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int etid = ew * 32 + lane;
     const bool store_thread = (ew & 3) == 0 && lane == 0;
     int as = 0;
-    uint32_t aph = 0;
+    uint32_t aph = 0, gph = 0;
     uint32_t ek0 = p.epi.k0, ek1 = p.epi.k1;
     if (p.epi.thresh != 0 && p.epi.epoch != nullptr) {
       const unsigned long long e = *p.epi.epoch;
@@ -427,17 +432,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (CLUSTER > 1) tc.m_blk = tc.m_blk * CLUSTER + crank;
       const int n0 = tc.n_blk * BN;
       const int m_glob = tc.m_blk * BM + row;  // global output row of this thread
-      // EPI_MUL: this row's multipliers of the first 32-column unit, requested before the accumulator is waited for
-      uint4 zq[4];
-      const __nv_bfloat16* zrow = p.epi.z + (long long)m_glob * p.epi.ldz + n0;
-      auto load_z = [&](uint4 (&dst)[4], int unit) {  // unit u -> chunk grp + 2 (u / 2), half u & 1
-        const int col = (grp + 2 * (unit >> 1)) * 64 + (unit & 1) * 32;
-        const uint4* zp = reinterpret_cast<const uint4*>(zrow + col);
+      // EPI_MUL: the multiplier tile G[128 rows x 256 cols] arrives by TMA, one [128 x 64] chunk per staging block
+      // (this group's two chunks -> blocks grp and 2 + grp), requested before the accumulator is waited for.  (Per-
+      // thread global loads of a row segment are 32-way divergent: 4096 LSU cycles per tile, measured +38 us per
+      // launch; the bulk copy costs nothing but its bytes.)  The product is written back in place and stored.
+      if (EPI == EPI_MUL && store_thread) {
+        tma_wait_group_read0();  // the previous tile's stores have finished reading both blocks
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          dst[q] = (m_glob < p.M && n0 + col + 8 * q < p.N) ? __ldg(zp + q) : make_uint4(0, 0, 0, 0);
-      };
-      if (EPI == EPI_MUL) load_z(zq, 0);
+        for (int k = 0; k < 2; ++k) {
+          const int cbk = grp + 2 * k;
+          if (n0 + cbk * 64 < p.N && !(p.epi.debug & 4)) {
+            mbar_expect_tx(bar_g + 8 * cbk, BM * 128);
+            tma_load_2d(&tmD2, bar_g + 8 * cbk, sC + cbk * (BM * 128), n0 + cbk * 64, tc.m_blk * BM);
+          } else {
+            mbar_arrive(bar_g + 8 * cbk);
+          }
+        }
+      }
       mbar_wait(bar_tfull + 8 * as, aph);
       tc_fence_after();
       float* bs_t = bias_s + as * BN;  // per accumulator stage: the other group may still be reading the previous tile's
@@ -447,16 +458,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       named_bar_sync(1, 256);
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
-#pragma unroll 1
+#pragma unroll
       for (int u = 0; u < UNITS; ++u) {
         const int cb = grp + 2 * (u >> 1), hf = u & 1;
+        const uint32_t blk_u = EPI == EPI_MUL ? sC + cb * (BM * 128) + row * 128 : blk_z;
         if (hf == 0) {
-          // this group's previous store must have finished READING the staging block(s)
-          if (store_thread) tma_wait_group_read0();
-          named_bar_sync(2 + grp, 128);
+          if (EPI == EPI_MUL) {
+            mbar_wait(bar_g + 8 * cb, gph);  // multiplier chunk landed (each thread touches only its own row of it)
+          } else {
+            // this group's previous store must have finished READING the staging block(s)
+            if (store_thread) tma_wait_group_read0();
+            named_bar_sync(2 + grp, 128);
+          }
         }
-        uint4 zn[4];
-        if (EPI == EPI_MUL && u + 1 < UNITS) load_z(zn, u + 1);  // in flight while this unit is in the ALUs
         uint32_t r[32];
         tmem_ld32(t_addr + cb * 64 + hf * 32, r);
         tmem_ld_wait();
@@ -483,8 +497,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                           make_float2(p.alpha, p.alpha), make_float2(bs[8 * q + e], bs[8 * q + e + 1]));
               const float2 dm = make_float2((kw & (1u << (8 * q + e))) ? p.epi.inv_keep : 0.f,
                                             (kw & (2u << (8 * q + e))) ? p.epi.inv_keep : 0.f);
-              float2 val, grad;
-              gelu_pair(v, val, grad);
+              float2 val = v, grad = v;
+              if (!(p.epi.debug & 2)) gelu_pair(v, val, grad);
               const float2 h2 = __fmul2_rn(val, dm), g2 = __fmul2_rn(grad, dm);
               hv[e] = h2.x;
               hv[e + 1] = h2.y;
@@ -498,8 +512,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                          "r"(pack_bf16(gv[2], gv[3])), "r"(pack_bf16(gv[4], gv[5])), "r"(pack_bf16(gv[6], gv[7]))
                          : "memory");
           } else {
-            const uint4 zu = zq[q];
-            const uint32_t zw[4] = {zu.x, zu.y, zu.z, zu.w};
+            uint32_t zw[4];
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(zw[0]), "=r"(zw[1]), "=r"(zw[2]), "=r"(zw[3])
+                         : "r"(blk_u + sw));
             uint32_t o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -509,27 +525,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                                      make_float2(p.alpha, p.alpha)), gm);
               o[e] = pack_bf16(d.x, d.y);
             }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk_z + sw), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk_u + sw), "r"(o[0]), "r"(o[1]), "r"(o[2]),
                          "r"(o[3])
                          : "memory");
           }
-        }
-        if (EPI == EPI_MUL && u + 1 < UNITS) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) zq[q] = zn[q];
         }
         if (hf == 1) {
           fence_proxy_async_smem();
           named_bar_sync(2 + grp, 128);
           if (store_thread) {
             if (n0 + cb * 64 < p.N) {
-              tma_store_2d(&tmD, sC + grp * (BM * 128), n0 + cb * 64, tc.m_blk * BM);
-              if (EPI == EPI_GELU_FWD) tma_store_2d(&tmD2, sC + (2 + grp) * (BM * 128), n0 + cb * 64, tc.m_blk * BM);
+              tma_store_2d(&tmD, sC + (EPI == EPI_MUL ? cb : grp) * (BM * 128), n0 + cb * 64, tc.m_blk * BM);
+              if (EPI == EPI_GELU_FWD && !(p.epi.debug & 1))
+                tma_store_2d(&tmD2, sC + (2 + grp) * (BM * 128), n0 + cb * 64, tc.m_blk * BM);
             }
             tma_commit_group();
           }
         }
       }
+      gph ^= 1;
       if (++as == 2) {
         as = 0;
         aph ^= 1;
@@ -666,6 +680,7 @@ void fill_epi(EpiParams& e, const EpiArgs& a) {
   e.thresh = a.p_drop > 0.f ? (uint32_t)(t > full - 1.0 ? full - 1.0 : t) : 0u;
   for (int i = 0; i < kEpiDropBits; ++i) e.tmask[i] = ((e.thresh >> i) & 1u) ? 0xFFFFFFFFu : 0u;
   e.inv_keep = a.p_drop > 0.f ? (float)(full / (full - (double)e.thresh)) : 1.0f;
+  e.debug = env_int("SCT_EPI_DBG", 0);
 }
 
 template <int BN, bool A_MN, bool B_MN, bool OUT_F32, int CLUSTER, int EPI = EPI_NONE>
@@ -695,6 +710,9 @@ int launch_impl(const void* A, int64_t lda, const void* B, int64_t ldb, void* D,
   CUtensorMap tmD2 = tmD;
   if (EPI == EPI_GELU_FWD) {
     rc = make_tmap_2d(&tmD2, ea.d2, 2, false, N, M, ea.ldd2 * 2, 64, BM, SWZ_128);
+    if (rc) return rc;
+  } else if (EPI == EPI_MUL) {  // the multiplier G is read through the same [128 x 64] boxes the product leaves by
+    rc = make_tmap_2d(&tmD2, ea.z, 2, false, N, M, ea.ldz * 2, 64, BM, SWZ_128);
     if (rc) return rc;
   }
 

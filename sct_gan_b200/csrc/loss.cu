@@ -126,6 +126,128 @@ ce_rows_kernel(__nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ t
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row-resident variant (the training path: gradient requested and the row fits in shared memory).  The row is pulled
+// into shared memory ONCE by a 1-D bulk copy (100 KB at V = 50265; two rows resident per SM, so one block's copy
+// overlaps the other block's arithmetic) and all three sweeps read it from there: HBM sees one read and one write of
+// the chunk instead of two reads and one write.  One exp2 per logit: sweep 1 = row maximum, sweep 2 = e_i =
+// exp2(x_i - max) summed in fp32 and parked back in shared memory as bf16, sweep 3 = (e_i / sum - onehot) * grad_scale
+// written to global memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int kCeThreads = 256;
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();  // `red` may still be read from the previous reduction
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int w = 1; w < kCeThreads / 32; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+  return r;
+}
+
+__global__ void __launch_bounds__(kCeThreads, 2)
+ce_rows_resident_kernel(__nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ targets,
+                        float* __restrict__ row_loss, float* __restrict__ row_lse, int V, long long ld,
+                        float grad_scale) {
+  extern __shared__ __align__(16) uint8_t ce_smem[];
+  __shared__ float red[kCeThreads / 32];
+  __shared__ __align__(8) unsigned long long bar_storage;
+  const int row = blockIdx.x;
+  const int tid = threadIdx.x;
+  __nv_bfloat16* x = logits + (long long)row * ld;
+  const long long tgt = targets[row];
+  const int V8 = V & ~7, nvec = V8 >> 3;
+  if (tgt < 0) {  // excluded row (last position of each sequence): zero loss, zero gradient
+    if (tid == 0) {
+      row_loss[row] = 0.f;
+      if (row_lse) row_lse[row] = 0.f;
+    }
+    for (int c = tid; c < nvec; c += kCeThreads) reinterpret_cast<uint4*>(x)[c] = make_uint4(0, 0, 0, 0);
+    for (int c = V8 + tid; c < V; c += kCeThreads) x[c] = __float2bfloat16(0.f);
+    return;
+  }
+  if (tgt >= V) __trap();  // out-of-range class index: F.cross_entropy device-asserts here as well
+  const uint32_t bar = smem_u32(&bar_storage);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    if (nvec > 0) {
+      mbar_expect_tx(bar, (uint32_t)V8 * 2u);
+      bulk_load_1d(smem_u32(ce_smem), x, (uint32_t)V8 * 2u, bar);
+    } else {
+      mbar_arrive(bar);
+    }
+  }
+  // the (V % 8) tail elements and the target logit come straight from global memory, before anything is overwritten
+  const int tcol = V8 + tid;
+  const float tail = tcol < V ? __bfloat162float(x[tcol]) : -INFINITY;
+  const float x_tgt = __bfloat162float(x[tgt]);
+  __syncthreads();  // barrier initialised before anybody waits on it
+  mbar_wait(bar, 0);
+  uint4* sv = reinterpret_cast<uint4*>(ce_smem);
+  // sweep 1: raw maximum (bf16 -> fp32 is a shift; log2e > 0 keeps the order)
+  float m = tail;
+  for (int c = tid; c < nvec; c += kCeThreads) {
+    const uint4 u = sv[c];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m = fmaxf(m, fmaxf(__uint_as_float(w[k] << 16), __uint_as_float(w[k] & 0xffff0000u)));
+  }
+  const float m2 = block_reduce(m, red, true) * kLog2e;  // row maximum in the log2 domain
+  // sweep 2: e_i = exp2(x_i log2e - m2); fp32 sum; bf16(e_i) back into the row buffer
+  const float2 sc2 = make_float2(kLog2e, kLog2e), nm2 = make_float2(-m2, -m2);
+  float2 s2 = make_float2(0.f, 0.f);
+  for (int c = tid; c < nvec; c += kCeThreads) {
+    const uint4 u = sv[c];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 a = __ffma2_rn(make_float2(__uint_as_float(w[k] << 16), __uint_as_float(w[k] & 0xffff0000u)), sc2, nm2);
+      const float2 e = make_float2(exp2f(a.x), exp2f(a.y));
+      s2 = __fadd2_rn(s2, e);
+      o[k] = pack_bf16(e.x, e.y);
+    }
+    sv[c] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  const float e_tail = tcol < V ? exp2f(fmaf(tail, kLog2e, -m2)) : 0.f;
+  const float S = block_reduce(s2.x + s2.y + e_tail, red, false);
+  if (tid == 0) {
+    const float lse2 = m2 + log2f(S);
+    row_loss[row] = lse2 * kLn2 - x_tgt;
+    if (row_lse) row_lse[row] = lse2 * kLn2;
+  }
+  // sweep 3: d loss / d logit = (softmax - onehot) * grad_scale, written over the chunk in global memory
+  const float k = grad_scale / S;
+  const float2 k2 = make_float2(k, k);
+  const int tvec = (int)(tgt >> 3), tsub = (int)(tgt & 7);
+  uint4* gx = reinterpret_cast<uint4*>(x);
+  for (int c = tid; c < nvec; c += kCeThreads) {  // (each thread re-reads exactly the vectors it wrote in sweep 2)
+    const uint4 u = sv[c];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    float g[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 v = __fmul2_rn(make_float2(__uint_as_float(w[q] << 16), __uint_as_float(w[q] & 0xffff0000u)), k2);
+      g[2 * q] = v.x;
+      g[2 * q + 1] = v.y;
+    }
+    if (c == tvec) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q == tsub) g[q] -= grad_scale;
+    }
+    gx[c] = make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]), pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7]));
+  }
+  if (tcol < V) {
+    float gt = e_tail * k;
+    if (tcol == tgt) gt -= grad_scale;
+    x[tcol] = __float2bfloat16(gt);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // small linear (fp32 math): y[m, n] = sum_k x[m, k] * w[n, k] + b[n],  K = NV * 128
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 ld_row4(const float* xf, const __nv_bfloat16* xb, long long off) {
@@ -319,8 +441,15 @@ int32_t sct_ce_rows(void* logits, const int64_t* targets, float* row_loss, float
   SCT_CHECK(logits && targets && row_loss, "null pointer");
   SCT_CHECK(ld % 8 == 0 && ld >= V, "logits pitch must be a multiple of 8 and >= V");
   SCT_CHECK(rows > 0 && V > 0, "empty input");
-  ce_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(
-      (__nv_bfloat16*)logits, targets, row_loss, row_lse, (int)V, ld, grad_scale, write_grad);
+  const size_t row_bytes = (size_t)(V & ~7) * 2 + 16;
+  if (write_grad && row_bytes <= 110 * 1024 && env_int("SCT_CE_RESIDENT", 1)) {  // two rows resident per SM
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(ce_rows_resident_kernel), (int)row_bytes)) return rc;
+    ce_rows_resident_kernel<<<(unsigned)rows, kCeThreads, row_bytes, (cudaStream_t)stream>>>(
+        (__nv_bfloat16*)logits, targets, row_loss, row_lse, (int)V, ld, grad_scale);
+  } else {
+    ce_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(
+        (__nv_bfloat16*)logits, targets, row_loss, row_lse, (int)V, ld, grad_scale, write_grad);
+  }
   SCT_LAUNCH_CHECK();
   return 0;
 }
