@@ -804,26 +804,32 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // is in the ALUs.  Per score: P = exp2(s * c - lse), m = keep ? 1 / (1 - p) : 0, P~ = P * m, dS = P * (dP * m - D) as
 // packed fp32 pairs (FFMA2 / FMUL2: ~5 instructions per score instead of ~13 scalar ones; the statistics arrive
 // NEGATED in shared memory so they are plain FFMA2 addends).
-template <bool DIAG, bool ROWMASK>
+// NSUB = 1: one thread per key row does all four chunks (8 arithmetic warps); NSUB = 2: two threads per key row, in
+// warps of the same TMEM lane quadrant, take two chunks each (`sub` = 0 / 1; 16 arithmetic warps: four per scheduler
+// instead of two, half the live registers per thread; kw0 is then the keep word of this thread's 32 queries).
+template <bool DIAG, bool ROWMASK, int NSUB>
 __device__ __forceinline__ void dkdv_half_tile(uint32_t tST, uint32_t tDPT, uint32_t tPT, uint32_t lane_sel,
                                                uint32_t sDSTh, const float* __restrict__ nlse,
                                                const float* __restrict__ ndv, uint32_t kw0, uint32_t kw1, int r, int hh,
-                                               bool row_valid, float scale_log2, float inv_keep) {
+                                               bool row_valid, float scale_log2, float inv_keep, int sub) {
+  constexpr int NCH = 4 / NSUB;  // chunks per thread
+  const int cc0 = NSUB == 1 ? 0 : 2 * sub;
   uint32_t rs[2][16], rp[2][16];
-  tmem_ld16(tST + lane_sel, rs[0]);
-  tmem_ld16(tDPT + lane_sel, rp[0]);
+  tmem_ld16(tST + lane_sel + cc0 * 16, rs[0]);
+  tmem_ld16(tDPT + lane_sel + cc0 * 16, rp[0]);
   const float2 sc2 = make_float2(scale_log2, scale_log2);
 #pragma unroll
-  for (int cc = 0; cc < 4; ++cc) {
+  for (int ci = 0; ci < NCH; ++ci) {
+    const int cc = cc0 + ci;
     const int c0 = cc * 16;
-    const uint32_t kw = (cc < 2 ? kw0 : kw1) >> ((cc & 1) * 16);
+    const uint32_t kw = NSUB == 1 ? ((cc < 2 ? kw0 : kw1) >> ((cc & 1) * 16)) : (kw0 >> (ci * 16));
     tmem_ld_wait();
-    if (cc + 1 < 4) {
-      tmem_ld16(tST + lane_sel + c0 + 16, rs[(cc + 1) & 1]);
-      tmem_ld16(tDPT + lane_sel + c0 + 16, rp[(cc + 1) & 1]);
+    if (ci + 1 < NCH) {
+      tmem_ld16(tST + lane_sel + c0 + 16, rs[(ci + 1) & 1]);
+      tmem_ld16(tDPT + lane_sel + c0 + 16, rp[(ci + 1) & 1]);
     }
-    const uint32_t (&s_)[16] = rs[cc & 1];
-    const uint32_t (&p_)[16] = rp[cc & 1];
+    const uint32_t (&s_)[16] = rs[ci & 1];
+    const uint32_t (&p_)[16] = rp[ci & 1];
     float pd[16], ds[16];
 #pragma unroll
     for (int i = 0; i < 16; i += 2) {
@@ -867,8 +873,10 @@ constexpr int BWD3_KV_SMEM = 1024 + 2 * QKV_BYTES + 4 * QKV_BYTES + 4 * HALF_BYT
 // 10 = dV / dK MMA issuer.  TWO issuing threads on different schedulers: a single thread needs >= 54 clk per
 // tcgen05.mma (tools/micro/mma_issue.cu) and ~70-90 clk when it shares its scheduler with busy arithmetic warps, which
 // made the one issuer of 40 small MMAs per query tile the critical path (measured with clock64 traces).
-constexpr int BWD_KV_THREADS = 352;
-__global__ void __launch_bounds__(BWD_KV_THREADS, 1)
+// AW = 16 (two threads per key row): 19 warps, <= 104 registers per thread.
+constexpr int bwd_kv_threads(int aw) { return (aw + 3) * 32; }
+template <int AW>
+__global__ void __launch_bounds__(bwd_kv_threads(AW), 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                       const __grid_constant__ CUtensorMap tmDS, const __grid_constant__ CUtensorMap tmDK,
@@ -905,19 +913,20 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_init(bar_qe + 8 * i, 2);  // both MMA issuers release a Q / dO stage
       mbar_init(bar_stf + 8 * i, 1);
       mbar_init(bar_sf + 8 * i, 1);
-      mbar_init(bar_pf + 8 * i, 4);
+      mbar_init(bar_pf + 8 * i, AW / 2);  // one arrival per arithmetic warp of the half
       mbar_init(bar_gd + 8 * i, 1);
     }
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc(tmem_ptr_addr, 512);
+  constexpr int W_S = AW, W_TMA = AW + 1, W_G = AW + 2;  // S^T / dP^T issuer, TMA producer, dV / dK issuer
+  if (warp == W_S) tmem_alloc(tmem_ptr_addr, 512);
   const int n_it = (kv0 < kv_extent(p, b, ext_slot)) ? nq_tiles - i_begin : 0;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_gen;
   // TMEM columns: S^T_h at 64h, dP^T_h at 128 + 64h, dV at 256, dK at 352, P^T_h (packed bf16) at 448 + 32h
-  if (warp == 9) {
+  if (warp == W_TMA) {
     if (lane == 0 && n_it > 0) {
       mbar_expect_tx(bar_kv, 2 * QKV_BYTES);
       load_tile(&tmK, bar_kv, sK, h * DH, kv0, b);
@@ -943,7 +952,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_stf + 8 * st);
     }
-  } else if (warp == 8) {
+  } else if (warp == W_S) {
     // ---- S^T_h = K Q_h^T and dP^T_h = V dO_h^T of the NEXT query tile, as soon as warpgroup h has consumed the
     //      current ones
     if (lane == 0 && n_it > 0) {
@@ -978,7 +987,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tc_commit(bar_qe + 8 * sn);
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == W_G) {
     // ---- dV += P^T_h dO_h (A = P^T_h packed bf16 in TMEM) and dK += dS^T_h Q_h (A = dS^T_h in shared memory, which
     //      is also what the workspace store reads)
     if (lane == 0 && n_it > 0) {
@@ -1016,7 +1025,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (p.write_ds) tma_wait_group0();  // workspace writes complete before the grid ends
     }
   } else {
-    const int hh = warp >> 2, quad = warp & 3;  // warpgroup hh owns query columns [64 hh, 64 hh + 64) of every tile
+    // warps [0, AW / 2) own query columns [0, 64) of every tile (hh = 0), the others [64, 128); with AW = 16 two warps
+    // of the same TMEM lane quadrant share a key row: sub = 0 takes the first 32 of the half's 64 queries, sub = 1 the rest
+    constexpr int NSUB = AW / 8;
+    const int hh = warp / (AW / 2), quad = warp & 3, sub = NSUB == 2 ? (warp >> 2) & 1 : 0;
     const int r = quad * 32 + lane;  // local key row
     const int kv = kv0 + r;
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
@@ -1032,11 +1044,11 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const int q0 = qi * TILE + hh * 64;  // first query of this half
       // keep bits of (q = q0 + c0 + i, k = this thread's key row): lane L makes the word of query q0 + c0 + L over the
       // warp's 32 keys, then the warp transposes the 32x32 bit tile (index-only work, done before the waits)
-      uint32_t kw0 = keep_word(p, dkey, bh, (uint32_t)(q0 + lane), (uint32_t)((kv0 >> 5) + quad));
-      uint32_t kw1 = keep_word(p, dkey, bh, (uint32_t)(q0 + 32 + lane), (uint32_t)((kv0 >> 5) + quad));
+      uint32_t kw0 = keep_word(p, dkey, bh, (uint32_t)(q0 + 32 * sub + lane), (uint32_t)((kv0 >> 5) + quad));
+      uint32_t kw1 = NSUB == 1 ? keep_word(p, dkey, bh, (uint32_t)(q0 + 32 + lane), (uint32_t)((kv0 >> 5) + quad)) : 0u;
       if (p.thresh16 != 0) {
         kw0 = warp_bit_transpose(kw0, lane);
-        kw1 = warp_bit_transpose(kw1, lane);
+        if (NSUB == 1) kw1 = warp_bit_transpose(kw1, lane);
       }
       mbar_wait(bar_stf + 8 * st, (it >> 1) & 1);
       mbar_wait(bar_sf + 8 * hh, it & 1);
@@ -1049,11 +1061,11 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const float* ndv = dv_s + st * 128 + hh * 64;
       const bool rowmask = !__all_sync(0xffffffffu, row_valid);
       if (diag) {
-        if (rowmask) dkdv_half_tile<true, true>(tST, tDPT, tPT, lane_sel, sDSTh, nlse, ndv, kw0, kw1, r, hh, row_valid, p.scale_log2, p.inv_keep);
-        else dkdv_half_tile<true, false>(tST, tDPT, tPT, lane_sel, sDSTh, nlse, ndv, kw0, kw1, r, hh, row_valid, p.scale_log2, p.inv_keep);
+        if (rowmask) dkdv_half_tile<true, true, NSUB>(tST, tDPT, tPT, lane_sel, sDSTh, nlse, ndv, kw0, kw1, r, hh, row_valid, p.scale_log2, p.inv_keep, sub);
+        else dkdv_half_tile<true, false, NSUB>(tST, tDPT, tPT, lane_sel, sDSTh, nlse, ndv, kw0, kw1, r, hh, row_valid, p.scale_log2, p.inv_keep, sub);
       } else {
-        if (rowmask) dkdv_half_tile<false, true>(tST, tDPT, tPT, lane_sel, sDSTh, nlse, ndv, kw0, kw1, r, hh, row_valid, p.scale_log2, p.inv_keep);
-        else dkdv_half_tile<false, false>(tST, tDPT, tPT, lane_sel, sDSTh, nlse, ndv, kw0, kw1, r, hh, row_valid, p.scale_log2, p.inv_keep);
+        if (rowmask) dkdv_half_tile<false, true, NSUB>(tST, tDPT, tPT, lane_sel, sDSTh, nlse, ndv, kw0, kw1, r, hh, row_valid, p.scale_log2, p.inv_keep, sub);
+        else dkdv_half_tile<false, false, NSUB>(tST, tDPT, tPT, lane_sel, sDSTh, nlse, ndv, kw0, kw1, r, hh, row_valid, p.scale_log2, p.inv_keep, sub);
       }
       tmem_st_wait();
       fence_proxy_async_smem();
@@ -1073,7 +1085,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const float sc = hh == 0 ? 1.0f : p.scale;
       const uint32_t stage = hh == 0 ? sV : sK;
 #pragma unroll 1
-      for (int c = 0; c < 3; ++c) {
+      for (int c = (NSUB == 2 && sub == 1) ? 2 : 0; c < ((NSUB == 2 && sub == 0) ? 2 : 3); ++c) {
         uint32_t rr[32];
         if (n_it > 0) {
           tmem_ld32(src + lane_sel + c * 32, rr);
@@ -1085,8 +1097,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         stage_chunk_sw64(stage, r, c, rr, sc);
       }
       fence_proxy_async_smem();
-      named_bar_sync(1 + hh, 128);
-      if (quad == 0 && lane == 0) {
+      named_bar_sync(1 + hh, 16 * AW);
+      if (quad == 0 && lane == 0 && sub == 0) {
         store_tile(hh == 0 ? &tmDV : &tmDK, stage, h * DH, kv0, b);
         tma_commit_group();
         tma_wait_group_read0();  // shared memory stays valid until the store has read it
@@ -1095,7 +1107,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 512);
+  if (warp == W_S) tmem_dealloc(tmem, 512);
 }
 
 
@@ -1399,7 +1411,8 @@ int32_t sct_attn_bwd_ws(const void* q, int64_t ldq, const void* k, const void* v
       return rc;
     p.write_ds = 1;
   }
-  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_bwd_dkdv_kernel), BWD3_KV_SMEM)) return rc;
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_bwd_dkdv_kernel<8>), BWD3_KV_SMEM)) return rc;
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_bwd_dkdv_kernel<16>), BWD3_KV_SMEM)) return rc;
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_bwd_dq_kernel), BWD3_Q_SMEM)) return rc;
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_bwd_dq_ds_kernel), DQ2_SMEM)) return rc;
   {
@@ -1407,7 +1420,10 @@ int32_t sct_attn_bwd_ws(const void* q, int64_t ldq, const void* k, const void* v
     CUtensorMap tdk, tdv;
     if (int rc = make_qkv_map(&tdk, dk, lddkv, B, Lk, H)) return rc;
     if (int rc = make_qkv_map(&tdv, dv, lddkv, B, Lk, H)) return rc;
-    attn_bwd_dkdv_kernel<<<grid, BWD_KV_THREADS, BWD3_KV_SMEM, st>>>(tq, tk, tv, tdo, tds_st, tdk, tdv, p);
+    if (env_int("SCT_ATTN_BWD_WARPS", 16) == 16)
+      attn_bwd_dkdv_kernel<16><<<grid, bwd_kv_threads(16), BWD3_KV_SMEM, st>>>(tq, tk, tv, tdo, tds_st, tdk, tdv, p);
+    else
+      attn_bwd_dkdv_kernel<8><<<grid, bwd_kv_threads(8), BWD3_KV_SMEM, st>>>(tq, tk, tv, tdo, tds_st, tdk, tdv, p);
     SCT_LAUNCH_CHECK();
   }
   {

@@ -540,3 +540,90 @@ def test_two_models_interleaved_keep_their_own_dropout_masks(cuda_dev):
     live = br.detach().float().abs() > 0
     assert torch.equal(keep_fwd & live, keep_bwd & live)
     assert 0.4 < keep_bwd.float().mean().item() < 0.6
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[0] at FULL model size against the unmodified reference (fixture: oracle/make_golden_cfg1.py)
+CFG1 = os.path.join(ROOT, "tests", "golden_cfg1", "cfg1_default_model.pt")
+
+
+@pytest.mark.skipif(not os.path.exists(CFG1), reason="cfg1 fixture not generated")
+def test_cfg1_default_model_matches_reference(cuda_dev):
+    """The default SmartContractTransformer (6 + 6 layers, d = 768, V = 50265, 262.6 M parameters) on the cfg1 batch
+    (B = 8, S = 512, P = 128): forward fingerprints, every scalar loss, the gradient norm of every parameter, full
+    small gradients, row fingerprints of large ones and greedy tokens against the reference's fp32 CPU run.
+    Tolerances as everywhere: ids bit-exact, activations rel-L2 <= 2e-2, losses <= 1e-2, gradients
+    cosine >= 0.999 / rel-L2 <= 3e-2, norms within 4e-2 or twice the reference's own bf16-autocast deviation."""
+    from sct_gan_b200 import SmartContractTrainer
+
+    g = torch.load(CFG1, map_location="cpu", weights_only=False)
+    m, _, batch = build(g, train=False)
+    tr = SmartContractTrainer(m, use_augmentation=True, use_gan=True, line_vuln_weight=g["hp"]["line_vuln_weight"],
+                              contract_vuln_weight=g["hp"]["contract_vuln_weight"])
+    tr.current_epoch = 0
+    out = m(input_ids=batch["input_ids"], attention_mask=batch["attention_mask"],
+            ast_input_ids=batch["ast_input_ids"], ast_attention_mask=batch["ast_attention_mask"],
+            target_ids=batch["target_ids"], token_to_line=batch["token_to_line"], fused_loss=True, return_logits=True)
+    ref = g["outputs"]
+    assert torch.equal(out["target_ids"].cpu(), ref["target_ids"])
+    logits = out["logits"]
+    assert logits.shape == (8 * 511, 50265)
+    lse = torch.logsumexp(logits, dim=-1).cpu()
+    assert (lse - ref["logits_lse"]).abs().max().item() < 2e-2 * ref["logits_lse"].abs().max().item()
+    assert (out["lse"].cpu() - ref["logits_lse"]).abs().max().item() < 2e-2 * ref["logits_lse"].abs().max().item()
+    assert rel_l2(logits[:, ref["logits_cols"].cuda()], ref["logits_at_cols"].float()) < 2e-2
+    am = logits.argmax(dim=-1).cpu()
+    clear = ref["logits_top2_gap"] > 0.1
+    assert clear.float().mean().item() > 0.5 and torch.equal(am[clear], ref["logits_argmax"][clear])
+    del logits
+    for k in ("encoder_output", "contract_vulnerability_logits"):
+        assert rel_l2(out[k], ref[k]) < 2e-2, k
+    n_lines = ref["line_vulnerability_logits"].shape[1]
+    assert rel_l2(out["line_vulnerability_logits"][:, :n_lines], ref["line_vulnerability_logits"]) < 2e-2
+    assert (out["discriminator_logits"].cpu() - ref["discriminator_logits"]).abs().max().item() < 2e-2 * max(
+        1.0, ref["discriminator_logits"].abs().max().item())
+    losses = tr.compute_losses(out, batch)
+    assert abs(out["gen_ce_loss"].item() - g["losses"]["gen_ce_loss"]) < 1e-2 * g["losses"]["gen_ce_loss"]
+    for k in ("contract_vuln_loss", "line_vuln_loss", "discriminator_loss", "total_loss"):
+        assert abs(losses[k].item() - g["losses"][k]) < 1e-2 * max(abs(g["losses"][k]), 1e-3), (k, losses[k].item(), g["losses"][k])
+    losses["total_loss"].backward()
+    named = dict(m.named_parameters())
+    bad = []
+    for n, refg in g["grads"].items():
+        c, r = cosine(named[n].grad, refg), rel_l2(named[n].grad, refg)
+        if not (c >= 0.999 and r <= 3e-2):
+            bad.append((n, c, r))
+    for n, refg in g["grad_rows"].items():
+        c, r = cosine(named[n].grad[:4], refg), rel_l2(named[n].grad[:4], refg)
+        if not (c >= 0.998 and r <= 5e-2):
+            bad.append((n + "[:4]", c, r))
+    ids = g["embedding_grad_ids"]
+    c, r = cosine(named["embedding.weight"].grad[ids.cuda()], g["embedding_grad_rows"]), \
+        rel_l2(named["embedding.weight"].grad[ids.cuda()], g["embedding_grad_rows"])
+    if not (c >= 0.998 and r <= 5e-2):
+        bad.append(("embedding.weight[ids]", c, r))
+    ac = g["grad_norms_autocast"]
+    for n, gn in g["grad_norms"].items():
+        if gn is None:
+            assert named[n].grad is None or float(named[n].grad.abs().max()) == 0.0, n
+            continue
+        if gn < 1e-7:
+            continue
+        mine = float(named[n].grad.float().norm())
+        tol = max(4e-2, 2.0 * abs(ac[n] - gn) / gn) if ac.get(n) is not None else 4e-2
+        if abs(mine - gn) > tol * gn:
+            bad.append((n + " |norm|", mine, gn, tol))
+    assert not bad, bad
+    # greedy tokens through the KV-cached decode
+    m.zero_grad(set_to_none=True)
+    ref_toks, gaps = g["greedy_tokens"], g["greedy_gaps"]
+    n_new = ref_toks.shape[1] - 1
+    gen = m(input_ids=batch["input_ids"], attention_mask=batch["attention_mask"],
+            ast_input_ids=batch["ast_input_ids"], ast_attention_mask=batch["ast_attention_mask"],
+            target_ids=None, token_to_line=batch["token_to_line"], greedy=True, max_new_tokens=n_new)
+    toks = gen["generated_sequence"].cpu()
+    for b in range(toks.shape[0]):
+        for t in range(n_new):
+            if gaps[b, t] <= 1e-2 / 0.7:
+                break
+            assert toks[b, t + 1] == ref_toks[b, t + 1], (b, t, float(gaps[b, t]))
