@@ -171,10 +171,18 @@ def _is_nccl(group):
         return False
 
 
-def _launch_bucket(bucket, world, group):
-    """Mean all-reduce of the gradients of `bucket`, in place and asynchronously.  NCCL: one grouped launch
-    (coalescing manager, ReduceOp.AVG: no flatten / copy-back / scaling passes).  Other back-ends (gloo in the CPU
+def _launch_bucket(bucket, world, group, wire_bf16=False):
+    """Mean all-reduce of the gradients of `bucket`, in place and asynchronously.  NCCL, fp32 wire: one grouped launch
+    (coalescing manager, ReduceOp.AVG: no flatten / copy-back / scaling passes).  NCCL, bf16 wire: the
+    bucket is packed into ONE bf16 buffer by a multi-tensor cast, all-reduced (half the NVLink bytes, one collective
+    instead of a group), and unpacked into the fp32 gradients by `_finish_bucket`.  Other back-ends (gloo in the CPU
     tests): flat SUM + scale."""
+    if _is_nccl(group) and wire_bf16:
+        sizes = [p.grad.numel() for p in bucket]
+        flat = torch.empty(sum(sizes), dtype=torch.bfloat16, device=bucket[0].grad.device)
+        views = [v.view_as(p.grad) for v, p in zip(flat.split(sizes), bucket)]
+        torch._foreach_copy_(views, [p.grad for p in bucket])
+        return (dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group, async_op=True), views, bucket)
     if _is_nccl(group):
         with dist._coalescing_manager(group=group, device=bucket[0].grad.device, async_ops=True) as cm:
             for p in bucket:
@@ -187,6 +195,9 @@ def _launch_bucket(bucket, world, group):
 def _finish_bucket(work, world):
     w, flat, ps = work
     w.wait()
+    if isinstance(flat, list):  # bf16 wire: averaged values back into the fp32 gradients (multi-tensor cast)
+        torch._foreach_copy_([p.grad for p in ps], flat)
+        return
     if flat is not None:
         off = 0
         for p in ps:
@@ -220,43 +231,49 @@ class OverlappedGradReducer:
     """The same exchange, overlapped with backward: a post-accumulate-grad hook on every parameter collects
     gradients as autograd finishes them and launches a bucket's all-reduce as soon as it is full, on NCCL's own
     stream, while backward keeps producing the next bucket.  `finish()` joins before the clips.  Works inside a
-    CUDA-graph capture (the collectives become graph nodes on a forked stream)."""
+    CUDA-graph capture (the collectives become graph nodes on a forked stream).
 
-    def __init__(self, params, world, group=None, bucket_bytes=32 << 20):
+    Buckets are kept PER PRODUCING STREAM (the vulnerability heads run their backward on a side stream, overlapped
+    with the decoder's): a bucket only holds gradients of one stream and its collective is launched from that stream,
+    so it orders itself after exactly the kernels that produced it.  (Making the main stream wait for the side stream
+    before every bucket — the first version — serialised the two branches 28 times per step.)"""
+
+    def __init__(self, params, world, group=None, bucket_bytes=32 << 20, wire_bf16=False):
         self.world, self.group, self.bucket_bytes = world, group, bucket_bytes
-        self.bucket, self.size, self.works = [], 0, []
-        self.streams = {}  # CUDA streams gradients were produced on (the vulnerability heads run on a side stream)
+        self.wire_bf16 = wire_bf16
+        self.buckets, self.works = {}, []  # stream id -> [stream, [params], bytes]
         self.handles = [p.register_post_accumulate_grad_hook(self._hook) for p in params if p.requires_grad]
 
-    def _launch(self):
-        """A bucket may hold gradients from several streams, and the collective only orders itself after the stream
-        it is launched from: make that stream wait for the others first."""
-        if self.bucket[0].grad.is_cuda:
-            cur = torch.cuda.current_stream()
-            for sid, s in self.streams.items():
-                if sid != cur.cuda_stream:
-                    cur.wait_stream(s)
-        self.works.append(_launch_bucket(self.bucket, self.world, self.group))
-        self.bucket, self.size = [], 0
+    def _launch(self, ent):
+        stream, bucket = ent[0], ent[1]
+        if stream is not None:
+            with torch.cuda.stream(stream):
+                self.works.append(_launch_bucket(bucket, self.world, self.group, self.wire_bf16))
+        else:
+            self.works.append(_launch_bucket(bucket, self.world, self.group, self.wire_bf16))
+        ent[1], ent[2] = [], 0
 
     def _hook(self, p):
         if p.grad is None:
             return
         if p.grad.is_cuda:
             cur = torch.cuda.current_stream()
-            self.streams.setdefault(cur.cuda_stream, cur)
-        self.bucket.append(p)
-        self.size += p.grad.numel() * p.grad.element_size()
-        if self.size >= self.bucket_bytes:
-            self._launch()
+            ent = self.buckets.setdefault(cur.cuda_stream, [cur, [], 0])
+        else:
+            ent = self.buckets.setdefault(0, [None, [], 0])
+        ent[1].append(p)
+        ent[2] += p.grad.numel() * p.grad.element_size()
+        if ent[2] >= self.bucket_bytes:
+            self._launch(ent)
 
     def finish(self):
-        if self.bucket:
-            self._launch()
-        for w in self.works:
+        for ent in self.buckets.values():
+            if ent[1]:
+                self._launch(ent)
+        for w in self.works:  # the caller's stream waits for every collective (and runs the bf16 unpack casts)
             _finish_bucket(w, self.world)
         self.works = []
-        self.streams = {}  # per step: a captured step runs on other streams than the eager warm-up before it
+        self.buckets = {}  # per step: a captured step runs on other streams than the eager warm-up before it
 
 
 class FusedClipAdamW:
@@ -412,8 +429,8 @@ class SmartContractTrainer:
 
     def __init__(self, model, learning_rate=1e-6, weight_decay=0.1, max_grad_norm=1.0, use_augmentation=False,
                  use_gan=False, line_vuln_weight=2.0, contract_vuln_weight=3.0, warmup_epochs=5,
-                 compute_vuln_heads=True, process_group=None, bucket_mb=32, use_cuda_graph=False,
-                 fused_optimizer=True, syntax_rules=None, line_metrics=False):
+                 compute_vuln_heads=True, process_group=None, bucket_mb=128, use_cuda_graph=False,
+                 fused_optimizer=True, syntax_rules=None, line_metrics=False, grad_wire_dtype="bf16"):
         self.model = model
         self.line_metrics = line_metrics  # also return the adaptive-threshold line metrics of train.py:1043-1140
         self.use_augmentation = use_augmentation
@@ -459,8 +476,10 @@ class SmartContractTrainer:
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.bucket_bytes = int(__import__("os").environ.get("SCT_DP_BUCKET_MB", bucket_mb)) << 20
-        self._reducer = OverlappedGradReducer(list(model.parameters()), self.world, process_group, self.bucket_bytes) \
-            if self.world > 1 else None
+        # gradient exchange on the wire: bf16 (default; half the NVLink bytes) or fp32 (SCT_DP_GRAD_DTYPE=fp32)
+        self.wire_bf16 = on_gpu and __import__("os").environ.get("SCT_DP_GRAD_DTYPE", grad_wire_dtype) == "bf16"
+        self._reducer = OverlappedGradReducer(list(model.parameters()), self.world, process_group, self.bucket_bytes,
+                                              self.wire_bf16) if self.world > 1 else None
         self.use_cuda_graph = use_cuda_graph and on_gpu
         self._fused_tail = FusedClipAdamW(self.optimizer, list(model.named_parameters()), use_gan, max_grad_norm) \
             if (fused_optimizer and on_gpu) else None

@@ -1,0 +1,110 @@
+"""Data parallelism on real GPUs (NCCL, 2 ranks): one adversarial train step of the drop-in model on a batch sharded
+8 = 4 + 4 must equal the single-GPU step on the whole batch — loss terms, gradient norm, updated weights — for both
+wire formats of the gradient exchange.  Skipped when fewer than two devices are visible (the round-end GPU tier has
+one); run with `gpurun --gpus 2 -- python -m pytest tests/test_dp_gpu.py -m gpu`."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+CFG_OVER = dict(num_encoder_layers=2, num_decoder_layers=2, dim_feedforward=1024, max_length=1024, vocab_size=4096,
+                dropout=0.0)
+B, S, P = 8, 1024, 256  # S = 1024: the spatial penalty (cross-sample per-line sums) is live
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _setup(dev):
+    from oracle import sct_oracle as O
+    from sct_gan_b200 import SmartContractTransformer
+
+    cfg = {**O.DEFAULT_CFG, **CFG_OVER}
+    torch.manual_seed(0)
+    m = SmartContractTransformer(**cfg)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict(O.synth_state_dict(shapes, 5))
+    m = m.to(dev)
+    batch = O.make_batch(B, S, P, cfg["vocab_size"], seed=5)
+    return m, batch
+
+
+def _probe(m, res):
+    named = dict(m.named_parameters())
+    keys = ["output_layer.weight", "encoder.layers.0.linear1.weight", "embedding.weight", "ast_embedding.weight",
+            "decoder.layers.1.multihead_attn.in_proj_weight", "disc_synthetic_head.4.weight",
+            "line_vulnerability_head_1.6.weight"]
+    out = {k: float(res[k]) for k in ("total_loss", "gen_loss", "line_vuln_loss", "contract_vuln_loss", "grad_norm")}
+    out["stepped"] = bool(res["stepped"])
+    out["weights"] = {k: named[k].detach().double().sum().item() for k in keys}
+    out["w_rows"] = {k: named[k].detach()[:2].float().cpu() for k in keys}
+    return out
+
+
+def _worker(rank, world, port, wire, ret):
+    import torch.distributed as dist
+
+    from sct_gan_b200 import SmartContractTrainer
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    m, batch = _setup(dev)
+    tr = SmartContractTrainer(m, learning_rate=1e-4, use_augmentation=True, use_gan=True, grad_wire_dtype=wire)
+    n = B // world
+    shard = {k: v[rank * n:(rank + 1) * n].to(dev) for k, v in batch.items()}
+    res = tr.train_step(shard, n_lines=int(batch["token_to_line"].max()) + 1)
+    torch.cuda.synchronize()
+    ret[rank] = _probe(m, res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("wire", ["fp32", "bf16"])
+def test_dp2_step_equals_single_gpu_step(cuda_dev, wire):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+
+    from sct_gan_b200 import SmartContractTrainer
+
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), wire, ret), nprocs=2, join=True)
+    m, batch = _setup(torch.device("cuda", 0))
+    tr = SmartContractTrainer(m, learning_rate=1e-4, use_augmentation=True, use_gan=True)
+    res = tr.train_step({k: v.cuda() for k, v in batch.items()}, n_lines=int(batch["token_to_line"].max()) + 1)
+    one = _probe(m, res)
+    r0, r1 = ret[0], ret[1]
+    assert r0["stepped"] and r1["stepped"] and one["stepped"]
+    # replicas agree bit for bit after the exchange + deterministic optimiser tail
+    assert r0["weights"] == r1["weights"] and r0["grad_norm"] == r1["grad_norm"]
+    # mean of the shard losses = loss of the whole batch (equal shards, mean-reduced terms)
+    for k in ("gen_loss", "contract_vuln_loss", "line_vuln_loss"):
+        avg = 0.5 * (r0[k] + r1[k])
+        assert abs(avg - one[k]) < 2e-3 * max(abs(one[k]), 1e-3), (k, avg, one[k])
+    tol = 2e-3 if wire == "fp32" else 1e-2  # bf16 wire: gradients rounded to 8 bits before the clip / AdamW
+    assert abs(r0["grad_norm"] - one["grad_norm"]) < tol * one["grad_norm"], (r0["grad_norm"], one["grad_norm"])
+    # AdamW moves every weight by ~lr per step in the direction of its gradient's sign: compare the update itself
+    m0, _ = _setup(torch.device("cuda", 0))
+    base = {k: v.detach()[:2].float().cpu() for k, v in dict(m0.named_parameters()).items() if k in one["w_rows"]}
+    for k, w1 in one["w_rows"].items():
+        d_one, d_dp = w1 - base[k], r0["w_rows"][k] - base[k]
+        moved = d_one.abs() > 0
+        if moved.sum() == 0:
+            continue
+        # (the first AdamW step is lr * sign(g): an element whose tiny gradient changes sign under a different
+        # summation order moves by 2 lr, so agreement is counted in signs: 5 % flips <=> relative distance 0.45)
+        agree = (torch.sign(d_one[moved]) == torch.sign(d_dp[moved])).float().mean().item()
+        assert agree > 0.95, (k, agree)
+        assert (d_one - d_dp).norm().item() < 0.45 * d_one.norm().item() + 1e-12, (k, agree)
