@@ -811,22 +811,44 @@ template <bool DIAG, bool ROWMASK, int NSUB>
 __device__ __forceinline__ void dkdv_half_tile(uint32_t tST, uint32_t tDPT, uint32_t tPT, uint32_t lane_sel,
                                                uint32_t sDSTh, const float* __restrict__ nlse,
                                                const float* __restrict__ ndv, uint32_t kw0, uint32_t kw1, int r, int hh,
-                                               bool row_valid, float scale_log2, float inv_keep, int sub) {
+                                               bool row_valid, float scale_log2, float inv_keep, int sub,
+                                               uint32_t bar_consumed) {
   constexpr int NCH = 4 / NSUB;  // chunks per thread
   const int cc0 = NSUB == 1 ? 0 : 2 * sub;
   uint32_t rs[2][16], rp[2][16];
   tmem_ld16(tST + lane_sel + cc0 * 16, rs[0]);
   tmem_ld16(tDPT + lane_sel + cc0 * 16, rp[0]);
+  if (NSUB == 2) {  // both chunks of this thread at once: its share of S^T / dP^T is in registers after ONE wait
+    tmem_ld16(tST + lane_sel + cc0 * 16 + 16, rs[1]);
+    tmem_ld16(tDPT + lane_sel + cc0 * 16 + 16, rp[1]);
+  }
+  // `bar_consumed`: S^T_h / dP^T_h have been read — the issuer may overwrite them with the NEXT query tile's scores
+  // while this tile is still in the ALUs (the profile showed the arithmetic warps waiting for those MMAs 31 % of
+  // the time when the hand-off only happened after the whole tile had been processed)
+  auto signal_consumed = [&]() {
+    tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar_consumed);
+  };
   const float2 sc2 = make_float2(scale_log2, scale_log2);
 #pragma unroll
   for (int ci = 0; ci < NCH; ++ci) {
     const int cc = cc0 + ci;
     const int c0 = cc * 16;
     const uint32_t kw = NSUB == 1 ? ((cc < 2 ? kw0 : kw1) >> ((cc & 1) * 16)) : (kw0 >> (ci * 16));
-    tmem_ld_wait();
-    if (ci + 1 < NCH) {
-      tmem_ld16(tST + lane_sel + c0 + 16, rs[(ci + 1) & 1]);
-      tmem_ld16(tDPT + lane_sel + c0 + 16, rp[(ci + 1) & 1]);
+    if (NSUB == 2) {
+      if (ci == 0) {
+        tmem_ld_wait();
+        signal_consumed();
+      }
+    } else {
+      tmem_ld_wait();
+      if (ci + 1 < NCH) {
+        tmem_ld16(tST + lane_sel + c0 + 16, rs[(ci + 1) & 1]);
+        tmem_ld16(tDPT + lane_sel + c0 + 16, rp[(ci + 1) & 1]);
+      } else {
+        signal_consumed();
+      }
     }
     const uint32_t (&s_)[16] = rs[ci & 1];
     const uint32_t (&p_)[16] = rp[ci & 1];
@@ -897,6 +919,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const uint32_t bar_kv = bar0, bar_qf = bar0 + 8, bar_qe = bar0 + 24, bar_stf = bar0 + 40, bar_sf = bar0 + 56,
                  bar_pf = bar0 + 72, bar_gd = bar0 + 88, bar_fin = bar0 + 104;
   const uint32_t tmem_ptr_addr = bar0 + 112;
+  const uint32_t bar_sc = bar0 + 128;  // [2] S^T_h / dP^T_h of the current tile are in the arithmetic warps' registers
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen + (tmem_ptr_addr - base));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -914,6 +937,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_init(bar_stf + 8 * i, 1);
       mbar_init(bar_sf + 8 * i, 1);
       mbar_init(bar_pf + 8 * i, AW / 2);  // one arrival per arithmetic warp of the half
+      mbar_init(bar_sc + 8 * i, AW / 2);
       mbar_init(bar_gd + 8 * i, 1);
     }
     fence_mbar_init();
@@ -980,7 +1004,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tc_fence_after();
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          mbar_wait(bar_pf + 8 * hh, it & 1);  // S^T_h / dP^T_h of tile `it` are in registers
+          mbar_wait(bar_sc + 8 * hh, it & 1);  // S^T_h / dP^T_h of tile `it` are in registers
           tc_fence_after();
           issue_s(hh, sn);
         }
@@ -1061,11 +1085,11 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const float* ndv = dv_s + st * 128 + hh * 64;
       const bool rowmask = !__all_sync(0xffffffffu, row_valid);
       if (diag) {
-        if (rowmask) dkdv_half_tile<true, true, NSUB>(tST, tDPT, tPT, lane_sel, sDSTh, nlse, ndv, kw0, kw1, r, hh, row_valid, p.scale_log2, p.inv_keep, sub);
-        else dkdv_half_tile<true, false, NSUB>(tST, tDPT, tPT, lane_sel, sDSTh, nlse, ndv, kw0, kw1, r, hh, row_valid, p.scale_log2, p.inv_keep, sub);
+        if (rowmask) dkdv_half_tile<true, true, NSUB>(tST, tDPT, tPT, lane_sel, sDSTh, nlse, ndv, kw0, kw1, r, hh, row_valid, p.scale_log2, p.inv_keep, sub, bar_sc + 8 * hh);
+        else dkdv_half_tile<true, false, NSUB>(tST, tDPT, tPT, lane_sel, sDSTh, nlse, ndv, kw0, kw1, r, hh, row_valid, p.scale_log2, p.inv_keep, sub, bar_sc + 8 * hh);
       } else {
-        if (rowmask) dkdv_half_tile<false, true, NSUB>(tST, tDPT, tPT, lane_sel, sDSTh, nlse, ndv, kw0, kw1, r, hh, row_valid, p.scale_log2, p.inv_keep, sub);
-        else dkdv_half_tile<false, false, NSUB>(tST, tDPT, tPT, lane_sel, sDSTh, nlse, ndv, kw0, kw1, r, hh, row_valid, p.scale_log2, p.inv_keep, sub);
+        if (rowmask) dkdv_half_tile<false, true, NSUB>(tST, tDPT, tPT, lane_sel, sDSTh, nlse, ndv, kw0, kw1, r, hh, row_valid, p.scale_log2, p.inv_keep, sub, bar_sc + 8 * hh);
+        else dkdv_half_tile<false, false, NSUB>(tST, tDPT, tPT, lane_sel, sDSTh, nlse, ndv, kw0, kw1, r, hh, row_valid, p.scale_log2, p.inv_keep, sub, bar_sc + 8 * hh);
       }
       tmem_st_wait();
       fence_proxy_async_smem();

@@ -270,16 +270,27 @@ small_linear_fwd_kernel(const float* __restrict__ xf, const __nv_bfloat16* __res
 #pragma unroll
   for (int j = 0; j < NV; ++j) wr[j] = *reinterpret_cast<const float4*>(w + (long long)n * K + (j * 32 + lane) * 4);
   const float bn = bias ? bias[n] : 0.f;
-  for (int m = 0; m < M; ++m) {
-    float acc = 0.f;
+  // four rows per trip: their loads and their butterfly reductions are independent, so the ~600-cycle round trips of a
+  // row's x loads and the five dependent shuffles of its reduction overlap (the one-row loop was a serial chain of both)
+  for (int m0 = 0; m0 < M; m0 += 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const float4 xv = ld_row4(xf, xb, (long long)m * K + (j * 32 + lane) * 4);
-      acc += (xv.x * wr[j].x + xv.y * wr[j].y) + (xv.z * wr[j].z + xv.w * wr[j].w);
+    for (int q = 0; q < 4; ++q) {
+      const int m = min(m0 + q, M - 1);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float4 xv = ld_row4(xf, xb, (long long)m * K + (j * 32 + lane) * 4);
+        acc[q] += (xv.x * wr[j].x + xv.y * wr[j].y) + (xv.z * wr[j].z + xv.w * wr[j].w);
+      }
     }
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      const float y = acc + bn;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+    }
+    if (lane < 4 && m0 + lane < M) {
+      const float y = (lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]) + bn;
+      const int m = m0 + lane;
       if (yf) yf[(long long)m * N + n] = y;
       if (yb) yb[(long long)m * N + n] = __float2bfloat16(y);
     }
@@ -300,6 +311,7 @@ small_linear_bwd_w_kernel(const float* __restrict__ dyf, const __nv_bfloat16* __
 #pragma unroll
   for (int j = 0; j < NV; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   float sb = 0.f;
+#pragma unroll 4
   for (int m = 0; m < M; ++m) {
     const float g = dyf ? dyf[(long long)m * N + n] : __bfloat162float(dyb[(long long)m * N + n]);
     sb += g;

@@ -13,6 +13,7 @@ Differences from the reference that do not change results:
 """
 from __future__ import annotations
 
+import contextlib
 import math
 
 import torch
@@ -488,6 +489,7 @@ class SmartContractTrainer:
             self._fused_tail.shadows = model._shadow  # bf16 weight copies are refreshed by the optimiser kernel
         self._graphs = {}
         self.last = {}
+        self._extras_stream = None
         self.use_grad_arena = on_gpu and __import__("os").environ.get("SCT_GRAD_ARENA", "1") != "0"  # =0: A/B timing
 
     # ------------------------------------------------------------------------------------------
@@ -580,17 +582,38 @@ class SmartContractTrainer:
                     ast_input_ids=batch["ast_input_ids"], ast_attention_mask=batch["ast_attention_mask"],
                     target_ids=target_ids, token_to_line=batch.get("token_to_line"), fused_loss=True,
                     return_logits=False, compute_vuln_heads=self.compute_vuln_heads, n_lines=n_lines)
-        if self.syntax_rules is not None:
-            syntax_penalty = self.syntax_rules.penalty(out["target_ids"])
-        losses = self.compute_losses(out, batch, syntax_penalty, n_lines)
-        losses["syntax_penalty"] = syntax_penalty if torch.is_tensor(syntax_penalty) else None
-        if self.line_metrics and self.compute_vuln_heads:
-            with torch.no_grad():
-                losses.update(line_vulnerability_metrics(out["line_vulnerability_logits"].detach(),
+        # The syntax penalty (a constant: train.py:327-330 builds it from .item() values, so it carries no gradient) and
+        # the line metrics (logging only) do not gate the backward pass: on the GPU they run on a side stream next to
+        # it (~90 tiny integer / sort kernels, 0.6 ms when serialised between forward and backward) and are joined
+        # before the optimiser tail, whose skip rule looks at the loss INCLUDING the penalty.
+        want_metrics = self.line_metrics and self.compute_vuln_heads
+        dev_rules = self.syntax_rules is not None
+        side = None
+        extras = {}
+        if (dev_rules or want_metrics) and out["gen_ce_loss"].is_cuda:
+            main = torch.cuda.current_stream()
+            if self._extras_stream is None or self._extras_stream.device != out["gen_ce_loss"].device:
+                self._extras_stream = torch.cuda.Stream(device=out["gen_ce_loss"].device)
+            side = self._extras_stream
+            side.wait_stream(main)
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()), torch.no_grad():
+            if dev_rules:
+                extras["syntax_penalty"] = self.syntax_rules.penalty(out["target_ids"])
+            if want_metrics:
+                extras.update(line_vulnerability_metrics(out["line_vulnerability_logits"].detach(),
                                                          batch["vulnerable_lines"]))
+        losses = self.compute_losses(out, batch, 0.0 if dev_rules else syntax_penalty, n_lines)
         self.optimizer.zero_grad(set_to_none=True)
         losses["total_loss"].backward()
         self._allreduce_grads()
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+        losses["syntax_penalty"] = extras.pop("syntax_penalty", None)
+        if dev_rules:  # gen = ce + 0.5 * penalty (train.py:330); total carries gen with weight 0.5 (0.6 without the GAN)
+            w_gen = 0.6 if (self.use_augmentation and not self.use_gan) else 0.5
+            losses["gen_loss"] = losses["gen_loss"].detach() + 0.5 * losses["syntax_penalty"]
+            losses["total_loss"] = losses["total_loss"].detach() + w_gen * 0.5 * losses["syntax_penalty"]
+        losses.update(extras)
         if self._fused_tail is not None:
             total_norm, ok = self._fused_tail.step(losses["total_loss"])
         else:
