@@ -251,6 +251,13 @@ __device__ __forceinline__ uint32_t cluster_map(uint32_t saddr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Same without release semantics.  `.release.cluster` compiles to MEMBAR.ALL.GPU (about a microsecond: it drains the
+// thread's outstanding global traffic); where the arrival publishes no generic-proxy memory — "this TMEM accumulator
+// stage has been read" (ordered by tcgen05.fence::before_thread_sync), "this queue slot has been consumed" — the
+// relaxed form is enough and costs one instruction.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 // TMA load issued by either CTA of the pair into its OWN shared memory; the bytes are counted on `bar`, a
 // shared::cluster address (the leader CTA's `full` barrier), which is what the MMA-issuing thread waits on.
 __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1) {

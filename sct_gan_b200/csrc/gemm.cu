@@ -31,6 +31,9 @@
 // (`empty`) and the accumulator hand-off (`tfull`) to both CTAs; both epilogues arrive on the leader's `tempty`.
 #include <stdlib.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "../../include/sct_b200.h"
 #include "common.cuh"
 
@@ -67,6 +70,8 @@ struct EpiParams {
 
 struct GemmParams {
   EpiParams epi;
+  int* sched;  // [2] device ints, zero on entry and on exit: next work item, leaders that have drained the queue
+  int dynamic; // 1: items drawn from the counter; 0: static stride over the grid (SCT_GEMM_DYNAMIC=0, A/B timing)
   int M, N, K;
   int m_tiles, n_tiles, k_splits;
   int kb_total, kb_per_split;
@@ -170,6 +175,58 @@ __device__ __forceinline__ uint32_t epi_keep_word(const EpiParams& e, uint32_t k
   return ~lt;
 }
 
+// ---- dynamic work distribution ---------------------------------------------------------------------------------
+// Work items (tiles, or pairs of tiles) are handed out by an atomic counter instead of a static stride over the grid:
+// a persistent kernel that ASSUMES all 148 SMs loses a whole extra wave when some are busy with something else — the
+// NCCL all-reduce kernels of the data-parallel gradient exchange hold 16-32 SMs for ~0.3 ms per bucket while backward
+// keeps launching GEMMs whose 227 KB CTAs cannot share an SM with them (measured: +1.3 ms per step at 2 GPUs).  With
+// the queue, CTAs that start late simply find less (or nothing) left.
+// The leader CTA's producer thread draws the item and publishes it through a 2-slot queue in shared memory (of both
+// CTAs of a pair: DSMEM store + remote arrive); every role of the CTA(s) — MMA issuer, epilogue warps, column-sum
+// warps, the peer's producer — consumes the slot and hands it back on the LEADER's `empty` barrier.
+// Cross-CTA signalling uses RELAXED cluster-scope operations only: a `.release.cluster` arrive compiles to
+// MEMBAR.ALL.GPU (it has to drain the thread's outstanding global traffic — the prefetched atomic, in-flight stores),
+// about a microsecond on the producer's critical path per tile (measured: -11 % throughput).  The leader therefore
+// sends the item to the peer CTA as ONE tagged word (sequence number | item) that the peer's roles poll for in their
+// own shared memory: a single-word message needs no ordering with anything else.
+struct TileQueue {
+  uint32_t full;          // leader CTA: its full[2] barriers
+  uint32_t empty_leader;  // the leader CTA's empty[2] barriers (shared::cluster address when remote)
+  const volatile uint32_t* slots;
+  int qs;
+  uint32_t ph;
+  uint32_t seq;           // items consumed so far (tag expected in the slot)
+  bool remote;
+  // consumer: all lanes of the calling warp (or a single thread) get the item; one lane releases the slot
+  __device__ __forceinline__ int next(bool whole_warp) {
+    uint32_t m;
+    if (!remote) {
+      mbar_wait(full + 8 * qs, ph);
+      m = slots[qs];
+    } else {
+      uint64_t t0 = 0;
+#pragma unroll 1
+      for (uint32_t spins = 1;; ++spins) {
+        m = slots[qs];
+        if ((m >> 24) == (seq & 0xFFu)) break;
+        __nanosleep(32);
+        if ((spins & 0x3FFFu) == 0 && mbar_wait_timeout_check(t0)) return -1;  // debug safety net: give up, drain
+      }
+    }
+    if (whole_warp) __syncwarp();
+    if (!whole_warp || (threadIdx.x & 31) == 0) {
+      if (remote)
+        mbar_arrive_cluster_relaxed(empty_leader + 8 * qs);
+      else
+        mbar_arrive(empty_leader + 8 * qs);
+    }
+    if ((qs ^= 1) == 0) ph ^= 1;
+    ++seq;
+    return (int)(m & 0xFFFFFFu) - 1;
+  }
+};
+__device__ __forceinline__ uint32_t tq_message(uint32_t seq, int t) { return ((seq & 0xFFu) << 24) | (uint32_t)(t + 1); }
+
 template <int BN, bool A_MN, bool B_MN, bool OUT_F32, int CLUSTER, int EPI>
 __global__ void __launch_bounds__(EPI != EPI_NONE ? kThreadsEpi : kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -191,6 +248,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t tmem_ptr_addr = bar_tempty + 16;
   const uint32_t bar_done = sAux + 512;  // [STAGES] colsum mode: the MMAs reading this stage have retired
   const uint32_t bar_g = sAux + 640;     // [4] EPI_MUL: the multiplier chunk has landed in staging block i
+  const uint32_t tq_full = sAux + 704, tq_empty = sAux + 720;  // [2] + [2] work-item queue
+  const uint32_t tq_slots = sAux + 736;                        // [2] ints
+  const volatile uint32_t* tq_gen = reinterpret_cast<const volatile uint32_t*>(smem_gen + (tq_slots - smem_base));
   volatile uint32_t* tmem_ptr_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_addr - smem_base));
   float* bias_s = reinterpret_cast<float*>(smem_gen + (sAux + C::AUX_BYTES - smem_base));
@@ -200,8 +260,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   // work items: with CLUSTER = 2 an item is a PAIR of vertically adjacent tiles (p.m_tiles then counts pairs)
   const int total_tiles = p.m_tiles * p.n_tiles * p.k_splits;
   const int crank = CLUSTER > 1 ? (int)cluster_ctarank() : 0;
-  const int item0 = CLUSTER > 1 ? (int)(blockIdx.x / CLUSTER) : (int)blockIdx.x;
-  const int item_stride = CLUSTER > 1 ? (int)(gridDim.x / CLUSTER) : (int)gridDim.x;
+  const int n_leaders = CLUSTER > 1 ? (int)(gridDim.x / CLUSTER) : (int)gridDim.x;
+  const bool cs_active = A_MN && EPI == EPI_NONE && p.colsum != nullptr;  // column-sum warps take part in the queue
+  constexpr int kEpiWarps = EPI != EPI_NONE ? 8 : 4;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -214,6 +275,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(bar_done + 8 * s, 1);
     }
     for (int s = 0; s < 4; ++s) mbar_init(bar_g + 8 * s, 1);
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(tq_slots), "r"(0x7F000000u) : "memory");      // tags no consumer expects
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(tq_slots + 4), "r"(0x7F000000u) : "memory");
+    {
+      // consumers of a queue slot: leader CTA = MMA thread + epilogue warps (+ 2 column-sum warps); peer CTA = its
+      // producer thread + epilogue warps (+ column-sum warps).  All of them arrive on the LEADER's `empty`.
+      const int per_cta = kEpiWarps + (cs_active ? 2 : 0) + 1;
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(tq_full + 8 * s, 1);
+        mbar_init(tq_empty + 8 * s, per_cta * CLUSTER);
+      }
+    }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
       mbar_init(bar_tempty + 8 * s, (EPI != EPI_NONE ? 8 : 4) * CLUSTER);  // one arrival per epilogue warp (of both CTAs of a pair)
@@ -229,13 +301,43 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  TileQueue tq;
+  tq.full = tq_full;
+  tq.remote = CLUSTER > 1 && crank != 0;
+  tq.empty_leader = tq.remote ? cluster_map(tq_empty, 0) : tq_empty;
+  tq.slots = tq_gen;
+  tq.qs = 0;
+  tq.ph = 0;
+  tq.seq = 0;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = item0; t < total_tiles; t += item_stride) {
+      int gq = 0;           // leader: queue slot to fill next
+      uint32_t gph = 0, gseq = 0;
+      // the draw for item i + 1 is issued while the loads of item i are being queued: the ~1 us round trip of the
+      // atomic would otherwise sit on the producer's critical path once per tile (measured: -10 % GEMM throughput)
+      const int leader_id = CLUSTER > 1 ? (int)(blockIdx.x / CLUSTER) : (int)blockIdx.x;
+      int t_next = crank == 0 ? (p.dynamic ? atomicAdd(p.sched, 1) : leader_id) : 0;
+      while (true) {
+        int t;
+        if (crank == 0) {   // publish the drawn work item to every role of the CTA (pair)
+          t = t_next < total_tiles ? t_next : -1;
+          if (t >= 0) t_next = p.dynamic ? atomicAdd(p.sched, 1) : t_next + n_leaders;
+          mbar_wait(tq_empty + 8 * gq, gph ^ 1);
+          const uint32_t msg = tq_message(gseq++, t);
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(tq_slots + 4 * gq), "r"(msg) : "memory");
+          mbar_arrive(tq_full + 8 * gq);
+          if (CLUSTER > 1)
+            asm volatile("st.relaxed.cluster.shared::cluster.b32 [%0], %1;" ::"r"(cluster_map(tq_slots + 4 * gq, 1)), "r"(msg)
+                         : "memory");
+          if ((gq ^= 1) == 0) gph ^= 1;
+        } else {
+          t = tq.next(false);
+        }
+        if (t < 0) break;
         TileCoord tc = decode_tile(p, t);
         if (CLUSTER > 1) tc.m_blk = tc.m_blk * CLUSTER + crank;
         for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
@@ -286,6 +388,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       }
+      // every leader draws exactly one item past the end; the last one to do so puts the counters back to zero for the
+      // next launch that uses this slot (launches of one stream are ordered; slots are not shared across streams)
+      if (crank == 0 && p.dynamic && atomicAdd(p.sched + 1, 1) == n_leaders - 1) {
+        p.sched[0] = 0;
+        p.sched[1] = 0;
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
@@ -301,7 +409,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
-      for (int t = item0; t < total_tiles; t += item_stride) {
+      for (int t = tq.next(false); t >= 0; t = tq.next(false)) {
         const TileCoord tc = decode_tile(p, t);
         mbar_wait(bar_tempty + 8 * as, aph ^ 1);
         tc_fence_after();
@@ -347,7 +455,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ===================== column sums of A (warps 6, 7; wgrad only) =====================
     // The n_tiles items that share a row block see the same A tiles: item n_blk sums the k-blocks with
     // kb % n_tiles == n_blk, so the extra shared-memory reads are spread over all items.
-    if (A_MN && p.colsum != nullptr) {
+    if (cs_active) {
       const int cw = warp - 6;  // 64-column block of the [64 k x 128 m] A tile this warp sums
       // lane reads the 16-byte chunk (lane & 7) of k-rows (lane >> 3) + 4 i; chunks are XOR-swizzled by (row & 7)
       const uint32_t rg = lane >> 3, ch = lane & 7;
@@ -355,7 +463,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t off_odd = rg * 128 + ((ch ^ (rg + 4)) << 4);   // rows with (row & 7) == rg + 4
       int s = 0;
       uint32_t done_ph = 0;  // phase bit per stage of the `done` barriers (only some stages use them)
-      for (int t = item0; t < total_tiles; t += item_stride) {
+      for (int t = tq.next(true); t >= 0; t = tq.next(true)) {
         TileCoord tc = decode_tile(p, t);
         float acc[8];
 #pragma unroll
@@ -427,7 +535,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     constexpr int UNITS = NCHUNK;  // 32-column units this group handles per tile: NCHUNK / 2 chunks x 2 halves
     const uint32_t blk_z = sC + grp * (BM * 128) + row * 128;  // H (forward) / dZ (backward) staging block of this group
     const uint32_t blk_h = blk_z + 2 * (BM * 128);             // G staging block (forward only)
-    for (int t = item0; t < total_tiles; t += item_stride) {
+    for (int t = tq.next(true); t >= 0; t = tq.next(true)) {
       TileCoord tc = decode_tile(p, t);
       if (CLUSTER > 1) tc.m_blk = tc.m_blk * CLUSTER + crank;
       const int n0 = tc.n_blk * BN;
@@ -478,7 +586,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (PAIR) mbar_arrive_cluster(cluster_map(bar_tempty + 8 * as, 0));
+            if (PAIR) mbar_arrive_cluster_relaxed(cluster_map(bar_tempty + 8 * as, 0));
             else mbar_arrive(bar_tempty + 8 * as);
           }
         }
@@ -558,7 +666,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const bool store_thread = (etid == 0);
     int as = 0;
     uint32_t aph = 0;
-    for (int t = item0; t < total_tiles; t += item_stride) {
+    for (int t = tq.next(true); t >= 0; t = tq.next(true)) {
       TileCoord tc = decode_tile(p, t);
       if (CLUSTER > 1) tc.m_blk = tc.m_blk * CLUSTER + crank;
       const int n0 = tc.n_blk * BN;
@@ -618,7 +726,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (PAIR) mbar_arrive_cluster(cluster_map(bar_tempty + 8 * as, 0));
+            if (PAIR) mbar_arrive_cluster_relaxed(cluster_map(bar_tempty + 8 * as, 0));
             else mbar_arrive(bar_tempty + 8 * as);
           }
         }
@@ -654,6 +762,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // -----------------------------------------------------------------------------------------------
 // host launcher
 // -----------------------------------------------------------------------------------------------
+// Work-queue counters: a ring of (next item, drained leaders) pairs in device global memory, zero between launches
+// (the kernel's last leader resets its pair).  A launch takes the next pair of the ring; 4096 pairs are far more than
+// the launches that can be in flight at once, and a captured graph keeps the pairs it was captured with.
+constexpr int kSchedSlots = 4096;
+__device__ int g_sched[2 * kSchedSlots];
+
+int* next_sched_slot() {
+  static std::atomic<unsigned> seq{0};
+  static std::mutex mu;
+  static int* base[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  int* b = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (base[dev] == nullptr) {
+      void* ptr = nullptr;
+      if (cudaGetSymbolAddress(&ptr, g_sched) != cudaSuccess) return nullptr;
+      base[dev] = static_cast<int*>(ptr);
+    }
+    b = base[dev];
+  }
+  return b + 2 * (seq.fetch_add(1) % kSchedSlots);
+}
+
 struct EpiArgs {  // host-side description of a fused epilogue (EPI_NONE: all zero)
   void* d2 = nullptr;       // EPI_GELU_FWD: second output H [M, ldd2]
   int64_t ldd2 = 0;
@@ -718,6 +851,9 @@ int launch_impl(const void* A, int64_t lda, const void* B, int64_t ldb, void* D,
 
   GemmParams p;
   fill_epi(p.epi, ea);
+  p.dynamic = env_int("SCT_GEMM_DYNAMIC", 1);
+  p.sched = next_sched_slot();
+  SCT_CHECK(p.sched != nullptr, "work-queue counters unavailable");
   p.M = (int)M;
   p.N = (int)N;
   p.K = (int)K;
