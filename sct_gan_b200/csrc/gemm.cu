@@ -851,7 +851,12 @@ int launch_impl(const void* A, int64_t lda, const void* B, int64_t ldb, void* D,
 
   GemmParams p;
   fill_epi(p.epi, ea);
-  p.dynamic = env_int("SCT_GEMM_DYNAMIC", 1);
+  // Measured (2 x B200, cfg3 step): with the static stride the data-parallel step is 46.5 ms against 46.3 ms on one
+  // GPU; drawing items from the counter makes it 48.2 ms (the GPU-scope atomics queue behind the NVLink traffic of the
+  // overlapped all-reduce).  What used to cost 1.8 ms per step under data parallelism was not SM contention but the
+  // MEMBAR.ALL.GPU of the `.release.cluster` hand-offs, which has to drain behind that same traffic.  Static is the
+  // default; SCT_GEMM_DYNAMIC=1 selects the counter.
+  p.dynamic = env_int("SCT_GEMM_DYNAMIC", 0);
   p.sched = next_sched_slot();
   SCT_CHECK(p.sched != nullptr, "work-queue counters unavailable");
   p.M = (int)M;

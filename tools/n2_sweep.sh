@@ -7,10 +7,10 @@ import json
 d=json.loads(open('gpurun_out/r2_n2_$name.json').read().strip().splitlines()[-1]); print('$name', round(d['ms_per_step'],2), d['dp_replicas_in_sync'], d['clocks']['sm_mhz'])
 "
 }
-run v2_b32_bf16 SCT_DP_BUCKET_MB=32
-run v2_b128_bf16 SCT_DP_BUCKET_MB=128
-run v2_b64_fp32 SCT_DP_BUCKET_MB=64 SCT_DP_GRAD_DTYPE=fp32
-python bench.py --steps 8 --warmup 3 --no-roofline --no-cpu-baseline > gpurun_out/r2_n1_ref2.json 2>/dev/null; python -c "
+run v3_dyn_b128 SCT_GEMM_DYNAMIC=1
+run v3_static_b128 SCT_GEMM_DYNAMIC=0
+run v3_dyn_b32 SCT_GEMM_DYNAMIC=1 SCT_DP_BUCKET_MB=32
+python bench.py --steps 8 --warmup 3 --no-roofline --no-cpu-baseline > gpurun_out/r2_n1_ref3.json 2>/dev/null; python -c "
 import json
-d=json.loads(open('gpurun_out/r2_n1_ref2.json').read().strip().splitlines()[-1]); print('n1', d['ms_per_step'], d['clocks'])
+d=json.loads(open('gpurun_out/r2_n1_ref3.json').read().strip().splitlines()[-1]); print('n1', d['ms_per_step'], d['clocks'])
 "
