@@ -9,7 +9,7 @@ cross-entropy (K4b) and the integrated discriminator (K5) — runs in the sm_100
 libsct_b200.so.  There is no CPU path: tensors must live on a B200.
 
 Additive, keyword-only extensions (reference-preserving defaults): `fused_loss`, `return_logits`,
-`compute_vuln_heads`, `greedy`, `max_new_tokens`, `n_lines`, `use_kv_cache`.
+`compute_vuln_heads`, `greedy`, `max_new_tokens`, `n_lines`, `use_kv_cache`, `head_loss_fn`.
 """
 from __future__ import annotations
 
@@ -497,7 +497,7 @@ class SmartContractTransformer(nn.Module):
     def forward(self, input_ids, attention_mask=None, ast_input_ids=None, ast_attention_mask=None,
                 target_ids=None, token_to_line=None, apply_syntax_constraints=True, *, fused_loss=False,
                 return_logits=True, compute_vuln_heads=True, greedy=False, max_new_tokens=None, n_lines=None,
-                use_kv_cache=True):
+                use_kv_cache=True, head_loss_fn=None):
         if not input_ids.is_cuda:
             raise RuntimeError("sct_gan_b200 runs on a B200 only (no CPU fallback): move the batch to cuda")
         B, S = input_ids.shape
@@ -529,13 +529,18 @@ class SmartContractTransformer(nn.Module):
             with torch.cuda.stream(heads_stream), kn_slot(1):
                 contract_logits = self._contract_heads(memory, mem_b)
                 line_logits = self._line_heads(memory, token_to_line, n_lines, mem_b)
+                # the trainer's vulnerability-head losses (dozens of tiny element-wise kernels, forward and backward)
+                # belong to this branch too: computed here they overlap with the decoder in both directions instead of
+                # sitting between the end of forward and the start of backward on the main stream
+                head_losses = head_loss_fn(contract_logits, line_logits) if head_loss_fn is not None else None
             mem.record_stream(heads_stream)
             mem_b.record_stream(heads_stream)
         elif compute_vuln_heads:
             contract_logits = self._contract_heads(memory, mem_b)
             line_logits = self._line_heads(memory, token_to_line, n_lines, mem_b)
+            head_losses = head_loss_fn(contract_logits, line_logits) if head_loss_fn is not None else None
         else:
-            contract_logits = line_logits = None
+            contract_logits = line_logits = head_losses = None
 
         if target_ids is None:
             seq = self._generate(mem_b, B, S, src_kpm, apply_syntax_constraints, greedy, max_new_tokens, use_kv_cache)
@@ -568,6 +573,8 @@ class SmartContractTransformer(nn.Module):
             line_logits.record_stream(main)
         out["contract_vulnerability_logits"] = contract_logits
         out["line_vulnerability_logits"] = line_logits
+        if head_losses is not None:
+            out["head_losses"] = head_losses
         out["encoder_output"] = memory.mean(dim=1)
         out["discriminator_logits"] = self.discriminator_forward(memory, mem_b) if self.use_gan else None
         return out

@@ -505,6 +505,22 @@ class SmartContractTrainer:
             self._w_line.fill_(v)
             self._w_line_host = v
 
+    def head_losses(self, contract_logits, line_logits, batch, n_lines=None):
+        """(contract focal loss, line spatial focal loss, "batch holds a vulnerable line" flag) of train.py:974-997 from
+        the vulnerability-head logits — the part of the loss block that only depends on the heads, so the model can run
+        it on the heads' side stream (`head_loss_fn`)."""
+        cv = contract_level_focal_loss(contract_logits, batch["contract_vulnerabilities"].float())
+        lvl = line_logits
+        vl = batch["vulnerable_lines"]
+        if lvl.shape != vl.shape and lvl.shape[1] == vl.shape[2] and lvl.shape[2] == vl.shape[1]:
+            vl = vl.transpose(1, 2).contiguous()
+        t2l = batch.get("token_to_line")
+        dp = (self.pg if self.pg is not None else dist.group.WORLD) if self.world > 1 else None
+        lv = spatial_aware_focal_loss(lvl.reshape(-1, lvl.shape[-1]), vl.reshape(-1, lvl.shape[-1]).float(),
+                                      t2l.reshape(-1) if t2l is not None else None, self.focal[0], self.focal[1],
+                                      self.focal[2], n_lines, dp)
+        return cv, lv, (vl.sum() > 0).float()
+
     def compute_losses(self, out, batch, syntax_penalty=0.0, n_lines=None):
         dev = out["gen_ce_loss"].device
         if not (dev.type == "cuda" and torch.cuda.is_current_stream_capturing()):
@@ -512,17 +528,10 @@ class SmartContractTrainer:
         gen = out["gen_ce_loss"] + 0.5 * syntax_penalty
         res = {"gen_loss": gen}
         if self.compute_vuln_heads:
-            cv = contract_level_focal_loss(out["contract_vulnerability_logits"], batch["contract_vulnerabilities"].float())
-            lvl = out["line_vulnerability_logits"]
-            vl = batch["vulnerable_lines"]
-            if lvl.shape != vl.shape and lvl.shape[1] == vl.shape[2] and lvl.shape[2] == vl.shape[1]:
-                vl = vl.transpose(1, 2).contiguous()
-            t2l = batch.get("token_to_line")
-            dp = (self.pg if self.pg is not None else dist.group.WORLD) if self.world > 1 else None
-            lv = spatial_aware_focal_loss(lvl.reshape(-1, lvl.shape[-1]), vl.reshape(-1, lvl.shape[-1]).float(),
-                                          t2l.reshape(-1) if t2l is not None else None, self.focal[0], self.focal[1],
-                                          self.focal[2], n_lines, dp)
-            has_line = (vl.sum() > 0).float()
+            hl = out.get("head_losses")
+            if hl is None:
+                hl = self.head_losses(out["contract_vulnerability_logits"], out["line_vulnerability_logits"], batch, n_lines)
+            cv, lv, has_line = hl
         else:
             cv = lv = torch.zeros((), device=dev)
             has_line = torch.zeros((), device=dev)
@@ -581,7 +590,9 @@ class SmartContractTrainer:
         out = model(input_ids=batch["input_ids"], attention_mask=batch["attention_mask"],
                     ast_input_ids=batch["ast_input_ids"], ast_attention_mask=batch["ast_attention_mask"],
                     target_ids=target_ids, token_to_line=batch.get("token_to_line"), fused_loss=True,
-                    return_logits=False, compute_vuln_heads=self.compute_vuln_heads, n_lines=n_lines)
+                    return_logits=False, compute_vuln_heads=self.compute_vuln_heads, n_lines=n_lines,
+                    head_loss_fn=(lambda cl, ll: self.head_losses(cl, ll, batch, n_lines))
+                    if self.compute_vuln_heads else None)
         # The syntax penalty (a constant: train.py:327-330 builds it from .item() values, so it carries no gradient) and
         # the line metrics (logging only) do not gate the backward pass: on the GPU they run on a side stream next to
         # it (~90 tiny integer / sort kernels, 0.6 ms when serialised between forward and backward) and are joined
