@@ -441,6 +441,354 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 // =================================================================================================
+// forward, second generation: the 128-key tile is processed as two 64-key halves so that, inside ONE CTA, the
+// tensor pipe works on one half while the softmax warps work on the other (the first-generation kernel above
+// alternates strictly between "MMA" and "softmax" per CTA and relies on the second resident CTA for overlap; its
+// profile shows the softmax warps parked at barriers a third of the time).
+//
+//   warps 0-7   softmax: thread (r, hf) owns query row r and, in each half, keys [32 hf, 32 hf + 32)
+//   warp 8      lane 0 issues every tcgen05.mma (all products accumulate into one O: they must come from one thread)
+//   warp 9      lane 0 issues every TMA load (taken off the MMA thread: 20 MMAs + 12 bulk copies per tile at >= 54
+//               cycles each made that one thread the critical path)
+//   TMEM        S_a [0, 64)  S_b [64, 128)  O [128, 224);  P_x (packed bf16) overwrites the first 16 columns of
+//               each thread's own 32 score columns, so no thread writes where another still has to read
+//   smem        Q | K_a K_b (one 64-key half tile each) | V_a[2] V_b[2] (double-buffered halves)
+//   per half x of tile j, in tensor-pipe order:  G(j, x) = [ O += P_x(j) V_x(j) ;  S_x(j + 1) = Q K_x(j + 1)^T ]
+//   hand-offs   softmax -> issuer: bar_p[x] (8 warp arrivals: P_x(j) is in TMEM, S_x(j) has been read)
+//               issuer -> softmax: bar_s[x] (tcgen05.commit after G(., x): S_x of the next tile is ready)
+//   No block-wide barrier in the steady state.
+//
+// Running maximum without a per-tile exchange: the two threads of a row publish the maxima of the half tiles they have
+// processed; the reference maximum m_ref used for tile j is decided at the start of tile j from what is guaranteed to be
+// visible to both of them then (their half-a maxima through tile j - 1, half-b maxima through tile j - 2; the mbarrier
+// chain through the issuer orders those writes), raised lazily (only when the seen maximum exceeds it by 2^8) and applied
+// to both halves of the tile.  The probabilities of a tile can therefore exceed 1 — by the amount the scores grew within
+// the last two tiles, harmless in fp32 / bf16 up to 2^100 — and the result O / l does not depend on the reference.
+// When m_ref moves, each thread rescales its half of the O row after the last P V product issued so far has retired
+// (it waits for that commit itself; the next product cannot be issued before this thread's own arrival).
+// Tile 0 establishes the reference exactly (one block-wide exchange per CTA).
+// =================================================================================================
+constexpr int FWD2_THREADS = 320;
+constexpr int HALF_TILE_BYTES = 64 * 192;  // [64 keys x 96] bf16 as three [64 x 32] swizzle-64 blocks of 4096 B
+constexpr int FWD2_SMEM = 1024 + QKV_BYTES + 2 * HALF_TILE_BYTES + 4 * HALF_TILE_BYTES + 12 * 1024;
+
+// one 64-row half tile of K or V by TMA (three 32-column blocks)
+__device__ __forceinline__ void load_half(const CUtensorMap* m64, uint32_t bar, uint32_t dst, int col0, int row0, int b) {
+  mbar_expect_tx(bar, HALF_TILE_BYTES);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) tma_load_3d(m64, bar, dst + c * 4096, col0 + 32 * c, row0, b);
+}
+
+__global__ void __launch_bounds__(FWD2_THREADS, 2)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK64,
+                 const __grid_constant__ CUtensorMap tmV64, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sQ = base;
+  const uint32_t sK = sQ + QKV_BYTES;                 // [2 halves]
+  const uint32_t sV = sK + 2 * HALF_TILE_BYTES;       // [2 halves][2 stages]
+  const uint32_t aux = sV + 4 * HALF_TILE_BYTES;
+  float* mx_s = reinterpret_cast<float*>(gen + (aux - base));  // [2 halves][3 ring][2 hf][128] published half-tile maxima
+  float* l_s = mx_s + 2 * 3 * 2 * 128;                          // [2][128]
+  const uint32_t bars = aux + 2 * 3 * 2 * 128 * 4 + 2 * 128 * 4;
+  const uint32_t bar_q = bars, bar_k = bars + 8 /*[2]*/, bar_v = bars + 24 /*[2 halves][2 stages]*/, bar_s = bars + 56 /*[2]*/,
+                 bar_p = bars + 72 /*[2]*/;
+  const uint32_t tmem_ptr_addr = bars + 96;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen + (tmem_ptr_addr - base));
+  int* ext_slot = reinterpret_cast<int*>(gen + (bars + 104 - base));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nq_tiles = gridDim.x;
+  const int qt = nq_tiles - 1 - blockIdx.x;  // heavy (late) causal tiles first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qt * TILE;
+
+  if (tid == 0) {
+    mbar_init(bar_q, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_k + 8 * i, 1);
+      mbar_init(bar_s + 8 * i, 1);
+      mbar_init(bar_p + 8 * i, 8);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(bar_v + 8 * i, 1);
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_ptr_addr, 256);
+  const int kv_end = kv_extent(p, b, ext_slot);  // contains __syncthreads when a mask is given
+  int nkv = (kv_end + TILE - 1) / TILE;
+  if (p.causal) nkv = min(nkv, qt + 1);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_gen;
+  const uint32_t tO = tmem + 128;
+  (void)lane;
+
+  if (warp == 9) {
+    // ===================== TMA producer (one thread) =====================
+    if (lane == 0 && nkv > 0) {
+      // prologue: Q, both K halves of tile 0, V halves of tiles 0 and 1; then K_x(1) as soon as S_x(0) has retired
+      mbar_expect_tx(bar_q, QKV_BYTES);
+      load_tile(&tmQ, bar_q, sQ, h * DH, q0, b);
+      for (int x = 0; x < 2; ++x) load_half(&tmK64, bar_k + 8 * x, sK + x * HALF_TILE_BYTES, h * DH, 64 * x, b);
+      for (int x = 0; x < 2; ++x) load_half(&tmV64, bar_v + 8 * (2 * x), sV + (2 * x) * HALF_TILE_BYTES, h * DH, 64 * x, b);
+      if (nkv > 1) {
+        for (int x = 0; x < 2; ++x)
+          load_half(&tmV64, bar_v + 8 * (2 * x + 1), sV + (2 * x + 1) * HALF_TILE_BYTES, h * DH, TILE + 64 * x, b);
+        for (int x = 0; x < 2; ++x) {
+          mbar_wait(bar_s + 8 * x, 0);
+          load_half(&tmK64, bar_k + 8 * x, sK + x * HALF_TILE_BYTES, h * DH, TILE + 64 * x, b);
+        }
+      }
+      // buffers freed by G(j, x) (completion #(j + 1) of bar_s[x]): K_x (S_x(j + 1) retired) -> K_x(j + 2);
+      // V_x stage j & 1 (the P V product of tile j retired) -> V_x(j + 2)
+      for (int j = 0; j + 2 < nkv; ++j) {
+        const int st = j & 1;
+        for (int x = 0; x < 2; ++x) {
+          mbar_wait(bar_s + 8 * x, (j + 1) & 1);
+          load_half(&tmK64, bar_k + 8 * x, sK + x * HALF_TILE_BYTES, h * DH, (j + 2) * TILE + 64 * x, b);
+          load_half(&tmV64, bar_v + 8 * (2 * x + st), sV + (2 * x + st) * HALF_TILE_BYTES, h * DH, (j + 2) * TILE + 64 * x, b);
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ===================== MMA issuer (one thread: every product accumulates into the same O, and only the MMAs of
+    //                       ONE thread are ordered among themselves) =====================
+    if (lane == 0 && nkv > 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, false, true);
+      const uint32_t bQ = base_k64(sQ);
+      auto issue_s = [&](int x) {  // S_x = Q K_x^T  (N = 64)
+        const uint32_t bK = umma_desc_lo(sK + x * HALF_TILE_BYTES, 16);
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+          tc_mma_bf16_lh(tmem + 64 * x, step_k64(bQ, k), kHi64, bK + ((((k >> 1) * 4096) + (k & 1) * 32) >> 4), kHi64,
+                         idesc_s, k > 0);
+      };
+      auto issue_pv = [&](int x, int st, bool first) {  // O += P_x V_x  (K = 64 keys in four steps of 16)
+        const uint32_t bV = umma_desc_lo(sV + (2 * x + st) * HALF_TILE_BYTES, 4096);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_bf16_ts(tO, tmem + 64 * x + 32 * (k >> 1) + 8 * (k & 1), bV + ((k * 1024) >> 4), kHi64, idesc_o,
+                         (!first || k > 0) ? 1u : 0u);
+      };
+      mbar_wait(bar_q, 0);
+      for (int x = 0; x < 2; ++x) {
+        mbar_wait(bar_k + 8 * x, 0);
+        tc_fence_after();
+        issue_s(x);
+        tc_commit(bar_s + 8 * x);  // completion #0 of bar_s[x]: S_x(0) ready
+      }
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j & 1;
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+          mbar_wait(bar_p + 8 * x, j & 1);                       // P_x(j) written, S_x(j) consumed
+          mbar_wait(bar_v + 8 * (2 * x + st), (j >> 1) & 1);     // V_x(j) landed
+          tc_fence_after();
+          issue_pv(x, st, j == 0 && x == 0);
+          if (j + 1 < nkv) {
+            mbar_wait(bar_k + 8 * x, (j + 1) & 1);               // K_x(j + 1) landed
+            tc_fence_after();
+            issue_s(x);
+          }
+          tc_commit(bar_s + 8 * x);                              // completion #(j + 1): G(j, x) retired
+        }
+      }
+    }
+  } else {
+    // ===================== softmax warps =====================
+    const int quad = warp & 3, hf = warp >> 2;
+    const int r = quad * 32 + lane;  // local query row
+    const int q = q0 + r;
+    const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t bh = (uint32_t)(b * p.H + h);
+    const DropKey dkey = drop_key(p);
+    const uint8_t* mrow = p.kpm ? p.kpm + (long long)b * p.Lk : nullptr;
+    float m_run = -INFINITY, m_seen = -INFINITY, l_run = 0.f;
+    auto mx_at = [&](int x, int ring, int hh) -> float& { return mx_s[((x * 3 + ring) * 2 + hh) * 128 + r]; };
+    // bit i set <=> key key0 + i takes no part (padding mask, past Lk, above the causal diagonal).  Zero for almost every
+    // block: the 32 mask bytes are OR-ed as two 16-byte words first.
+    auto dead_bits = [&](int j, int x) -> uint32_t {
+      const int kloc = 64 * x + 32 * hf;  // first key of the block inside the tile
+      const int key0 = j * TILE + kloc;
+      uint32_t dead = 0u;
+      if (key0 + 32 > p.Lk) dead = key0 >= p.Lk ? 0xFFFFFFFFu : (0xFFFFFFFFu << (p.Lk - key0));
+      if (mrow != nullptr && key0 < p.Lk) {
+        const int n = min(32, p.Lk - key0);
+        if (n == 32 && (reinterpret_cast<uintptr_t>(mrow + key0) & 15) == 0) {
+          const uint4 a = *reinterpret_cast<const uint4*>(mrow + key0);
+          const uint4 c = *reinterpret_cast<const uint4*>(mrow + key0 + 16);
+          if ((a.x | a.y | a.z | a.w | c.x | c.y | c.z | c.w) != 0u) {
+            const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu) dead |= 1u << i;
+          }
+        } else {
+          for (int i = 0; i < n; ++i)
+            if (mrow[key0 + i] != 0) dead |= 1u << i;
+        }
+      }
+      if (p.causal && j == qt) {  // keys kloc + i > r
+        const int first_dead = r + 1 - kloc;  // index of the first key above the diagonal
+        if (first_dead <= 0) dead = 0xFFFFFFFFu;
+        else if (first_dead < 32) dead |= 0xFFFFFFFFu << first_dead;
+      }
+      return dead;
+    };
+
+    // one half tile: 32 scores of this thread -> P (packed bf16, back into the first 16 of its own score columns);
+    // returns the maximum of the (masked) scaled scores
+    auto half_tile = [&](int j, int x, float m_eff) -> float {
+      const int key0 = j * TILE + 64 * x + 32 * hf;  // first key of this thread's 32
+      const uint32_t t_s = tmem + lane_sel + 64 * x + 32 * hf;
+      const uint32_t dead = dead_bits(j, x);  // index-only work: before the scores are waited for
+      const uint32_t kw = keep_word(p, dkey, bh, (uint32_t)q, (uint32_t)(key0 >> 5));
+      mbar_wait(bar_s + 8 * x, j & 1);
+      tc_fence_after();
+      uint32_t sr[32];
+      tmem_ld32(t_s, sr);
+      tmem_ld_wait();
+      if (dead != 0u) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (dead & (1u << i)) sr[i] = __float_as_uint(-INFINITY);
+      }
+      float mx = __uint_as_float(sr[0]);
+#pragma unroll
+      for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sr[i]));
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_eff, -m_eff);
+      float2 rs2 = make_float2(0.f, 0.f);
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const float2 xx = __ffma2_rn(make_float2(__uint_as_float(sr[i]), __uint_as_float(sr[i + 1])), sc2, nm2);
+        const float2 e = make_float2(exp2f(xx.x), exp2f(xx.y));
+        rs2 = __fadd2_rn(rs2, e);
+        pk[i >> 1] = pack_bf16((kw & (1u << i)) ? e.x : 0.f, (kw & (2u << i)) ? e.y : 0.f);
+      }
+      l_run += rs2.x + rs2.y;
+      {
+        const uint32_t(&p0)[8] = *reinterpret_cast<const uint32_t(*)[8]>(&pk[0]);
+        const uint32_t(&p1)[8] = *reinterpret_cast<const uint32_t(*)[8]>(&pk[8]);
+        tmem_st8(t_s, p0);
+        tmem_st8(t_s + 8, p1);
+      }
+      return mx * p.scale_log2;  // scale > 0
+    };
+    auto arrive_p = [&](int x) {
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p + 8 * x);
+    };
+
+    for (int j = 0; j < nkv; ++j) {
+      const int ring = j % 3;
+      // ---- reference maximum of this tile
+      float m_next = m_run;
+      if (j == 0) {
+        // exact maximum of tile 0: both halves' scores, both threads of the row (one block-wide exchange per CTA)
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int x = 0; x < 2; ++x) {
+          mbar_wait(bar_s + 8 * x, 0);
+          tc_fence_after();
+          uint32_t sr[32];
+          tmem_ld32(tmem + lane_sel + 64 * x + 32 * hf, sr);
+          tmem_ld_wait();
+          const uint32_t dead = dead_bits(0, x);
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (!(dead & (1u << i))) mx = fmaxf(mx, __uint_as_float(sr[i]));
+        }
+        l_s[hf * 128 + r] = mx;
+        named_bar_sync(1, 256);
+        m_seen = fmaxf(mx, l_s[(hf ^ 1) * 128 + r]) * p.scale_log2;
+        named_bar_sync(1, 256);  // l_s is reused at the end
+        m_next = m_seen;
+      } else {
+        // what both threads of the row are guaranteed to see by now: half a of tile j - 1, half b of tile j - 2
+        const int ra = (j - 1) % 3;
+        m_seen = fmaxf(m_seen, fmaxf(mx_at(0, ra, 0), mx_at(0, ra, 1)));
+        if (j >= 2) {
+          const int rb = (j - 2) % 3;
+          m_seen = fmaxf(m_seen, fmaxf(mx_at(1, rb, 0), mx_at(1, rb, 1)));
+        }
+        if (m_run == -INFINITY || m_seen > m_run + 8.0f) m_next = fmaxf(m_run, m_seen);
+      }
+      {
+        // rescale l and this thread's half of the O row (rare after the first tiles).  Warp-uniform: tcgen05.ld / st are
+        // .sync.aligned, so every lane takes part as soon as one row of the warp moves its reference (alpha = 1 for
+        // the others).
+        const bool moved = m_next != m_run && m_run != -INFINITY;
+        if (__any_sync(0xffffffffu, moved)) {
+          const float alpha = moved ? exp2f(m_run - m_next) : 1.0f;
+          l_run *= alpha;
+          mbar_wait(bar_s + 8, j & 1);  // G(j - 1, b) retired: no P V product is in flight or can be issued
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 3; ++c) {
+            uint32_t rr[16];
+            tmem_ld16(tO + lane_sel + 48 * hf + 16 * c, rr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) * alpha);
+            tmem_st16(tO + lane_sel + 48 * hf + 16 * c, rr);
+          }
+          tmem_st_wait();
+        }
+        m_run = m_next;
+      }
+      const float m_eff = (m_run == -INFINITY) ? 0.f : m_run;
+#pragma unroll 1
+      for (int x = 0; x < 2; ++x) {
+        const float mx = half_tile(j, x, m_eff);
+        mx_at(x, ring, hf) = mx;  // published before the arrival below (the issuer's acquire orders it)
+        arrive_p(x);
+      }
+    }
+    // ---- epilogue
+    if (nkv > 0) {
+      mbar_wait(bar_s, nkv & 1);      // G(nkv - 1, a)
+      mbar_wait(bar_s + 8, nkv & 1);  // G(nkv - 1, b)
+      tc_fence_after();
+    }
+    l_s[hf * 128 + r] = l_run;
+    named_bar_sync(1, 256);
+    const float l_tot = l_s[r] + l_s[128 + r];
+    const float inv_l = l_tot > 0.f ? p.inv_keep / l_tot : 0.f;
+    // O / l -> bf16, staged in the (dead) Q tile and stored by one thread with TMA (rows past Lq are clipped)
+#pragma unroll 1
+    for (int c = (hf == 0 ? 0 : 2); c < (hf == 0 ? 2 : 3); ++c) {
+      uint32_t rr[32];
+      if (nkv > 0) {
+        tmem_ld32(tO + lane_sel + c * 32, rr);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rr[i] = 0u;
+      }
+      stage_chunk_sw64(sQ, r, c, rr, inv_l);
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 256);
+    if (tid == 0) {
+      store_tile(&tmO, sQ, h * DH, q0, b);
+      tma_commit_group();
+      tma_wait_group_read0();
+    }
+    if (q < p.Lq && hf == 0 && p.lse2)
+      p.lse2[((long long)b * p.H + h) * p.Lq + q] = l_tot > 0.f ? (m_run + log2f(l_tot)) : INFINITY;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 256);
+}
+
+// =================================================================================================
 // decode step (Lq = 1, inference): one block per (head, batch) streams that head's K and V rows once — the op is a
 // pure read of the KV cache (2 * Lk * 192 B per block), so it is written as a SIMT stream, not as 128-row tensor-core
 // tiles of which one row would be real.  Four lanes share a key row (48 bytes = 24 head dims = three 16-byte loads
@@ -1358,8 +1706,22 @@ int32_t sct_attn_fwd_strided(const void* q, int64_t ldq, const void* k, const vo
   if (int rc = make_qkv_map(&to, o, ldo, B, Lq, H)) return rc;
   if (int rc = make_qkv_map(&tk, k, ldkv, B, Lk, H, kv_batch_stride)) return rc;
   if (int rc = make_qkv_map(&tv, v, ldkv, B, Lk, H, kv_batch_stride)) return rc;
-  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_fwd_kernel), FWD_SMEM)) return rc;
   dim3 grid((unsigned)((Lq + TILE - 1) / TILE), (unsigned)H, (unsigned)B);
+  if (env_int("SCT_ATTN_FWD", 2) == 2 && Lq > 1) {  // two 64-key halves pipelined inside the CTA
+    CUtensorMap tk64, tv64;
+    const uint64_t bs = kv_batch_stride > 0 ? (uint64_t)kv_batch_stride : (uint64_t)Lk * ldkv;
+    if (int rc = make_tmap_3d(&tk64, k, 2, (uint64_t)(H * DH), (uint64_t)Lk, (uint64_t)B, (uint64_t)ldkv * 2, bs * 2, 32, 64,
+                              SWZ_64))
+      return rc;
+    if (int rc = make_tmap_3d(&tv64, v, 2, (uint64_t)(H * DH), (uint64_t)Lk, (uint64_t)B, (uint64_t)ldkv * 2, bs * 2, 32, 64,
+                              SWZ_64))
+      return rc;
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_fwd2_kernel), FWD2_SMEM)) return rc;
+    attn_fwd2_kernel<<<grid, FWD2_THREADS, FWD2_SMEM, (cudaStream_t)stream>>>(tq, tk64, tv64, to, p);
+    SCT_LAUNCH_CHECK();
+    return 0;
+  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_fwd_kernel), FWD_SMEM)) return rc;
   attn_fwd_kernel<<<grid, 256, FWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, to, p);
   SCT_LAUNCH_CHECK();
   return 0;
@@ -1444,7 +1806,7 @@ int32_t sct_attn_bwd_ws(const void* q, int64_t ldq, const void* k, const void* v
     CUtensorMap tdk, tdv;
     if (int rc = make_qkv_map(&tdk, dk, lddkv, B, Lk, H)) return rc;
     if (int rc = make_qkv_map(&tdv, dv, lddkv, B, Lk, H)) return rc;
-    if (env_int("SCT_ATTN_BWD_WARPS", 16) == 16)
+    if (env_int("SCT_ATTN_BWD_WARPS", 8) == 16)  // (measured equal or slower than 8: the arithmetic warps are not the limiter)
       attn_bwd_dkdv_kernel<16><<<grid, bwd_kv_threads(16), BWD3_KV_SMEM, st>>>(tq, tk, tv, tdo, tds_st, tdk, tdv, p);
     else
       attn_bwd_dkdv_kernel<8><<<grid, bwd_kv_threads(8), BWD3_KV_SMEM, st>>>(tq, tk, tv, tdo, tds_st, tdk, tdv, p);

@@ -578,3 +578,41 @@ def test_fused_ffn_autograd_matches_unfused(cuda_dev):
                      l2.bias.grad.clone()])
     for a, b in zip(*outs):
         assert ((a - b).norm() / b.norm()).item() < 1e-2
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_attention_fwd_running_max_rescale(cuda_dev, causal):
+    """Scores that GROW along the key axis (keys scaled by a ramp): every later tile raises the row maximum by far
+    more than the lazy-rescale threshold (2^8), so the forward's reference-maximum update and the rescale of the O
+    accumulator in TMEM run on every tile — including rows of a warp that do not move while others do.  Rows are
+    given different growth rates so the rescale is divergent inside warps."""
+    from sct_gan_b200 import kernels as kn
+
+    B, H, dh, L = 2, 8, 96, 768
+    d = H * dh
+    g = torch.Generator(device="cuda").manual_seed(77)
+    q = torch.randn(B * L, d, device="cuda", generator=g)
+    k = torch.randn(B * L, d, device="cuda", generator=g)
+    v = torch.randn(B * L, d, device="cuda", generator=g)
+    # align k with a fixed direction and ramp its length along the sequence; query rows project on that direction with
+    # row-dependent strength (some negative: their scores shrink instead, so their reference never moves)
+    u = torch.nn.functional.normalize(torch.randn(dh, device="cuda", generator=g), dim=0)
+    ramp = torch.linspace(0.0, 300.0, L, device="cuda").repeat(B)[:, None]
+    k = (k.view(B * L, H, dh) * 0.3 + ramp[:, None, :] * u).reshape(B * L, d)
+    gain = torch.linspace(-1.0, 3.0, L, device="cuda").repeat(B)[:, None]
+    q = (q.view(B * L, H, dh) * 0.3 + gain[:, None, :] * u).reshape(B * L, d)
+    qb, kb, vb = q.to(BF16), k.to(BF16), v.to(BF16)
+    o, lse2 = kn.attn_fwd(qb, kb, vb, B, H, L, L, causal=causal)
+    _no_timeouts()
+
+    def heads(t):
+        return t.float().reshape(B, L, H, dh).permute(0, 2, 1, 3)
+
+    ref = _attn_ref(heads(qb), heads(kb), heads(vb), None, causal, dh ** -0.5)
+    assert rel_l2(o.float().reshape(B, L, H, dh).permute(0, 2, 1, 3), ref) < 1e-2
+    s = torch.einsum("bhqd,bhkd->bhqk", heads(qb), heads(kb)) * dh ** -0.5
+    if causal:
+        s = s.masked_fill(torch.ones(L, L, device="cuda", dtype=torch.bool).triu(1), float("-inf"))
+    lse_ref = torch.logsumexp(s, dim=-1) * math.log2(math.e)
+    assert (lse2 - lse_ref).abs().max().item() < 5e-2 * max(1.0, lse_ref.abs().max().item())
+    assert float((s.max(dim=-1).values * math.log2(math.e)).max()) > 60  # the growth really exceeded the threshold
