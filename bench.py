@@ -564,6 +564,18 @@ def run_decode(args, model, dev, world, rank, local, barrier):
     for _ in range(W):
         gen(batch)
     barrier()
+    if args.trace:
+        from torch.profiler import ProfilerActivity, profile
+
+        CFG["new_tokens"], n_new = 24, 24  # a short call is enough to see the step's kernels
+        gen(batch)
+        gen(batch)
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            gen(batch)
+            torch.cuda.synchronize()
+        prof.export_chrome_trace(args.trace)
+        return
     _lib.Stats.launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
