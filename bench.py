@@ -457,7 +457,7 @@ def main():
             for _ in range(2):
                 trainer.train_step(batch, n_lines=n_lines)
             torch.cuda.synchronize()
-        prof.export_chrome_trace(args.trace)
+        prof.export_chrome_trace(args.trace if world == 1 else f"{args.trace}.rank{rank}")
         return
     if args.torch_profile:
         from torch.profiler import ProfilerActivity, profile

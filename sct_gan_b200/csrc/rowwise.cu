@@ -212,9 +212,12 @@ embed_ln_pe_bwd_kernel(const float* __restrict__ g_f32, const __nv_bfloat16* __r
       msk[j] = make_float4(m[0], m[1], m[2], m[3]);
       xh[j] = make_float4((v.x * scale * m[0] - mean) * rstd, (v.y * scale * m[1] - mean) * rstd,
                           (v.z * scale * m[2] - mean) * rstd, (v.w * scale * m[3] - mean) * rstd);
-      float4 gy;
+      float4 gy = make_float4(0.f, 0.f, 0.f, 0.f);  // either or both incoming gradients (fp32 residual stream, bf16 copy)
       if (g_f32) gy = ld4(g_f32 + (long long)row * D + c);
-      else gy = ldbf4(g_bf16 + (long long)row * D + c);
+      if (g_bf16) {
+        const float4 t = ldbf4(g_bf16 + (long long)row * D + c);
+        gy.x += t.x; gy.y += t.y; gy.z += t.z; gy.w += t.w;
+      }
       const float4 gm = ld4(gamma + c);
       ag[j].x += gy.x * xh[j].x; ag[j].y += gy.y * xh[j].y; ag[j].z += gy.z * xh[j].z; ag[j].w += gy.w * xh[j].w;
       ab[j].x += gy.x; ab[j].y += gy.y; ab[j].z += gy.z; ab[j].w += gy.w;

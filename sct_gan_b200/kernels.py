@@ -75,15 +75,19 @@ def embed_ln_pe_fwd(ids, table, gamma, beta, pe, seq_len, scale, p_drop=0.0, see
 
 
 def embed_ln_pe_bwd(g, ids, table, gamma, stats, dtable, dgamma, dbeta, scale, p_drop=0.0, seed=0,
-                    offset=0, epoch=None):
-    """dtable / dgamma / dbeta (fp32) are accumulated into."""
+                    offset=0, epoch=None, g2=None):
+    """dtable / dgamma / dbeta (fp32) are accumulated into.  `g` and the optional `g2` are the incoming gradients of
+    the fp32 and the bf16 output (one of each dtype at most); the kernel sums them while loading."""
     vocab, d = table.shape
     n_tok = ids.numel()
-    g_f32 = g if g.dtype == F32 else None
-    g_bf16 = g if g.dtype == BF16 else None
-    assert g.is_contiguous() and g.numel() == n_tok * d
+    gs = [t for t in (g, g2) if t is not None]
+    g_f32 = next((t for t in gs if t.dtype == F32), None)
+    g_bf16 = next((t for t in gs if t.dtype == BF16), None)
+    assert len(gs) == (g_f32 is not None) + (g_bf16 is not None), "at most one gradient per dtype"
+    for t in gs:
+        assert t.is_contiguous() and t.numel() == n_tok * d
     # dY + re-gathered fp32 row + fp32 read-modify-write scatter into the table gradient + stats
-    _lib.Stats.annotate(float(n_tok) * (g.element_size() * d + 4 * d + 8 * d + 8 + 8))
+    _lib.Stats.annotate(float(n_tok) * (sum(t.element_size() for t in gs) * d + 4 * d + 8 * d + 8 + 8))
     _lib.call("sct_embed_ln_pe_bwd", _ptr(g_f32), _ptr(g_bf16), _ptr(ids), _ptr(table), _ptr(gamma),
               _ptr(stats), _ptr(dtable), _ptr(dgamma), _ptr(dbeta), n_tok, vocab, d, float(scale),
               float(p_drop), seed, offset, _eptr(epoch), _stream())

@@ -212,7 +212,9 @@ class GradArena:
         if ent is not None:
             return ent, False
         buf = self.zeros(shape, device)
-        self.shared[key] = buf
+        # keep an ALIAS, hand out the original: autograd's AccumulateGrad only adopts a gradient it holds the sole
+        # reference to; a tensor that is also referenced from here would be cloned (a 154 MB copy per table and step)
+        self.shared[key] = buf.detach()
         return buf, True
 
 
@@ -242,17 +244,14 @@ class EmbedLnPe(torch.autograd.Function):
     def backward(ctx, g_f32, g_bf16):
         ids_flat, table, gamma, stats = ctx.saved_tensors
         scale, p_drop, seed, off, ep = ctx.cfg
-        if g_f32 is not None and g_bf16 is not None:
-            g = g_f32 + g_bf16.float()
-        else:
-            g = g_f32 if g_f32 is not None else g_bf16
+        g, g2 = (g_f32, g_bf16) if g_f32 is not None else (g_bf16, None)
         # the table / gamma / beta accumulators are shared by every pass that uses this embedding in the step
         dtable, first = ARENA.zeros_for(table, table.shape, table.device)
         dgamma, _ = ARENA.zeros_for(gamma, gamma.shape, gamma.device)
         dbeta, _ = ARENA.zeros_for(ctx.beta_key, gamma.shape, gamma.device)
         if g is not None:
             kn.embed_ln_pe_bwd(g.contiguous(), ids_flat, table.detach(), gamma.detach(), stats, dtable, dgamma,
-                               dbeta, scale, p_drop, seed, off, ep)
+                               dbeta, scale, p_drop, seed, off, ep, g2=None if g2 is None else g2.contiguous())
         if not first:  # already handed to autograd by the other pass: accumulated in place
             return None, None, None, None, None, None, None, None, None, None
         return None, dtable, dgamma, dbeta, None, None, None, None, None, None

@@ -264,6 +264,49 @@ def test_embed_ln_pe(cuda_dev, B, S):
     touched[ids.view(-1)] = True
     assert torch.equal((dtable.abs().sum(1) != 0) | ~touched, torch.ones_like(touched) & ((table.grad.abs().sum(1) != 0) | ~touched))
     assert dtable[~touched].abs().max().item() == 0.0
+    # both outputs carried a gradient: the kernel sums the fp32 and the bf16 one while loading
+    gy2 = torch.randn(B * S, d, device="cuda", generator=g).to(BF16)
+    dt2 = torch.zeros_like(table)
+    dg2, db2 = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+    kn.embed_ln_pe_bwd(gy, ids.view(-1), table.detach(), gamma.detach(), stats, dt2, dg2, db2, scale, g2=gy2)
+    dt3 = torch.zeros_like(table)
+    dg3, db3 = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+    kn.embed_ln_pe_bwd(gy + gy2.float(), ids.view(-1), table.detach(), gamma.detach(), stats, dt3, dg3, db3, scale)
+    assert rel_l2(dt2, dt3) < 1e-6 and rel_l2(dg2, dg3) < 1e-5 and rel_l2(db2, db3) < 1e-5
+
+
+def test_arena_buffers_are_adopted_by_autograd_without_a_copy(cuda_dev):
+    """A parameter used at two sites of one step (the shared embedding table) accumulates into ONE arena buffer and
+    autograd adopts that buffer as `.grad` (no clone): the gradient lives at the arena address."""
+    from sct_gan_b200 import ops
+
+    V, d, S = 1000, 768, 32
+    table = (torch.randn(V, d, device="cuda") * 0.02).requires_grad_(True)
+    gamma = torch.ones(d, device="cuda", requires_grad=True)
+    beta = torch.zeros(d, device="cuda", requires_grad=True)
+    pe = torch.zeros(S, d, device="cuda")
+    ids = torch.randint(0, V, (2, S), device="cuda")
+
+    def step():
+        table.grad = gamma.grad = beta.grad = None
+        ops.ARENA.begin(table.device)
+        a, _ = ops.embed_ln_pe(ids, table, gamma, beta, pe, S, 1.0)
+        b, _ = ops.embed_ln_pe(ids.flip(1), table, gamma, beta, pe, S, 1.0)
+        (a.sum() + 2 * b.square().sum()).backward()
+        ops.ARENA.end()
+
+    step()  # sizing pass
+    step()
+    lo, hi = ops.ARENA.buf.data_ptr(), ops.ARENA.buf.data_ptr() + ops.ARENA.buf.numel() * 4
+    assert lo <= table.grad.data_ptr() < hi and lo <= gamma.grad.data_ptr() < hi
+    g_arena = table.grad.clone()
+    ops.ARENA.buf = None
+    ops.ARENA.need_last = 0
+    table.grad = gamma.grad = beta.grad = None
+    a, _ = ops.embed_ln_pe(ids, table, gamma, beta, pe, S, 1.0)
+    b, _ = ops.embed_ln_pe(ids.flip(1), table, gamma, beta, pe, S, 1.0)
+    (a.sum() + 2 * b.square().sum()).backward()
+    assert rel_l2(g_arena, table.grad) < 1e-5
 
 
 def test_embed_gather_bit_exact(cuda_dev):
