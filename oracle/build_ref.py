@@ -5,9 +5,10 @@
 The reference is a directory of Python scripts (no setup.py, no native code), so "compiling the reference" means
 `py_compile`: SCT-GAN/model.py (the model), SCT-GAN/train.py (its loss classes: SoliditySyntaxLoss,
 ContractLevelFocalLoss, SpatialAwareFocalLoss) and SCT-GAN/data_augmentation.py (imported by train.py) are compiled
-to `oracle/_ref/*.pyc` — compiled artefacts only, no reference source enters the repository.  `oracle/_ref/` is
+to `oracle/_ref/*.refbin` (pyc bytes under a neutral suffix: `*.pyc` files did not survive the snapshot to the GPU
+box) — compiled artefacts only, no reference source enters the repository.  `oracle/_ref/` is
 git-ignored (it stays out of history) but not gpurun-ignored, so it travels to the GPU box like our own .so, where
-/root/reference does not exist.  `oracle/ref_loader.py` imports the three modules from the .pyc files.
+/root/reference does not exist.  `oracle/ref_loader.py` imports the three modules from those files.
 
 This is test / measurement infrastructure: only tests/, __graft_entry__ and bench.py's CPU legs
 (`cpu_baseline`, `--impl reference`) load it; the product path never does.
@@ -26,7 +27,7 @@ def build(force=False):
         return False
     os.makedirs(OUT, exist_ok=True)
     for name in MODULES:
-        src, dst = os.path.join(REF, name + ".py"), os.path.join(OUT, name + ".pyc")
+        src, dst = os.path.join(REF, name + ".py"), os.path.join(OUT, name + ".refbin")
         if force or not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
             # unchecked pyc: the loader must not look for the (absent) source file's mtime on the GPU box
             py_compile.compile(src, cfile=dst, dfile=f"reference/SCT-GAN/{name}.py", doraise=True,

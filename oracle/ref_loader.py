@@ -1,4 +1,4 @@
-"""Imports the unmodified reference modules from `oracle/_ref/*.pyc` (built by oracle/build_ref.py).
+"""Imports the unmodified reference modules from `oracle/_ref/*.refbin` (built by oracle/build_ref.py).
 
 Test / measurement infrastructure only (tests/, __graft_entry__.smoke(), bench.py's CPU legs)."""
 import contextlib
@@ -13,7 +13,7 @@ _PREFIX = "sct_reference_"
 
 
 def available() -> bool:
-    return all(os.path.exists(os.path.join(_DIR, n + ".pyc")) for n in ("model", "train", "data_augmentation"))
+    return all(os.path.exists(os.path.join(_DIR, n + ".refbin")) for n in ("model", "train", "data_augmentation"))
 
 
 def _load(name):
@@ -22,7 +22,7 @@ def _load(name):
     key = _PREFIX + name
     if key in sys.modules:
         return sys.modules[key]
-    path = os.path.join(_DIR, name + ".pyc")
+    path = os.path.join(_DIR, name + ".refbin")
     loader = importlib.machinery.SourcelessFileLoader(name, path)
     spec = importlib.util.spec_from_loader(name, loader)
     mod = importlib.util.module_from_spec(spec)

@@ -1,6 +1,6 @@
 """One adversarial train step of the UNMODIFIED reference on CPU — the CPU arm of bench.py.
 
-The model is the reference's own `SmartContractTransformer` (oracle/_ref/model.pyc, byte-compiled from
+The model is the reference's own `SmartContractTransformer` (oracle/_ref/model.refbin, byte-compiled from
 /root/reference/SCT-GAN/model.py by oracle/build_ref.py), the losses are the reference's own classes
 (train.py: ContractLevelFocalLoss, SpatialAwareFocalLoss), the optimiser is torch.optim.AdamW with the groups of
 train.py:512-540.  `SmartContractTrainer` itself cannot be constructed (ReduceLROnPlateau(verbose=True) is a
