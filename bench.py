@@ -449,7 +449,7 @@ def main():
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
         emit({"ncu_step": "done", "launches_per_step_through_cabi": _lib.Stats.launches // (W + 1)})
-        return
+        return finish(world, trainer)
     if args.trace:
         from torch.profiler import ProfilerActivity, profile
 
@@ -458,7 +458,7 @@ def main():
                 trainer.train_step(batch, n_lines=n_lines)
             torch.cuda.synchronize()
         prof.export_chrome_trace(args.trace if world == 1 else f"{args.trace}.rank{rank}")
-        return
+        return finish(world, trainer)
     if args.torch_profile:
         from torch.profiler import ProfilerActivity, profile
 
@@ -470,7 +470,7 @@ def main():
         with open(args.torch_profile, "w") as f:
             f.write(f"wall_ms_under_profiler {wall * 1e3:.2f}\n")
             f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=80, max_name_column_width=90))
-        return
+        return finish(world, trainer)
     # ---- value: K steps, inputs resident in HBM, CUDA events, max over ranks
     _lib.Stats.launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -538,7 +538,7 @@ def main():
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu,
             "host_enqueue_ms_per_step": round(cpu_ms_per_step, 2), "dp_replicas_in_sync": in_sync,
         })
-    finish(world)
+    finish(world, trainer)
 
 
 def run_decode(args, model, dev, world, rank, local, barrier):
@@ -637,16 +637,30 @@ def run_decode(args, model, dev, world, rank, local, barrier):
         })
 
 
-def finish(world):
+def finish(world, trainer=None):
+    """Orderly teardown: release the captured graphs (they hold the NCCL kernels), then destroy the process group.
+    A watchdog ends the process if the communicator teardown stalls anyway (the JSON line is already out)."""
+    if trainer is not None:
+        trainer.close()
     if world > 1:
+        import threading
+
         import torch.distributed as dist
 
-        # Tearing the NCCL communicator down while captured graphs still reference its collectives hangs
-        # (seen on 2 GPUs): drain the device, make sure every rank got here, then leave without the destructor.
         torch.cuda.synchronize()
         dist.barrier()
         sys.stdout.flush()
-        os._exit(0)
+
+        def bail():
+            sys.stderr.write("bench.py: process-group teardown stalled; leaving without it\n")
+            sys.stderr.flush()
+            os._exit(0)
+
+        t = threading.Timer(30.0, bail)
+        t.daemon = True
+        t.start()
+        dist.destroy_process_group()
+        t.cancel()
 
 
 if __name__ == "__main__":

@@ -658,6 +658,20 @@ class SmartContractTrainer:
             self.optimizer.step()
         return total_norm, ok
 
+    def close(self):
+        """Releases the captured step graphs (and with them the NCCL collectives recorded inside): call before
+        `torch.distributed.destroy_process_group()` — tearing a communicator down while a live CUDA graph still holds
+        its kernels hangs.  The trainer stays usable; the next step of a signature is captured again."""
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        for ent in self._graphs.values():
+            if isinstance(ent, tuple):
+                ent[0].reset()
+        self._graphs.clear()
+        self.last = None
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+
     def train_step(self, batch, syntax_penalty=0.0, n_lines=None):
         """One optimisation step; returns a dict of DEVICE scalars (`stepped` included) — nothing in here waits
         for the GPU.  `n_lines` = token_to_line.max() + 1 if the caller knows it on the host (the data loader

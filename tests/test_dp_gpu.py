@@ -66,8 +66,21 @@ def _worker(rank, world, port, wire, ret):
     res = tr.train_step(shard, n_lines=int(batch["token_to_line"].max()) + 1)
     torch.cuda.synchronize()
     ret[rank] = _probe(m, res)
+    # lifecycle: capture + replay the step (NCCL collectives inside the graph), then release the graphs and tear the
+    # process group down in order — no os._exit needed
+    for _ in range(2):
+        tr.train_step(shard, n_lines=int(batch["token_to_line"].max()) + 1)
+    torch.cuda.synchronize()
+    import threading
+
+    dog = threading.Timer(90.0, lambda: os._exit(3))  # a stalled teardown fails the test instead of hanging the box
+    dog.daemon = True
+    dog.start()
+    tr.close()
     dist.barrier()
     dist.destroy_process_group()
+    dog.cancel()
+    ret[f"closed{rank}"] = True
 
 
 @pytest.mark.parametrize("wire", ["fp32", "bf16"])
@@ -86,6 +99,7 @@ def test_dp2_step_equals_single_gpu_step(cuda_dev, wire):
     res = tr.train_step({k: v.cuda() for k, v in batch.items()}, n_lines=int(batch["token_to_line"].max()) + 1)
     one = _probe(m, res)
     r0, r1 = ret[0], ret[1]
+    assert ret.get("closed0") and ret.get("closed1")  # captured graphs released, process group destroyed in order
     assert r0["stepped"] and r1["stepped"] and one["stepped"]
     # replicas agree bit for bit after the exchange + deterministic optimiser tail
     assert r0["weights"] == r1["weights"] and r0["grad_norm"] == r1["grad_norm"]

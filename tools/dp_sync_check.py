@@ -63,10 +63,10 @@ def main():
         compare(f"step {step} weights", False)
         if rank == 0:
             print(f"   loss {float(out['total_loss']):.5f} stepped {bool(out['stepped'])}", flush=True)
-    torch.cuda.synchronize()
+    trainer.close()  # captured graphs hold the NCCL kernels: release them before the communicator goes
     dist.barrier()
     sys.stdout.flush()
-    os._exit(0)
+    dist.destroy_process_group()
 
 
 if __name__ == "__main__":
