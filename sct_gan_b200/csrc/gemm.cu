@@ -64,8 +64,6 @@ struct EpiParams {
   uint32_t tmask[kEpiDropBits];     // bit i of the threshold spread over a word
   uint32_t thresh;         // 0 = no dropout
   float inv_keep;
-  int debug;               // SCT_EPI_DBG (timing experiments only): 1 = skip the G store, 2 = skip the activation math,
-                           // 4 = skip the G loads
 };
 
 struct GemmParams {
@@ -549,7 +547,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const int cbk = grp + 2 * k;
-          if (n0 + cbk * 64 < p.N && !(p.epi.debug & 4)) {
+          if (n0 + cbk * 64 < p.N) {
             mbar_expect_tx(bar_g + 8 * cbk, BM * 128);
             tma_load_2d(&tmD2, bar_g + 8 * cbk, sC + cbk * (BM * 128), n0 + cbk * 64, tc.m_blk * BM);
           } else {
@@ -606,7 +604,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const float2 dm = make_float2((kw & (1u << (8 * q + e))) ? p.epi.inv_keep : 0.f,
                                             (kw & (2u << (8 * q + e))) ? p.epi.inv_keep : 0.f);
               float2 val = v, grad = v;
-              if (!(p.epi.debug & 2)) gelu_pair(v, val, grad);
+              gelu_pair(v, val, grad);
               const float2 h2 = __fmul2_rn(val, dm), g2 = __fmul2_rn(grad, dm);
               hv[e] = h2.x;
               hv[e + 1] = h2.y;
@@ -644,7 +642,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (store_thread) {
             if (n0 + cb * 64 < p.N) {
               tma_store_2d(&tmD, sC + (EPI == EPI_MUL ? cb : grp) * (BM * 128), n0 + cb * 64, tc.m_blk * BM);
-              if (EPI == EPI_GELU_FWD && !(p.epi.debug & 1))
+              if (EPI == EPI_GELU_FWD)
                 tma_store_2d(&tmD2, sC + (2 + grp) * (BM * 128), n0 + cb * 64, tc.m_blk * BM);
             }
             tma_commit_group();
@@ -813,7 +811,6 @@ void fill_epi(EpiParams& e, const EpiArgs& a) {
   e.thresh = a.p_drop > 0.f ? (uint32_t)(t > full - 1.0 ? full - 1.0 : t) : 0u;
   for (int i = 0; i < kEpiDropBits; ++i) e.tmask[i] = ((e.thresh >> i) & 1u) ? 0xFFFFFFFFu : 0u;
   e.inv_keep = a.p_drop > 0.f ? (float)(full / (full - (double)e.thresh)) : 1.0f;
-  e.debug = env_int("SCT_EPI_DBG", 0);
 }
 
 template <int BN, bool A_MN, bool B_MN, bool OUT_F32, int CLUSTER, int EPI = EPI_NONE>
