@@ -43,7 +43,11 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kThreads = 256;      // plain kernel: TMA, MMA, 4 epilogue warps, 2 column-sum warps (wgrad)
-constexpr int kThreadsEpi = 320;   // fused-epilogue kernels: TMA, MMA, 8 epilogue warps (two per TMEM lane quadrant)
+// fused-epilogue kernels: TMA, MMA + epilogue warps.  EPI_MUL: 8 (two per TMEM lane quadrant); EPI_GELU_FWD: 16 (four
+// per quadrant: the activation is a long dependent instruction stream per element, and a scheduler with only two such
+// warps issues ~0.3 instructions per clock)
+__host__ __device__ constexpr int epi_warps(int epi) { return epi == 1 /*EPI_GELU_FWD*/ ? 16 : 8; }
+__host__ __device__ constexpr int epi_threads(int epi) { return 64 + 32 * epi_warps(epi); }
 constexpr int kSmemLimit = 232448;  // 227 KB
 
 // Fused epilogues (SURVEY §8b epilogue enum) for the feed-forward block.
@@ -96,7 +100,7 @@ struct Cfg {
   static constexpr int STAGES_RAW = (kSmemLimit - 1024 - C_BYTES - AUX_BYTES - BIAS_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + C_BYTES + AUX_BYTES + BIAS_BYTES;
-  static constexpr int THREADS = EPI != EPI_NONE ? kThreadsEpi : kThreads;
+  static constexpr int THREADS = EPI != EPI_NONE ? epi_threads(EPI) : kThreads;
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages (256 or 512, powers of two)
   static_assert(STAGES >= 2, "pipeline too shallow");
 };
@@ -226,7 +230,7 @@ struct TileQueue {
 __device__ __forceinline__ uint32_t tq_message(uint32_t seq, int t) { return ((seq & 0xFFu) << 24) | (uint32_t)(t + 1); }
 
 template <int BN, bool A_MN, bool B_MN, bool OUT_F32, int CLUSTER, int EPI>
-__global__ void __launch_bounds__(EPI != EPI_NONE ? kThreadsEpi : kThreads, 1)
+__global__ void __launch_bounds__(EPI != EPI_NONE ? epi_threads(EPI) : kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2, const GemmParams p) {
   using C = Cfg<BN, OUT_F32, CLUSTER, EPI>;
@@ -260,7 +264,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int crank = CLUSTER > 1 ? (int)cluster_ctarank() : 0;
   const int n_leaders = CLUSTER > 1 ? (int)(gridDim.x / CLUSTER) : (int)gridDim.x;
   const bool cs_active = A_MN && EPI == EPI_NONE && p.colsum != nullptr;  // column-sum warps take part in the queue
-  constexpr int kEpiWarps = EPI != EPI_NONE ? 8 : 4;
+  constexpr int kEpiWarps = EPI != EPI_NONE ? epi_warps(EPI) : 4;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -286,7 +290,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_tempty + 8 * s, (EPI != EPI_NONE ? 8 : 4) * CLUSTER);  // one arrival per epilogue warp (of both CTAs of a pair)
+      mbar_init(bar_tempty + 8 * s, kEpiWarps * CLUSTER);  // one arrival per epilogue warp (of both CTAs of a pair)
     }
     fence_mbar_init();
   }
@@ -512,9 +516,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ===================== fused epilogue (warps 2..9 = 256 threads) =====================
     // The activation costs ~13 (forward) / ~20 (backward) instructions per element, and a lone warp per scheduler
     // issues a dependent stream at ~0.25 instructions per clock (measured: four epilogue warps needed 23 k cycles for
-    // a 128 x 256 tile against the 5.8 k of a K = 768 mainloop).  Eight warps: two per TMEM lane quadrant; warp group
-    // g = (warp - 2) / 4 takes the 64-column chunks of parity g, with a staging block (pair) and a bulk-store queue of
-    // its own, so one group's arithmetic overlaps the other's store.
+    // a 128 x 256 tile against the 5.8 k of a K = 768 mainloop).  Eight warps: two per TMEM lane quadrant, in two
+    // groups g = (warp - 2) / 4.  EPI_MUL: group g takes the 64-column chunks of parity g (the multiplier chunk sits in
+    // its own staging block).  EPI_GELU_FWD: both groups share a chunk (32 columns each) and chunks alternate between
+    // two staging sets, see below.
     const int ew = warp - 2;       // 0..7
     const int grp = ew >> 2;       // chunk parity
     const int quad = warp & 3;     // TMEM lane quadrant this warp may access
@@ -531,8 +536,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     constexpr int NCHUNK = BN / 64;
     constexpr int UNITS = NCHUNK;  // 32-column units this group handles per tile: NCHUNK / 2 chunks x 2 halves
-    const uint32_t blk_z = sC + grp * (BM * 128) + row * 128;  // H (forward) / dZ (backward) staging block of this group
-    const uint32_t blk_h = blk_z + 2 * (BM * 128);             // G staging block (forward only)
     for (int t = tq.next(true); t >= 0; t = tq.next(true)) {
       TileCoord tc = decode_tile(p, t);
       if (CLUSTER > 1) tc.m_blk = tc.m_blk * CLUSTER + crank;
@@ -558,44 +561,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait(bar_tfull + 8 * as, aph);
       tc_fence_after();
       float* bs_t = bias_s + as * BN;  // per accumulator stage: the other group may still be reading the previous tile's
-      for (int i = etid; i < BN; i += 256) {
+      for (int i = etid; i < BN; i += kEpiWarps * 32) {
         const int n = n0 + i;
         bs_t[i] = (p.bias != nullptr && n < p.N) ? p.bias[n] : 0.f;
       }
-      named_bar_sync(1, 256);
+      named_bar_sync(1, kEpiWarps * 32);
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+      if (EPI == EPI_GELU_FWD) {
+        // All four warps of a TMEM lane quadrant work on the SAME 64-column chunk (warp `sub` = ew / 4 takes columns
+        // [16 sub, 16 sub + 16) of its row); consecutive chunks alternate between two staging sets (H block c & 1, G
+        // block 2 + (c & 1)).  The bulk stores of chunk c - 1 get the whole arithmetic of chunk c to finish reading
+        // their set before chunk c + 1 overwrites it, so the wait in front of the barrier is free.
+        const bool st_thread = ew == 0 && lane == 0;
+        const int sub = ew >> 2;  // 0..3
 #pragma unroll
-      for (int u = 0; u < UNITS; ++u) {
-        const int cb = grp + 2 * (u >> 1), hf = u & 1;
-        const uint32_t blk_u = EPI == EPI_MUL ? sC + cb * (BM * 128) + row * 128 : blk_z;
-        if (hf == 0) {
-          if (EPI == EPI_MUL) {
-            mbar_wait(bar_g + 8 * cb, gph);  // multiplier chunk landed (each thread touches only its own row of it)
-          } else {
-            // this group's previous store must have finished READING the staging block(s)
-            if (store_thread) tma_wait_group_read0();
-            named_bar_sync(2 + grp, 128);
+        for (int c = 0; c < NCHUNK; ++c) {
+          const uint32_t row_h = sC + (c & 1) * (BM * 128) + row * 128;
+          const uint32_t row_g = row_h + 2 * (BM * 128);
+          uint32_t r[16];
+          tmem_ld16(t_addr + c * 64 + sub * 16, r);
+          tmem_ld_wait();
+          if (c == NCHUNK - 1) {  // this warp's last read of the accumulator stage: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (PAIR) mbar_arrive_cluster_relaxed(cluster_map(bar_tempty + 8 * as, 0));
+              else mbar_arrive(bar_tempty + 8 * as);
+            }
           }
-        }
-        uint32_t r[32];
-        tmem_ld32(t_addr + cb * 64 + hf * 32, r);
-        tmem_ld_wait();
-        if (u == UNITS - 1) {  // this warp's last read of the accumulator stage: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (PAIR) mbar_arrive_cluster_relaxed(cluster_map(bar_tempty + 8 * as, 0));
-            else mbar_arrive(bar_tempty + 8 * as);
-          }
-        }
-        const uint32_t kw = EPI == EPI_GELU_FWD
-                                ? epi_keep_word(p.epi, ek0, ek1, (uint32_t)m_glob, (uint32_t)((n0 + cb * 64) >> 5) + hf)
-                                : 0u;
-        const float* bs = bs_t + cb * 64 + hf * 32;
+          // keep bits of this thread's 16 columns: half of the word of the 32-column block they lie in
+          const uint32_t kw = epi_keep_word(p.epi, ek0, ek1, (uint32_t)m_glob, (uint32_t)((n0 + c * 64) >> 5) + (sub >> 1)) >>
+                              (16 * (sub & 1));
+          const float* bs = bs_t + c * 64 + sub * 16;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t sw = ((((hf * 4 + q) ^ (row & 7)) & 7) << 4);
-          if (EPI == EPI_GELU_FWD) {
+          for (int q = 0; q < 2; ++q) {
+            const uint32_t sw = ((((sub * 2 + q) ^ (row & 7)) & 7) << 4);
             float hv[8], gv[8];
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {
@@ -611,13 +611,44 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               gv[e] = g2.x;
               gv[e + 1] = g2.y;
             }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk_z + sw), "r"(pack_bf16(hv[0], hv[1])),
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_h + sw), "r"(pack_bf16(hv[0], hv[1])),
                          "r"(pack_bf16(hv[2], hv[3])), "r"(pack_bf16(hv[4], hv[5])), "r"(pack_bf16(hv[6], hv[7]))
                          : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk_h + sw), "r"(pack_bf16(gv[0], gv[1])),
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_g + sw), "r"(pack_bf16(gv[0], gv[1])),
                          "r"(pack_bf16(gv[2], gv[3])), "r"(pack_bf16(gv[4], gv[5])), "r"(pack_bf16(gv[6], gv[7]))
                          : "memory");
-          } else {
+          }
+          fence_proxy_async_smem();
+          if (st_thread) tma_wait_group_read0();  // chunk c - 1's stores (the OTHER set) have finished reading
+          named_bar_sync(2, kEpiWarps * 32);
+          if (st_thread) {
+            if (n0 + c * 64 < p.N) {
+              tma_store_2d(&tmD, sC + (c & 1) * (BM * 128), n0 + c * 64, tc.m_blk * BM);
+              tma_store_2d(&tmD2, sC + (2 + (c & 1)) * (BM * 128), n0 + c * 64, tc.m_blk * BM);
+            }
+            tma_commit_group();
+          }
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < UNITS; ++u) {
+          const int cb = grp + 2 * (u >> 1), hf = u & 1;
+          const uint32_t blk_u = sC + cb * (BM * 128) + row * 128;
+          if (hf == 0) mbar_wait(bar_g + 8 * cb, gph);  // multiplier chunk landed (a thread touches only its own row of it)
+          uint32_t r[32];
+          tmem_ld32(t_addr + cb * 64 + hf * 32, r);
+          tmem_ld_wait();
+          if (u == UNITS - 1) {  // this warp's last read of the accumulator stage: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (PAIR) mbar_arrive_cluster_relaxed(cluster_map(bar_tempty + 8 * as, 0));
+              else mbar_arrive(bar_tempty + 8 * as);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t sw = ((((hf * 4 + q) ^ (row & 7)) & 7) << 4);
             uint32_t zw[4];
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                          : "=r"(zw[0]), "=r"(zw[1]), "=r"(zw[2]), "=r"(zw[3])
@@ -635,17 +666,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                          "r"(o[3])
                          : "memory");
           }
-        }
-        if (hf == 1) {
-          fence_proxy_async_smem();
-          named_bar_sync(2 + grp, 128);
-          if (store_thread) {
-            if (n0 + cb * 64 < p.N) {
-              tma_store_2d(&tmD, sC + (EPI == EPI_MUL ? cb : grp) * (BM * 128), n0 + cb * 64, tc.m_blk * BM);
-              if (EPI == EPI_GELU_FWD)
-                tma_store_2d(&tmD2, sC + (2 + grp) * (BM * 128), n0 + cb * 64, tc.m_blk * BM);
+          if (hf == 1) {
+            fence_proxy_async_smem();
+            named_bar_sync(2 + grp, 128);
+            if (store_thread) {
+              if (n0 + cb * 64 < p.N) tma_store_2d(&tmD, sC + cb * (BM * 128), n0 + cb * 64, tc.m_blk * BM);
+              tma_commit_group();
             }
-            tma_commit_group();
           }
         }
       }
