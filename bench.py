@@ -111,9 +111,10 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.skip = [], None, index, 0
 
-    def __enter__(self):
+    def start(self):
+        """Launch nvidia-smi (it needs a second or more to come up on an 8-GPU box: call before the warm-up steps)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -122,6 +123,16 @@ class ClockSampler:
             self.t.start()
         except Exception:
             self.proc = None
+        return self
+
+    def ready(self):
+        return bool(self.rows) or self.proc is None or self.proc.poll() is not None
+
+    def __enter__(self):
+        """Start of the timed region: samples from before it are not used."""
+        if self.proc is None and not self.rows:
+            self.start()
+        self.skip = len(self.rows)
         return self
 
     def _read(self):
@@ -137,10 +148,11 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        rows = self.rows[self.skip:] or self.rows  # samples taken inside the region (all of them if it was too short)
+        sm = [float(r[0]) for r in rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -440,8 +452,15 @@ def main():
     n_lines = (S - 1) // CFG["lines_per"] + 1  # = token_to_line.max() + 1, known on the host by construction
     batch = synthetic_batch(B, S, P, model.vocab_size, 1234 + rank, CFG["lines_per"], device=dev)
 
+    clk = ClockSampler(local)
+    if not (args.ncu_step or args.trace or args.torch_profile):
+        clk.start()
     for _ in range(W):
         trainer.train_step(batch, n_lines=n_lines)
+    t_wait = time.perf_counter()
+    while not clk.ready() and time.perf_counter() - t_wait < 10.0:  # keep the GPU under load until nvidia-smi reports
+        trainer.train_step(batch, n_lines=n_lines)
+        torch.cuda.synchronize()
     barrier()
     if args.ncu_step:
         torch.cuda.cudart().cudaProfilerStart()
@@ -474,7 +493,7 @@ def main():
     # ---- value: K steps, inputs resident in HBM, CUDA events, max over ranks
     _lib.Stats.launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
+    with clk:
         barrier()
         e0.record()
         t_cpu = time.perf_counter()
