@@ -49,6 +49,7 @@ SIGNATURES = {
                         _i64, _i64, _i64, _i32, _f, _f, _u64, _u64, _p, _p, _i64, _p],
     "sct_attn_bwd_workspace_bytes": [_i64, _i64, _i64, _i64],
     "sct_ce_rows": [_p, _p, _p, _p, _i64, _i64, _i64, _f, _i32, _p],
+    "sct_sample_rows": [_p, _i64, _i64, _i64, _f, _i32, _f, _i32, _p, _u64, _u64, _p, _p, _p],
     "sct_small_linear_fwd": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p],
     "sct_small_linear_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p],
     "sct_gan_loss_fwd": [_p, _i64, _p, _p, _p],

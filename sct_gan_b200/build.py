@@ -18,7 +18,7 @@ BUILD_DIR = CSRC / "build"
 LIB_PATH = PKG_DIR / "libsct_b200.so"
 INCLUDE = PKG_DIR.parent / "include"
 
-SOURCES = ["api.cu", "gemm.cu", "attn.cu", "rowwise.cu", "loss.cu", "optim.cu"]
+SOURCES = ["api.cu", "gemm.cu", "attn.cu", "rowwise.cu", "loss.cu", "optim.cu", "sample.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

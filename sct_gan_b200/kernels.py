@@ -408,6 +408,24 @@ def ce_rows(logits, targets, V, grad_scale=1.0, write_grad=True):
     return row_loss, row_lse
 
 
+def sample_rows(logits, V, prev_tokens=None, temperature=0.7, top_k=50, top_p=0.95, greedy=False, seed=0, offset=0,
+                epoch=None, out=None):
+    """Next token per row of bf16 logits [rows, ld >= V]: temperature, syntax tweak (prev_tokens: int64 [rows] or None),
+    top-k, top-p, multinomial — or argmax when greedy — in one launch (model.py:892-918).  Returns int64 [rows, 1]."""
+    logits, ld = _rows2d(logits, BF16, "logits")
+    rows = logits.shape[0]
+    if prev_tokens is not None:
+        _chk(prev_tokens, torch.int64, "prev_tokens")
+        assert prev_tokens.numel() == rows
+    if out is None:
+        out = torch.empty((rows, 1), dtype=torch.int64, device=logits.device)
+    assert out.dtype == torch.int64 and out.is_contiguous() and out.numel() == rows
+    _lib.Stats.annotate(float(rows) * V * 2)  # the row is read once
+    _lib.call("sct_sample_rows", _ptr(logits), ld, rows, V, float(temperature), int(top_k), float(top_p), int(bool(greedy)),
+              _ptr(prev_tokens, 8), int(seed), int(offset), _eptr(epoch), _ptr(out, 8), _stream())
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- K5
 def small_linear_fwd(x, w, bias, out_bf16=False):
     M, K = x.shape

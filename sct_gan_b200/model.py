@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import kernels as kn
 from . import ops
 from .kernels import use_ws_slot as kn_slot
 from .ops import BF16, F32
@@ -589,20 +590,35 @@ class SmartContractTransformer(nn.Module):
             logits[:, 59] = torch.where(hit, logits[:, 59] * 2.0, logits[:, 59])
         return logits
 
+    def _sample_rng(self, dev):
+        """Draw counter of the sampling kernel on `dev` (a device int64 the kernel reads at run time, so a captured
+        decode step draws new numbers on every replay).  It restarts from a hash of torch's seed whenever
+        `torch.manual_seed` has been called since the last look — generation is reproducible under a fixed seed."""
+        state = self.__dict__.setdefault("_sample_state", {})
+        st = state.get(dev)
+        if st is None:
+            st = state[dev] = {"ctr": torch.zeros(1, dtype=torch.long, device=dev), "seed": None}
+        if not torch.cuda.is_current_stream_capturing() and st["seed"] != torch.initial_seed():
+            st["seed"] = torch.initial_seed()
+            st["ctr"].fill_((st["seed"] * 0x9E3779B97F4A7C15 + 0x632BE59BD9B4E019) & ((1 << 62) - 1))
+        return st
+
     def _sample(self, logits, tgt, apply_syntax_constraints, greedy):
-        """model.py:892-918: temperature 0.7, syntax tweak, top-k 50, top-p 0.95, multinomial (or argmax)."""
-        logits = logits.float() / 0.7
-        if apply_syntax_constraints:
-            logits = self._apply_syntax_constraints(logits, tgt)
+        """model.py:892-918: temperature 0.7, syntax tweak, top-k 50, top-p 0.95, multinomial (or argmax) — one kernel
+        over the bf16 logits rows (csrc/sample.cu, `sct_sample_rows`).  Returns int64 [rows, 1]."""
+        V = logits.shape[-1]
+        if logits.dtype != BF16 or logits.stride(-1) != 1 or logits.stride(0) % 8 or logits.data_ptr() % 16:
+            buf = torch.empty((logits.shape[0], (V + 7) // 8 * 8), dtype=BF16, device=logits.device)[:, :V]
+            buf.copy_(logits)
+            logits = buf
+        prev = tgt[:, -1].contiguous() if apply_syntax_constraints else None
         if greedy:
-            return logits.argmax(dim=-1, keepdim=True)
-        topv, topi = torch.topk(logits, 50, dim=-1)
-        probs = torch.softmax(topv, dim=-1)
-        remove = torch.cumsum(probs, dim=-1) > 0.95
-        remove[:, 1:] = remove[:, :-1].clone()
-        remove[:, 0] = False
-        probs = torch.softmax(topv.masked_fill(remove, float("-inf")), dim=-1)
-        return topi.gather(1, torch.multinomial(probs, 1))
+            return kn.sample_rows(logits, V, prev, greedy=True)
+        st = self._sample_rng(logits.device)
+        nxt = kn.sample_rows(logits, V, prev, temperature=0.7, top_k=50, top_p=0.95, greedy=False,
+                             seed=st["seed"] & ((1 << 63) - 1), offset=0, epoch=st["ctr"])
+        st["ctr"].add_(1)
+        return nxt
 
     @staticmethod
     def _stop_update(stop_at, nxt, pos):
@@ -662,6 +678,8 @@ class SmartContractTransformer(nn.Module):
         if early_stop:
             st["stop_at"].fill_(t_max + 1)
         self._shadow.begin_step(refresh=False)
+        if not greedy:
+            self._sample_rng(dev)  # a torch.manual_seed since the last call restarts the draw counter (outside the graph)
         for li, l in enumerate(layers):
             ca = l.multihead_attn
             st["mem_kv"][li].copy_(self._lin_rows(mem_b, ca.in_proj_weight, ca.in_proj_bias, d, 3 * d))

@@ -659,3 +659,68 @@ def test_attention_fwd_running_max_rescale(cuda_dev, causal):
     lse_ref = torch.logsumexp(s, dim=-1) * math.log2(math.e)
     assert (lse2 - lse_ref).abs().max().item() < 5e-2 * max(1.0, lse_ref.abs().max().item())
     assert float((s.max(dim=-1).values * math.log2(math.e)).max()) > 60  # the growth really exceeded the threshold
+
+
+# ------------------------------------------------------------------------------------ sampling tail (§8 f4)
+def _kept_set(row_f32, tweak):
+    """Token ids the reference rule (model.py:892-918) can emit for one row, ties to the lowest index."""
+    z = row_f32.double().clone()
+    z /= 0.7
+    if tweak:
+        z[59] *= 2.0
+    srt = torch.sort(z, descending=True, stable=True)
+    k = min(50, z.numel())
+    topv, topi = srt.values[:k], srt.indices[:k]
+    pr = torch.softmax(topv, dim=-1)
+    remove = torch.cumsum(pr, dim=-1) > 0.95
+    remove[1:] = remove[:-1].clone()
+    remove[0] = False
+    return set(topi[~remove].tolist()), int(topi[0])
+
+
+@pytest.mark.parametrize("V", [50265, 40, 4096])
+def test_sample_rows_kernel(cuda_dev, V):
+    from sct_gan_b200 import kernels as kn
+
+    B = 24
+    g = torch.Generator().manual_seed(V)
+    ld = (V + 7) // 8 * 8
+    rows = (torch.randn(B, V, generator=g) * 2.0).bfloat16()
+    if V >= 64:
+        rows[3] = 0.5                  # a constant row: 50 survivors are ids 0..49 (ties -> lowest index), argmax = 0
+    rows[4, 7], rows[4, V - 1] = 30.0, 30.0   # the maximum appears twice: argmax = 7
+    if V > 59:
+        rows[5] = 0.0
+        rows[5, 59], rows[5, 10] = 3.0, 4.0   # after the x2 tweak id 59 (6.0) beats id 10 (4.0)
+    buf = torch.full((B, ld), float("inf"), dtype=BF16, device="cuda")  # pitch columns hold garbage larger than any logit
+    buf[:, :V] = rows.cuda()
+    logits = buf[:, :V]
+    prev = torch.full((B,), 7, dtype=torch.long, device="cuda")
+    prev[5], prev[6] = 2001, 2002
+    # greedy = lowest index among the maxima of the (tweaked) row
+    got = kn.sample_rows(logits, V, prev, greedy=True).view(-1).cpu()
+    for b in range(B):
+        tweak = V > 59 and int(prev[b]) in (2000, 2001, 2002)
+        assert int(got[b]) == _kept_set(rows[b].float(), tweak)[1], b
+    assert torch.equal(kn.sample_rows(logits, V, None, greedy=True).view(-1).cpu()[:5], got[:5])
+    # sampling: every draw lies inside the reference's nucleus; the counter changes the draw, the same counter repeats it
+    ep = torch.zeros(1, dtype=torch.long, device="cuda")
+    seen = [set() for _ in range(B)]
+    first = None
+    for it in range(60):
+        ep.fill_(it)
+        nxt = kn.sample_rows(logits, V, prev, 0.7, 50, 0.95, False, seed=11, offset=3, epoch=ep).view(-1).cpu()
+        first = nxt if first is None else first
+        for b in range(B):
+            seen[b].add(int(nxt[b]))
+    for b in range(B):
+        tweak = V > 59 and int(prev[b]) in (2000, 2001, 2002)
+        kept, _ = _kept_set(rows[b].float(), tweak)
+        assert seen[b] <= kept, (b, sorted(seen[b] - kept))
+    if V >= 64:
+        assert len(seen[3]) > 10 and seen[3] <= set(range(48))  # the constant row samples among its 48 kept ids
+    ep.fill_(0)
+    again = kn.sample_rows(logits, V, prev, 0.7, 50, 0.95, False, seed=11, offset=3, epoch=ep).view(-1).cpu()
+    assert torch.equal(again, first)
+    other = kn.sample_rows(logits, V, prev, 0.7, 50, 0.95, False, seed=12, offset=3, epoch=ep).view(-1).cpu()
+    assert not torch.equal(other, first)

@@ -110,10 +110,13 @@ def test_sampling_tail_distribution_matches_reference_rule(cuda_dev):
     g = torch.Generator().manual_seed(9)
     V, N = 5000, 40000
     for trial, spread in enumerate((1.0, 3.0, 0.2)):
-        row = torch.randn(V, generator=g) * spread
+        # bf16-representable logits (the sampler reads the vocab GEMM's bf16 rows); such values tie, and ties resolve
+        # to the lowest index: a stable descending sort states the same rule
+        row = (torch.randn(V, generator=g) * spread).bfloat16().float()
         # the reference rule, written out on the CPU in fp64
         z = row.double() / 0.7
-        topv, topi = torch.topk(z, 50)
+        srt = torch.sort(z, descending=True, stable=True)
+        topv, topi = srt.values[:50], srt.indices[:50]
         pr = torch.softmax(topv, dim=-1)
         remove = torch.cumsum(pr, dim=-1) > 0.95
         remove[1:] = remove[:-1].clone()
@@ -121,7 +124,7 @@ def test_sampling_tail_distribution_matches_reference_rule(cuda_dev):
         pr = torch.softmax(topv.masked_fill(remove, float("-inf")), dim=-1)
         expected = torch.zeros(V, dtype=torch.float64)
         expected[topi] = pr
-        logits = row.cuda()[None, :].expand(N, V).contiguous()
+        logits = row.cuda().to(torch.bfloat16)[None, :].expand(N, V).contiguous()
         prev = torch.ones((N, 1), dtype=torch.long, device="cuda")
         torch.manual_seed(100 + trial)
         draws = m._sample(logits, prev, apply_syntax_constraints=False, greedy=False).view(-1).cpu()
