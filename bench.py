@@ -263,10 +263,26 @@ def run_reference_arm(args):
         "impl": "reference", "metric": metric_name(), "value": v, "unit": cpu["unit"], "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(), "sample": cpu["sample"]},
+        "config": config_record(int(os.environ.get("WORLD_SIZE", "1")), args),
         "cpu_baseline": cpu,
         "e2e": {"value": v, "unit": cpu["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
+
+
+def config_record(world, args):
+    """The `config` object of the result line: the same for both arms (the reference arm times a bounded sample of this
+    workload on the host, described in its `cpu_baseline.sample`)."""
+    B, S, P = CFG["B"], CFG["S"], CFG["P"]
+    if CFG["mode"] == "decode":
+        return {"workload": workload_name(), "global_batch": world * B, "seq_len": S, "new_tokens": CFG["new_tokens"],
+                "parallelism": f"dp{world} (independent replicas)", "cuda_graph": True,
+                "l2": "K/V caches + weights per step (> 2 GB) exceed the 126 MB L2"}
+    full = CFG["mode"] == "full"
+    heads = full and not args.no_vuln_heads
+    return {"workload": workload_name(), "global_batch": world * B, "seq_len": S, "path_len": P,
+            "parallelism": f"dp{world}", "vuln_heads": heads, "syntax_penalty": full, "line_metrics": heads,
+            "cuda_graph": not args.no_graph,
+            "l2": "no explicit flush: each step streams several GB of activations/weights (>> 126 MB L2)"}
 
 
 def metric_name():
@@ -549,10 +565,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(), "global_batch": world * B, "seq_len": S, "path_len": P,
-                       "parallelism": f"dp{world}", "vuln_heads": heads, "syntax_penalty": rules is not None,
-                       "line_metrics": heads, "cuda_graph": not args.no_graph,
-                       "l2": "no explicit flush: each step streams several GB of activations/weights (>> 126 MB L2)"},
+            "config": config_record(world, args),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu,
             "host_enqueue_ms_per_step": round(cpu_ms_per_step, 2), "dp_replicas_in_sync": in_sync,
@@ -646,9 +659,7 @@ def run_decode(args, model, dev, world, rank, local, barrier):
             "metric": metric_name(), "value": value, "unit": "new tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(), "global_batch": world * B, "seq_len": S, "new_tokens": n_new,
-                       "parallelism": f"dp{world} (independent replicas)", "cuda_graph": True,
-                       "l2": "K/V caches + weights per step (> 2 GB) exceed the 126 MB L2"},
+            "config": config_record(world, args),
             "e2e": {"value": e2e_value, "unit": "new tokens/s",
                     "h2d_bytes_per_step": sum(host[k].numel() * host[k].element_size() for k in keys),
                     "d2h_bytes_per_step": d2h},

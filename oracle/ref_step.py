@@ -105,9 +105,9 @@ class ReferenceStep:
         total_norm = total_norm ** 0.5
         if torch.isnan(total) or torch.isinf(total) or total_norm > 1000:
             self.optimizer.zero_grad()
-            return float(total), total_norm, False
+            return float(total.detach()), total_norm, False
         self.optimizer.step()
-        return float(total), total_norm, True
+        return float(total.detach()), total_norm, True
 
 
 def synthetic_batch(B, S, P, vocab, seed, lines_per=12):
