@@ -472,6 +472,97 @@ add_dropout_ln_bwd_kernel(const float* __restrict__ g_xout, const __nv_bfloat16*
   }
 }
 
+// The common case of the backward (both the residual gradient and the LayerNorm gradient arrive, d = 768), software-
+// pipelined by one row: the kernel above runs one block of 8 warps per SM (156 registers), and a warp has loads in
+// flight only while it is not in its reduction / store phase.  Registers are free up to 255 at that occupancy, so the
+// NEXT row's three inputs are fetched into a second register set before the current row's reductions.
+template <int NV>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 1)
+add_dropout_ln_bwd_pf_kernel(const float* __restrict__ g_xout, const __nv_bfloat16* __restrict__ g_yln,
+                             const __nv_bfloat16* __restrict__ g_ycast, const float* __restrict__ xprime,
+                             const float* __restrict__ stats, const float* __restrict__ gamma, float alpha,
+                             float* __restrict__ g_x, __nv_bfloat16* __restrict__ g_branch,
+                             float* __restrict__ dgamma, float* __restrict__ dbeta, int n_rows, DropCfg dc_in) {
+  const DropCfg dc = resolve_epoch(dc_in);
+  constexpr int D = NV * 128;
+  constexpr float inv_d = 1.0f / D;
+  __shared__ float red[kWarpsPerBlock * D];
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int warps_total = gridDim.x * kWarpsPerBlock;
+  float4 ag[NV], ab[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) ag[j] = ab[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 n_gx[NV], n_xp[NV];
+  uint2 n_gy[NV];
+  float n_mean = 0.f, n_rstd = 0.f;
+  auto fetch = [&](int row) {
+    const long long base = (long long)row * D;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = (j * 32 + lane) * 4;
+      n_gx[j] = ld4(g_xout + base + c);
+      n_xp[j] = ld4(xprime + base + c);
+      n_gy[j] = *reinterpret_cast<const uint2*>(g_yln + base + c);
+    }
+    n_mean = stats[2 * row];
+    n_rstd = stats[2 * row + 1];
+  };
+  int row = warp_global;
+  if (row < n_rows) fetch(row);
+  for (; row < n_rows; row += warps_total) {
+    const long long base = (long long)row * D;
+    float4 acc[NV], xh[NV], g[NV];
+    const float mean = n_mean, rstd = n_rstd;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = (j * 32 + lane) * 4;
+      acc[j] = n_gx[j];
+      const float4 xv = n_xp[j];
+      xh[j] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+      const float2 ga = unpack_bf16(n_gy[j].x), gb = unpack_bf16(n_gy[j].y);
+      const float4 gy = make_float4(ga.x, ga.y, gb.x, gb.y);
+      const float4 gm = ld4(gamma + c);
+      ag[j].x += gy.x * xh[j].x; ag[j].y += gy.y * xh[j].y; ag[j].z += gy.z * xh[j].z; ag[j].w += gy.w * xh[j].w;
+      ab[j].x += gy.x; ab[j].y += gy.y; ab[j].z += gy.z; ab[j].w += gy.w;
+      g[j] = make_float4(gy.x * gm.x, gy.y * gm.y, gy.z * gm.z, gy.w * gm.w);
+      s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
+      s2 += (g[j].x * xh[j].x + g[j].y * xh[j].y) + (g[j].z * xh[j].z + g[j].w * xh[j].w);
+    }
+    if (row + warps_total < n_rows) fetch(row + warps_total);  // in flight during the reductions and stores below
+    if (g_ycast) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float4 t = ldbf4(g_ycast + base + (j * 32 + lane) * 4);
+        acc[j].x += t.x; acc[j].y += t.y; acc[j].z += t.z; acc[j].w += t.w;
+      }
+    }
+    s1 = warp_sum(s1) * inv_d;
+    s2 = warp_sum(s2) * inv_d;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = (j * 32 + lane) * 4;
+      acc[j].x += rstd * (g[j].x - s1 - xh[j].x * s2);
+      acc[j].y += rstd * (g[j].y - s1 - xh[j].y * s2);
+      acc[j].z += rstd * (g[j].z - s1 - xh[j].z * s2);
+      acc[j].w += rstd * (g[j].w - s1 - xh[j].w * s2);
+      if (g_x) st4(g_x + base + c, acc[j]);
+      if (g_branch) {
+        float m[4];
+        drop4(dc, (uint64_t)base + c, m);
+        stbf4(g_branch + base + c,
+              make_float4(alpha * m[0] * acc[j].x, alpha * m[1] * acc[j].y, alpha * m[2] * acc[j].z,
+                          alpha * m[3] * acc[j].w));
+      }
+    }
+  }
+  if (dgamma) {
+    flush_col_partials<NV>(ag, dgamma, red);
+    flush_col_partials<NV>(ab, dbeta, red);
+  }
+}
+
 // =================================================================================================
 // ln_act:  h = dropout(gelu(LN(z)))  on bf16 rows  (feature_fusion / disc_* Sequential blocks)
 // =================================================================================================
@@ -819,6 +910,16 @@ int32_t sct_add_dropout_ln_bwd(const float* g_xout, const void* g_yln, const voi
   const DropCfg dc = make_drop(p_drop, seed, offset, epoch);
   const int blocks = persistent_blocks((int)n_rows);
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_yln && g_xout && d == 768 && n_rows >= 4096 && env_int("SCT_LN_BWD_PREFETCH", 1)) {  // =0: plain kernel (A/B)
+    constexpr int NV = 6;
+    int pb = num_sms();  // one block of 8 warps per SM is what the register file holds
+    if (pb > blocks) pb = blocks;
+    add_dropout_ln_bwd_pf_kernel<NV><<<pb, kWarpsPerBlock * 32, 0, st>>>(
+        g_xout, (const __nv_bfloat16*)g_yln, (const __nv_bfloat16*)g_ycast, xprime, stats, gamma, alpha, g_x,
+        (__nv_bfloat16*)g_branch, dgamma, dbeta, (int)n_rows, dc);
+    SCT_LAUNCH_CHECK();
+    return 0;
+  }
   DISPATCH_NV(d, (add_dropout_ln_bwd_kernel<NV><<<blocks, kWarpsPerBlock * 32, 0, st>>>(
                      g_xout, (const __nv_bfloat16*)g_yln, (const __nv_bfloat16*)g_ycast, xprime, stats,
                      gamma, alpha, g_x, (__nv_bfloat16*)g_branch, dgamma, dbeta, (int)n_rows, dc)));

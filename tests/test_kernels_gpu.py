@@ -351,6 +351,21 @@ def test_add_dropout_ln(cuda_dev, d, n):
     assert rel_l2(gb, brf.grad) < 4e-3
     assert rel_l2(dgamma, gamma.grad) < 1e-3
     assert rel_l2(dbeta, beta.grad) < 1e-3
+    if n >= 4096 and d == 768:
+        # the software-pipelined backward (>= 4096 rows) against the plain kernel (fewer rows) on the same leading rows,
+        # with all three incoming gradients and dropout: identical per-row arithmetic, so identical bits
+        g_c = torch.randn(n, d, device="cuda", generator=g).to(BF16)
+        m = 4000
+        dg1, db1 = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+        gx1, gb1 = kn.add_dropout_ln_bwd(g_x, g_y, g_c, x_out, stats, gamma.detach(), 0.1, dg1, db1, p_drop=0.3, seed=3, offset=4)
+        dg2, db2 = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+        gx2, gb2 = kn.add_dropout_ln_bwd(g_x[:m], g_y[:m], g_c[:m], x_out[:m], stats[:m], gamma.detach(), 0.1, dg2, db2,
+                                         p_drop=0.3, seed=3, offset=4)
+        assert torch.equal(gx1[:m], gx2) and torch.equal(gb1[:m], gb2)
+        dg3, db3 = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+        kn.add_dropout_ln_bwd(g_x[m:], g_y[m:], g_c[m:], x_out[m:], stats[m:], gamma.detach(), 0.1, dg3, db3, p_drop=0.3,
+                              seed=3, offset=4)
+        assert rel_l2(dg1, dg2 + dg3) < 1e-5 and rel_l2(db1, db2 + db3) < 1e-5
 
 
 @pytest.mark.parametrize("n", [2048, 4500])  # plain and bulk-copy-staged kernels generate the same masks
