@@ -133,7 +133,7 @@ ce_rows_kernel(__nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ t
 // exp2(x_i - max) summed in fp32 and parked back in shared memory as bf16, sweep 3 = (e_i / sum - onehot) * grad_scale
 // written to global memory.
 // ---------------------------------------------------------------------------------------------
-constexpr int kCeThreads = 256;
+constexpr int kCeThreads = 512;
 __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   v = is_max ? warp_max(v) : warp_sum(v);
